@@ -1,0 +1,148 @@
+/*
+ * vgaudio_b200.h — C ABI of libvgaudio_b200.so: the B200 (sm_100a) batch codec engine that replaces the
+ * per-channel CPU hot path of Thealexbarney/VGAudio.
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/src/VGAudio/).  The reference-side binding (C# P/Invoke) a maintainer
+ * would add is shown in INTEGRATION.md and bindings/csharp/.
+ *
+ * Conventions
+ *   - cdecl, plain pointers and sizes only; all buffers are caller-owned, nothing allocated here crosses the
+ *     boundary except through vgb_host_alloc/vgb_host_free.
+ *   - Every function returns an int32 status: VGB_OK (0) or a negative VGB_E_* code; vgb_last_error() gives the
+ *     thread-local message.  The C# shim maps the codes back to the exception types the reference throws.
+ *   - "host" entry points take HOST pointers and perform the H2D/D2H copies themselves (pinned memory is used
+ *     directly, pageable memory is staged).  "_dev" entry points take DEVICE pointers that are already resident
+ *     in HBM and a cudaStream_t (passed as void*); they never touch host memory and never synchronise.
+ *   - There is NO CPU fallback: without a usable CUDA device every codec call fails with VGB_E_CUDA.
+ *   - Thread-safe: concurrent calls from different host threads are serialised per device workspace.
+ */
+#ifndef VGAUDIO_B200_H
+#define VGAUDIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGB_OK        0
+#define VGB_E_ARG    -1  /* ArgumentException / ArgumentOutOfRangeException on the C# side */
+#define VGB_E_DATA   -2  /* InvalidDataException */
+#define VGB_E_STATE  -3  /* InvalidOperationException */
+#define VGB_E_CUDA   -4  /* no device / CUDA runtime failure */
+#define VGB_E_NCCL   -5  /* reserved for the multi-GPU gather */
+#define VGB_E_NOMEM  -6  /* OutOfMemoryException */
+
+#define VGB_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Library / device control
+ * ------------------------------------------------------------------------------------------------------- */
+int32_t vgb_abi_version(void);
+/* Bind the calling process to CUDA device `device` (>= 0) and create the workspace.  Idempotent. */
+int32_t vgb_init(int32_t device, uint32_t flags);
+int32_t vgb_shutdown(void);
+const char *vgb_last_error(void);
+/* Pinned host memory, so the host entry points can DMA straight from/to the caller's buffers. */
+int32_t vgb_host_alloc(void **ptr_out, uint64_t bytes);
+int32_t vgb_host_free(void *ptr);
+/* Number of kernel launches issued by this library since vgb_init (bench.py reports it as gpu_launches). */
+int64_t vgb_kernel_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GcAdpcmMath (Codecs/GcAdpcm/GcAdpcmMath.cs:7-47) — so the caller can size its output arrays first
+ * ------------------------------------------------------------------------------------------------------- */
+int32_t vgb_gcadpcm_sample_count_to_byte_count(int32_t sample_count);   /* :46 */
+int32_t vgb_gcadpcm_byte_count_to_sample_count(int32_t byte_count);     /* :47 */
+int32_t vgb_gcadpcm_sample_count_to_nibble_count(int32_t sample_count); /* :20-27 */
+int32_t vgb_gcadpcm_nibble_count_to_sample_count(int32_t nibble_count); /* :11-18 */
+int32_t vgb_gcadpcm_sample_to_nibble(int32_t sample);                   /* :38-44 */
+int32_t vgb_gcadpcm_nibble_to_sample(int32_t nibble);                   /* :29-36 */
+
+/* Mirror of GcAdpcmParameters : CodecParameters (Codecs/GcAdpcm/GcAdpcmParameters.cs:3-7,
+ * Codecs/CodecParameters.cs:3-17).  sample_count == -1 means "the whole input" exactly as in
+ * GcAdpcmEncoder.Encode (GcAdpcmEncoder.cs:17) / GcAdpcmDecoder.Decode (GcAdpcmDecoder.cs:12). */
+typedef struct vgb_gc_params {
+    int32_t sample_count;
+    int16_t history1;
+    int16_t history2;
+} vgb_gc_params;
+
+/* IProgressReport.ReportAdd (IProgressReport.cs:3-28) — invoked from the calling host thread between device
+ * chunks with the number of frames finished since the last call; the deltas sum to the reference's
+ * SetTotal value (GcAdpcmFormat.cs:62-63). */
+typedef void (*vgb_progress_cb)(void *user, int64_t frames_done_delta);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GC-ADPCM, host buffers.  One call replaces one Parallel.For over channels.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* GcAdpcmCoefficients.CalculateCoefficients (GcAdpcmCoefficients.cs:9-110) for n_channels independent
+ * channels.  pcm[c] points at n_samples[c] int16 samples; coefs_out is [n_channels][16]. */
+int32_t vgb_gcadpcm_coefs_batch(const int16_t *const *pcm, const int32_t *n_samples, int32_t n_channels,
+                                int16_t *coefs_out);
+
+/* GcAdpcmFormat.EncodeFromPcm16's loop body (Formats/GcAdpcm/GcAdpcmFormat.cs:65-68 -> EncodeChannel :129-135
+ * = CalculateCoefficients + GcAdpcmEncoder.Encode, GcAdpcmEncoder.cs:14-46) for every channel at once.
+ *   params      NULL (all defaults) or [n_channels]
+ *   coefs_in    NULL = run the coefficient analysis; else [n_channels][16] (GcAdpcmEncoder.Encode only)
+ *   coefs_out   [n_channels][16], receives the coefficients used (may alias coefs_in)
+ *   adpcm_out   adpcm_out[c] receives SampleCountToByteCount(sample_count) bytes
+ *   cb/user     optional progress callback */
+int32_t vgb_gcadpcm_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
+                                 const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out,
+                                 uint8_t *const *adpcm_out, vgb_progress_cb cb, void *user);
+
+/* GcAdpcmFormat.ToPcm16's loop body (GcAdpcmFormat.cs:45-48 -> GcAdpcmChannel.GetPcmAudio, GcAdpcmChannel.cs:57-60
+ * -> GcAdpcmDecoder.Decode, GcAdpcmDecoder.cs:10-54).  n_bytes[c] is the length of adpcm[c]; params[c].sample_count
+ * == -1 decodes ByteCountToSampleCount(n_bytes[c]) samples.  pcm_out[c] receives sample_count samples. */
+int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                 const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out);
+
+/* GcAdpcmEncoder.DspEncodeFrame (GcAdpcmEncoder.cs:48-94) for n_frames INDEPENDENT frames (the IDspTool /
+ * GcAdpcmAlignment use, Formats/GcAdpcm/GcAdpcmAlignment.cs:57).  pcm_in_out is [n_frames][16]: two history samples
+ * (older first) then 14 samples, rewritten with the reconstruction; sample_count[f] in 0..14 (NULL = 14);
+ * coefs is [n_frames][16]; adpcm_out is [n_frames][8]. */
+int32_t vgb_gcadpcm_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs,
+                                  int32_t n_frames, uint8_t *adpcm_out);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GC-ADPCM, device-resident ("_dev").  Channel c occupies
+ *      d_pcm   + pcm_offset[c]    .. n_samples[c] samples      (pcm_offset in samples, multiple of 8)
+ *      d_adpcm + adpcm_offset[c]  .. byte count of the channel (adpcm_offset in bytes, multiple of 16)
+ * The offset/length tables are HOST arrays (they are tiny and are uploaded on `stream`); both slabs must be
+ * padded so that each channel's region is readable/writable up to the next multiple of 16 bytes.
+ * vgb_gcadpcm_workspace_bytes() tells how much scratch HBM the call needs for the given total frame count.
+ * ------------------------------------------------------------------------------------------------------- */
+uint64_t vgb_gcadpcm_workspace_bytes(int64_t total_frames, int32_t n_channels);
+
+int32_t vgb_gcadpcm_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples,
+                               const vgb_gc_params *params, int32_t n_channels,
+                               const int16_t *d_coefs_in, int16_t *d_coefs_out,
+                               uint8_t *d_adpcm, const int64_t *adpcm_offset,
+                               void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+
+int32_t vgb_gcadpcm_coefs_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples,
+                              int32_t n_channels, int16_t *d_coefs_out,
+                              void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+
+int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offset, const int16_t *d_coefs,
+                               const vgb_gc_params *params /* sample_count must be >= 0 */, int32_t n_channels,
+                               int16_t *d_pcm, const int64_t *pcm_offset,
+                               void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+
+/* Per-kernel device time (ms, CUDA events on the launching stream) of the most recent *_dev or host call on this
+ * thread's workspace: [0] coefficient phase 1, [1] coefficient refinement, [2] encode, [3] decode.  Only filled
+ * when vgb_set_kernel_timing(1) was called; bench.py uses it for the roofline object. */
+int32_t vgb_set_kernel_timing(int32_t enabled);
+int32_t vgb_last_kernel_ms(float *ms_out, int32_t n);
+
+/* Debug/test taps (tests/ only): run coefficient phase 1 and return, per frame, the direct-form pair and the
+ * accept flag the refinement consumes.  Host buffers; dir_out [frames][2] doubles, accepted_out [frames] bytes. */
+int32_t vgb_gcadpcm_debug_records(const int16_t *pcm, int32_t n_samples, double *dir_out, uint8_t *accepted_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGAUDIO_B200_H */

@@ -1,0 +1,119 @@
+"""ctypes wrapper of oracle/libvgoracle.so — TEST INFRASTRUCTURE (see oracle/vgoracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgoracle.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        i32, i64, vp = C.c_int, C.c_int64, C.c_void_p
+        for name in ("vgo_gc_nibble_count_to_sample_count", "vgo_gc_sample_count_to_nibble_count",
+                     "vgo_gc_nibble_to_sample", "vgo_gc_sample_to_nibble", "vgo_gc_sample_count_to_byte_count",
+                     "vgo_gc_byte_count_to_sample_count"):
+            getattr(L, name).argtypes = [i32]
+            getattr(L, name).restype = i32
+        L.vgo_divide_by_round_up.argtypes = [i32, i32]
+        L.vgo_gc_calculate_coefficients.argtypes = [vp, i32, vp]
+        L.vgo_gc_calculate_coefficients.restype = None
+        L.vgo_gc_coef_records.argtypes = [vp, i32, vp, vp, vp]
+        L.vgo_gc_encode.argtypes = [vp, i32, vp, i32, C.c_int16, C.c_int16, vp]
+        L.vgo_gc_encode.restype = None
+        L.vgo_gc_dsp_encode_frame.argtypes = [vp, i32, vp, vp]
+        L.vgo_gc_dsp_encode_frame.restype = None
+        L.vgo_gc_decode.argtypes = [vp, vp, i32, C.c_int16, C.c_int16, vp]
+        L.vgo_gc_decode.restype = None
+        L.vgo_gc_encode_batch.argtypes = [vp, i64, i32, i32, vp, vp, i64, i32]
+        L.vgo_gc_decode_batch.argtypes = [vp, i64, vp, i32, i32, vp, i64, i32]
+        _lib = L
+    return _lib
+
+
+def sample_count_to_byte_count(n: int) -> int:
+    return lib().vgo_gc_sample_count_to_byte_count(n)
+
+
+def calculate_coefficients(pcm) -> np.ndarray:
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    co = np.zeros(16, dtype=np.int16)
+    lib().vgo_gc_calculate_coefficients(pcm.ctypes.data, len(pcm), co.ctypes.data)
+    return co
+
+
+def coef_records(pcm):
+    """(accepted[frames] uint8, records[frames,2], direct[frames,2]) of coefficient phase 1."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    frames = (len(pcm) + 13) // 14
+    rec = np.zeros((frames, 2)); dire = np.zeros((frames, 2)); acc = np.zeros(frames, dtype=np.uint8)
+    lib().vgo_gc_coef_records(pcm.ctypes.data, len(pcm), rec.ctypes.data, dire.ctypes.data, acc.ctypes.data)
+    return acc, rec, dire
+
+
+def encode(pcm, coefs, sample_count: int = -1, history1: int = 0, history2: int = 0) -> np.ndarray:
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    n = len(pcm) if sample_count == -1 else sample_count
+    out = np.zeros(sample_count_to_byte_count(n), dtype=np.uint8)
+    lib().vgo_gc_encode(pcm.ctypes.data, len(pcm), coefs.ctypes.data, sample_count, history1, history2, out.ctypes.data)
+    return out
+
+
+def dsp_encode_frame(pcm_in_out: np.ndarray, sample_count: int, coefs) -> np.ndarray:
+    assert pcm_in_out.dtype == np.int16 and pcm_in_out.flags.c_contiguous and pcm_in_out.size == 16
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    out = np.zeros(8, dtype=np.uint8)
+    lib().vgo_gc_dsp_encode_frame(pcm_in_out.ctypes.data, sample_count, out.ctypes.data, coefs.ctypes.data)
+    return out
+
+
+def decode(adpcm, coefs, sample_count: int, history1: int = 0, history2: int = 0) -> np.ndarray:
+    adpcm = np.ascontiguousarray(adpcm, dtype=np.uint8)
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    out = np.zeros(sample_count, dtype=np.int16)
+    lib().vgo_gc_decode(adpcm.ctypes.data, coefs.ctypes.data, sample_count, history1, history2, out.ctypes.data)
+    return out
+
+
+def encode_batch(pcm2d: np.ndarray, n_threads: int = 0):
+    """Reference Parallel.For path: (coefs[n,16], adpcm[n,bytes], threads_used)."""
+    pcm2d = np.ascontiguousarray(pcm2d, dtype=np.int16)
+    n_ch, n = pcm2d.shape
+    nb = sample_count_to_byte_count(n)
+    coefs = np.zeros((n_ch, 16), dtype=np.int16)
+    out = np.zeros((n_ch, nb), dtype=np.uint8)
+    used = lib().vgo_gc_encode_batch(pcm2d.ctypes.data, n, n_ch, n, coefs.ctypes.data, out.ctypes.data, nb, n_threads)
+    return coefs, out, used
+
+
+def decode_batch(adpcm2d: np.ndarray, coefs: np.ndarray, sample_count: int, n_threads: int = 0):
+    adpcm2d = np.ascontiguousarray(adpcm2d, dtype=np.uint8)
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    n_ch, nb = adpcm2d.shape
+    out = np.zeros((n_ch, sample_count), dtype=np.int16)
+    used = lib().vgo_gc_decode_batch(adpcm2d.ctypes.data, nb, coefs.ctypes.data, n_ch, sample_count, out.ctypes.data,
+                                     sample_count, n_threads)
+    return out, used

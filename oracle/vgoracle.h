@@ -1,0 +1,75 @@
+/*
+ * vgoracle.h — CPU ORACLE for the VGAudio hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C restatement of the reference's (Thealexbarney/VGAudio, C#)
+ * per-channel codec arithmetic.  It exists so the CUDA kernels can be checked
+ * bit-for-bit; it is NOT part of the product.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * Parity status:
+ *   - GcAdpcmMath helpers ........ pinned by the reference's own KAT tables
+ *                                  (src/VGAudio.Tests/Formats/GcAdpcm/GcAdpcmHelpersTests.cs:8-100)
+ *   - GC-ADPCM encode/decode ..... pinned by the reference's round-trip properties
+ *                                  (GcAdpcmFormatTests.cs:87-157 ramps exact; GcAdpcmAlignmentTests.cs:64-108
+ *                                  sine <= 2 LSB and encoder-reconstruction == decoder).
+ *                                  The reference holds NO golden bitstream and cannot be run here
+ *                                  (no .NET toolchain) => encoded BYTES are "parity unpinned".
+ *   - CRI ADX ...................... reference has zero tests => "parity unpinned".
+ *   - CRI HCA tables ............... pinned bit-exact by CriHcaTableTests.cs literals; encoder output unpinned.
+ *
+ * All file:line citations are relative to /root/reference/src/VGAudio/.
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fno-fast-math).
+ */
+#ifndef VGORACLE_H
+#define VGORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- GcAdpcmMath (Codecs/GcAdpcm/GcAdpcmMath.cs:7-47) ---- */
+int vgo_gc_nibble_count_to_sample_count(int nibble_count);
+int vgo_gc_sample_count_to_nibble_count(int sample_count);
+int vgo_gc_nibble_to_sample(int nibble);
+int vgo_gc_sample_to_nibble(int sample);
+int vgo_gc_sample_count_to_byte_count(int sample_count);
+int vgo_gc_byte_count_to_sample_count(int byte_count);
+/* Utilities/Extensions.cs:145 */
+int vgo_divide_by_round_up(int value, int divisor);
+
+/* ---- GcAdpcmCoefficients.CalculateCoefficients (Codecs/GcAdpcm/GcAdpcmCoefficients.cs:9-110) ---- */
+void vgo_gc_calculate_coefficients(const int16_t *source, int length, int16_t coefs_out[16]);
+
+/* Phase-1 only (GcAdpcmCoefficients.cs:40-61): one (accepted, r1, r2) triple per 14-sample frame,
+ * NOT compacted, plus the direct-form vector MatrixFilter (:285-305) derives from it.
+ * rec_out: [frames][2] = record[z,1], record[z,2];  dir_out: [frames][2] = MatrixFilter dst[1], dst[2].
+ * Returns the number of accepted records.  Used to test the GPU phase-1 kernel in isolation. */
+int vgo_gc_coef_records(const int16_t *source, int length, double *rec_out, double *dir_out, uint8_t *accepted_out);
+
+/* ---- GcAdpcmEncoder (Codecs/GcAdpcm/GcAdpcmEncoder.cs) ---- */
+/* Encode :14-46.  sample_count == -1 means pcm_length.  adpcm_out holds SampleCountToByteCount(sample_count) bytes. */
+void vgo_gc_encode(const int16_t *pcm, int pcm_length, const int16_t coefs[16],
+                   int sample_count, int16_t history1, int16_t history2, uint8_t *adpcm_out);
+/* DspEncodeFrame :48-94.  pcm_in_out[0..1] = history (older first), [2..15] = samples; rewritten with the
+ * reconstructed samples. */
+void vgo_gc_dsp_encode_frame(int16_t pcm_in_out[16], int sample_count, uint8_t adpcm_out[8], const int16_t coefs[16]);
+
+/* ---- GcAdpcmDecoder.Decode (Codecs/GcAdpcm/GcAdpcmDecoder.cs:10-54) ---- */
+void vgo_gc_decode(const uint8_t *adpcm, const int16_t coefs[16], int sample_count,
+                   int16_t history1, int16_t history2, int16_t *pcm_out);
+
+/* ---- batch drivers: the reference's Parallel.For over channels (Formats/GcAdpcm/GcAdpcmFormat.cs:58-74,
+ * :42-54, :129-135) restated with a pthread pool (dynamic schedule); n_threads <= 0 means all host cores.  Channel c lives at
+ * pcm + c*pcm_stride (samples) / adpcm + c*adpcm_stride (bytes).  Returns threads used. ---- */
+int vgo_gc_encode_batch(const int16_t *pcm, int64_t pcm_stride, int n_channels, int sample_count,
+                        int16_t *coefs_out /* [n_channels][16] */, uint8_t *adpcm_out, int64_t adpcm_stride,
+                        int n_threads);
+int vgo_gc_decode_batch(const uint8_t *adpcm, int64_t adpcm_stride, const int16_t *coefs, int n_channels,
+                        int sample_count, int16_t *pcm_out, int64_t pcm_stride, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

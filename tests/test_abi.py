@@ -1,0 +1,79 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/vgaudio_b200.h declares, the pure-integer
+size helpers match the reference's KAT tables, and codec calls FAIL LOUDLY (VGB_E_CUDA) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vgaudio_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vgb_[a-z0-9_]+)\s*\(", text)) - {"vgb_progress_cb"})
+
+
+def test_library_exports_every_declared_symbol(vg):
+    from vgaudio_b200 import _native
+
+    raw = C.CDLL(_native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+        assert name in _native.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_native.SIGNATURES) == set(names)
+
+
+def test_abi_version(vg):
+    assert vg.lib.vgb_abi_version() == 1
+
+
+# GcAdpcmHelpersTests.cs:8-100 through the product's helpers (host-side integer math, no device needed)
+@pytest.mark.parametrize("fn,arg,expected", [
+    ("nibble_to_sample", 2, 0), ("nibble_to_sample", 19, 15), ("nibble_to_sample", 100010, 87508),
+    ("sample_to_nibble", 0, 2), ("sample_to_nibble", 14, 18), ("sample_to_nibble", 87508, 100010),
+    ("nibble_count_to_sample_count", 17, 14), ("nibble_count_to_sample_count", 100000, 87500),
+    ("sample_count_to_nibble_count", 1, 3), ("sample_count_to_nibble_count", 87500, 100000),
+    ("sample_count_to_byte_count", 1, 2), ("sample_count_to_byte_count", 15, 10),
+    ("sample_count_to_byte_count", 87500, 50000), ("byte_count_to_sample_count", 8, 14),
+])
+def test_size_helpers(vg, fn, arg, expected):
+    assert getattr(vg.gcadpcm, fn)(arg) == expected
+
+
+def test_argument_errors_do_not_need_a_device(vg):
+    from vgaudio_b200 import _native as N
+
+    lens = np.array([-5], dtype=np.int32)
+    tab = (C.c_void_p * 1)()
+    co = np.zeros(16, dtype=np.int16)
+    assert vg.lib.vgb_gcadpcm_coefs_batch(tab, lens.ctypes.data, 1, co.ctypes.data) == N.VGB_E_ARG
+    assert b"negative" in vg.lib.vgb_last_error()
+    assert vg.lib.vgb_gcadpcm_coefs_batch(tab, lens.ctypes.data, -1, co.ctypes.data) == N.VGB_E_ARG
+    assert vg.lib.vgb_init(-1, 0) == N.VGB_E_ARG
+
+
+def test_no_cpu_fallback_without_gpu(vg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for GPU-less hosts")
+    with pytest.raises(vg.VgbError) as info:
+        vg.gcadpcm.calculate_coefficients(np.zeros(100, dtype=np.int16))
+    assert info.value.code == -4  # VGB_E_CUDA
+    with pytest.raises(vg.VgbError):
+        vg.gcadpcm.decode(np.zeros(8, dtype=np.uint8), np.zeros(16, dtype=np.int16))
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under vgaudio_b200/ may reference oracle/ (the oracle is test infrastructure)."""
+    pkg = os.path.join(ROOT, "vgaudio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyoracle" not in text and "vgoracle" not in text and "libvgoracle" not in text, f

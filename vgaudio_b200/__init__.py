@@ -1,0 +1,9 @@
+"""vgaudio_b200 — B200-native batch engine for VGAudio's per-channel codec hot path.
+
+Host-side mirror of the reference's interface for that path (names follow the reference):
+  codecs.gcadpcm : GcAdpcmMath helpers, GcAdpcmCoefficients, GcAdpcmEncoder, GcAdpcmDecoder, GcAdpcmParameters
+  formats        : Pcm16Format, GcAdpcmChannel, GcAdpcmFormat (.encode_from_pcm16 / .to_pcm16)
+All arithmetic runs in libvgaudio_b200.so (CUDA, sm_100a) through the C ABI in include/vgaudio_b200.h.
+"""
+from ._native import VgbError, lib  # noqa: F401  (fails loudly when the native library is missing)
+from . import gcadpcm, formats  # noqa: F401

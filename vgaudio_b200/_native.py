@@ -1,0 +1,97 @@
+"""ctypes binding of libvgaudio_b200.so (C ABI in include/vgaudio_b200.h).
+
+The library is the product; this module only loads it and declares the signatures.  There is no Python or CPU
+fallback: if the shared object is missing the import fails loudly, and if no CUDA device is usable every codec call
+raises VgbError(VGB_E_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgaudio_b200.so")
+
+VGB_OK, VGB_E_ARG, VGB_E_DATA, VGB_E_STATE, VGB_E_CUDA, VGB_E_NCCL, VGB_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+
+
+class VgbGcParams(C.Structure):
+    """Mirror of GcAdpcmParameters (Codecs/GcAdpcm/GcAdpcmParameters.cs:3-7)."""
+
+    _fields_ = [("sample_count", C.c_int32), ("history1", C.c_int16), ("history2", C.c_int16)]
+
+
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64)
+
+# name -> (restype, argtypes); also the list tests/test_abi.py checks against include/vgaudio_b200.h
+SIGNATURES = {
+    "vgb_abi_version": (C.c_int32, []),
+    "vgb_init": (C.c_int32, [C.c_int32, C.c_uint32]),
+    "vgb_shutdown": (C.c_int32, []),
+    "vgb_last_error": (C.c_char_p, []),
+    "vgb_host_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "vgb_host_free": (C.c_int32, [C.c_void_p]),
+    "vgb_kernel_launch_count": (C.c_int64, []),
+    "vgb_gcadpcm_sample_count_to_byte_count": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_byte_count_to_sample_count": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_sample_count_to_nibble_count": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_nibble_count_to_sample_count": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_sample_to_nibble": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_nibble_to_sample": (C.c_int32, [C.c_int32]),
+    "vgb_gcadpcm_coefs_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_gcadpcm_encode_batch": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "vgb_gcadpcm_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_gcadpcm_encode_frames": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_gcadpcm_workspace_bytes": (C.c_uint64, [C.c_int64, C.c_int32]),
+    "vgb_gcadpcm_encode_dev": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_uint64, C.c_void_p],
+    ),
+    "vgb_gcadpcm_coefs_dev": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p],
+    ),
+    "vgb_gcadpcm_decode_dev": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+         C.c_void_p],
+    ),
+    "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
+    "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "vgb_gcadpcm_debug_records": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+
+class VgbError(RuntimeError):
+    """Raised for a non-zero status.  `.code` is the VGB_E_* value; the C# shim maps the same codes to
+    ArgumentException / InvalidDataException / InvalidOperationException."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"vgaudio_b200 error {code}: {message}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  vgaudio_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    if status != VGB_OK:
+        raise VgbError(status, (lib.vgb_last_error() or b"").decode("utf-8", "replace"))

@@ -1,0 +1,731 @@
+// c_abi.cu — the extern "C" boundary of libvgaudio_b200.so (declared in include/vgaudio_b200.h).
+//
+// Host-side responsibilities only: argument validation with the reference's error behaviour, HBM layout of a
+// batch (channel slabs + tables), H2D/D2H movement, kernel sequencing on one stream, timing taps.
+// No codec arithmetic happens on the CPU here; without a CUDA device every codec entry point fails (VGB_E_CUDA).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vgaudio_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vgb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(e_ == cudaErrorMemoryAllocation ? VGB_E_NOMEM : VGB_E_CUDA, "%s failed: %s", #expr, \
+                        cudaGetErrorString(e_));                                                            \
+    } while (0)
+
+#define VGB_TRY(expr)              \
+    do {                           \
+        int32_t s_ = (expr);       \
+        if (s_ != VGB_OK) return s_; \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t bytes)
+    {
+        if (bytes <= cap && p) return VGB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) bytes = 256;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            p = nullptr;
+            return fail(VGB_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
+        return VGB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int kTimers = 4;  // 0 coef phase 1, 1 coef refine, 2 encode, 3 decode
+
+struct Context {
+    std::mutex mu;
+    bool ready = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf pcm, adpcm, coefs, ws, misc;
+    bool timing = false;
+    cudaEvent_t ev[2 * kTimers] = {};
+    bool ev_used[kTimers] = {};
+    std::atomic<int64_t> launches{0};
+};
+
+Context g_ctx;
+
+int32_t ensure_ready_locked()
+{
+    if (g_ctx.ready) {
+        CUDA_TRY(cudaSetDevice(g_ctx.device));
+        return VGB_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return fail(VGB_E_CUDA, "no CUDA device available (%s): libvgaudio_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (g_ctx.device >= count) return fail(VGB_E_ARG, "device %d out of range (%d devices)", g_ctx.device, count);
+    CUDA_TRY(cudaSetDevice(g_ctx.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    for (auto &ev : g_ctx.ev) CUDA_TRY(cudaEventCreate(&ev));
+    g_ctx.ready = true;
+    return VGB_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void tick(int slot, bool begin, cudaStream_t stream)
+{
+    if (!g_ctx.timing) return;
+    cudaEventRecord(g_ctx.ev[2 * slot + (begin ? 0 : 1)], stream);
+    if (!begin) g_ctx.ev_used[slot] = true;
+}
+
+// ---- batch layout ----------------------------------------------------------------------------------------
+struct GcLayout {
+    int32_t n_channels = 0;
+    std::vector<int64_t> pcm_off, adpcm_off, rec_off;
+    std::vector<int32_t> n_samples, enc_count;
+    std::vector<int16_t> hist;  // [ch][2] = hist1, hist2
+    int64_t pcm_total = 0;      // samples, padded
+    int64_t adpcm_total = 0;    // bytes, padded
+    int64_t rec_total = 0;      // frames, padded to a multiple of 32 per channel
+    int32_t max_frames = 0;     // over analysis and encode lengths
+    int64_t total_frames = 0;   // sum over channels of encode frames (progress total, GcAdpcmFormat.cs:62)
+};
+
+// Workspace carve-up (every region 256-byte aligned).  [0, table_bytes) is the host-built table blob.
+struct GcWorkspace {
+    size_t off_pcm_off, off_adpcm_off, off_rec_off, off_n_samples, off_enc_count, off_hist, off_records, off_mask;
+    size_t table_bytes;
+    size_t total;
+};
+
+GcWorkspace carve(int64_t rec_total_frames, int32_t n_channels)
+{
+    GcWorkspace w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t n = (size_t)(n_channels > 0 ? n_channels : 1);
+    w.off_pcm_off = take(n * 8);
+    w.off_adpcm_off = take(n * 8);
+    w.off_rec_off = take(n * 8);
+    w.off_n_samples = take(n * 4);
+    w.off_enc_count = take(n * 4);
+    w.off_hist = take(n * 4);
+    w.table_bytes = o;
+    w.off_records = take((size_t)rec_total_frames * sizeof(double2));
+    w.off_mask = take((size_t)(rec_total_frames / 32 + 1) * 4);
+    w.total = o;
+    return w;
+}
+
+// upper bound of the padded record slab for a given total frame count (what workspace_bytes promises)
+int64_t padded_rec_bound(int64_t total_frames, int32_t n_channels) { return total_frames + 32ll * n_channels + 32; }
+
+GcChannelTable table_view(void *ws, const GcWorkspace &w, int32_t n_channels)
+{
+    char *b = static_cast<char *>(ws);
+    GcChannelTable t;
+    t.pcm_off = reinterpret_cast<const int64_t *>(b + w.off_pcm_off);
+    t.adpcm_off = reinterpret_cast<const int64_t *>(b + w.off_adpcm_off);
+    t.rec_off = reinterpret_cast<const int64_t *>(b + w.off_rec_off);
+    t.n_samples = reinterpret_cast<const int32_t *>(b + w.off_n_samples);
+    t.enc_count = reinterpret_cast<const int32_t *>(b + w.off_enc_count);
+    t.hist = reinterpret_cast<int16_t *>(b + w.off_hist);
+    t.n_channels = n_channels;
+    return t;
+}
+
+int32_t upload_tables(const GcLayout &lay, const GcWorkspace &w, void *ws, cudaStream_t stream)
+{
+    std::vector<char> blob(w.table_bytes, 0);
+    const size_t n = (size_t)lay.n_channels;
+    if (n) {
+        memcpy(blob.data() + w.off_pcm_off, lay.pcm_off.data(), n * 8);
+        memcpy(blob.data() + w.off_adpcm_off, lay.adpcm_off.data(), n * 8);
+        memcpy(blob.data() + w.off_rec_off, lay.rec_off.data(), n * 8);
+        memcpy(blob.data() + w.off_n_samples, lay.n_samples.data(), n * 4);
+        memcpy(blob.data() + w.off_enc_count, lay.enc_count.data(), n * 4);
+        memcpy(blob.data() + w.off_hist, lay.hist.data(), n * 4);
+    }
+    // pageable source: the runtime stages it before returning, so `blob` may die at scope exit
+    CUDA_TRY(cudaMemcpyAsync(ws, blob.data(), w.table_bytes, cudaMemcpyHostToDevice, stream));
+    return VGB_OK;
+}
+
+// Validates lengths/params and fills everything in `lay` except pcm_off / adpcm_off.
+// `decode`: n_samples is the decoded sample count and enc_count mirrors it.
+int32_t layout_common(GcLayout &lay, const int32_t *n_samples, const vgb_gc_params *params, int32_t n_channels,
+                      bool decode)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative (%d)", n_channels);
+    if (n_channels > 0 && !n_samples) return fail(VGB_E_ARG, "n_samples is NULL");
+    lay.n_channels = n_channels;
+    lay.n_samples.resize(n_channels);
+    lay.enc_count.resize(n_channels);
+    lay.rec_off.resize(n_channels);
+    lay.hist.assign((size_t)n_channels * 2, 0);
+    int64_t rec = 0;
+    for (int c = 0; c < n_channels; c++) {
+        const int32_t n = n_samples[c];
+        if (n < 0) return fail(VGB_E_ARG, "channel %d: negative sample count %d", c, n);
+        int32_t enc = n;
+        if (params) {
+            if (!decode && params[c].sample_count != -1) {
+                enc = params[c].sample_count;
+                // GcAdpcmEncoder.Encode would run Array.Copy past pcm.Length and throw ArgumentException
+                if (enc < 0 || enc > n)
+                    return fail(VGB_E_ARG, "channel %d: sample_count %d outside the %d available samples", c, enc, n);
+            }
+            lay.hist[2 * c] = params[c].history1;
+            lay.hist[2 * c + 1] = params[c].history2;
+        }
+        lay.n_samples[c] = n;
+        lay.enc_count[c] = enc;
+        const int32_t frames = div_round_up(n, kGcFrameSamples);
+        lay.rec_off[c] = rec;
+        rec += align_up((size_t)frames, 32);
+        if (frames > lay.max_frames) lay.max_frames = frames;
+        lay.total_frames += div_round_up(enc, kGcFrameSamples);
+    }
+    lay.rec_total = rec + 32;
+    return VGB_OK;
+}
+
+void layout_pack_offsets(GcLayout &lay)
+{
+    lay.pcm_off.resize(lay.n_channels);
+    lay.adpcm_off.resize(lay.n_channels);
+    int64_t ps = 0, ab = 0;
+    for (int c = 0; c < lay.n_channels; c++) {
+        lay.pcm_off[c] = ps;
+        lay.adpcm_off[c] = ab;
+        ps += (int64_t)align_up((size_t)lay.n_samples[c], 8);
+        ab += (int64_t)align_up((size_t)gc_sample_count_to_byte_count(lay.n_samples[c]), 16);
+    }
+    lay.pcm_total = ps + 8;
+    lay.adpcm_total = ab + 16;
+}
+
+// Kernel sequence of one encode call on `stream` (device pointers only).
+int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *d_coefs_in, int16_t *d_coefs_out,
+                      uint8_t *d_adpcm, void *d_ws, const GcWorkspace &w, cudaStream_t stream, bool do_encode)
+{
+    VGB_TRY(upload_tables(lay, w, d_ws, stream));
+    if (lay.n_channels == 0) return VGB_OK;
+    GcChannelTable tab = table_view(d_ws, w, lay.n_channels);
+    char *b = static_cast<char *>(d_ws);
+    double2 *records = reinterpret_cast<double2 *>(b + w.off_records);
+    uint32_t *mask = reinterpret_cast<uint32_t *>(b + w.off_mask);
+
+    if (!d_coefs_in) {
+        tick(0, true, stream);
+        launch_gc_coef_frames(d_pcm, tab, records, mask, lay.max_frames, 0, INT_MAX, stream);
+        tick(0, false, stream);
+        tick(1, true, stream);
+        launch_gc_coef_refine(tab, records, mask, d_coefs_out, stream);
+        tick(1, false, stream);
+        g_ctx.launches += (lay.max_frames > 0 ? 1 : 0) + 1;
+    } else if (d_coefs_in != d_coefs_out) {
+        CUDA_TRY(cudaMemcpyAsync(d_coefs_out, d_coefs_in, (size_t)lay.n_channels * 32, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (do_encode) {
+        tick(2, true, stream);
+        launch_gc_encode(d_pcm, tab, d_coefs_out, d_adpcm, lay.max_frames, 0, INT_MAX, stream);
+        tick(2, false, stream);
+        g_ctx.launches += lay.max_frames > 0 ? 1 : 0;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return VGB_OK;
+}
+
+int32_t run_gc_decode(const uint8_t *d_adpcm, const GcLayout &lay, const int16_t *d_coefs, int16_t *d_pcm, void *d_ws,
+                      const GcWorkspace &w, cudaStream_t stream)
+{
+    VGB_TRY(upload_tables(lay, w, d_ws, stream));
+    if (lay.n_channels == 0) return VGB_OK;
+    GcChannelTable tab = table_view(d_ws, w, lay.n_channels);
+    tick(3, true, stream);
+    launch_gc_decode(d_adpcm, tab, d_coefs, d_pcm, lay.max_frames, 0, INT_MAX, stream);
+    tick(3, false, stream);
+    g_ctx.launches += lay.max_frames > 0 ? 1 : 0;
+    CUDA_TRY(cudaGetLastError());
+    return VGB_OK;
+}
+
+// If ptr[c] == ptr[0] + c*stride for every c (the caller handed one slab), returns true and the stride in bytes.
+template <typename T>
+bool uniform_stride(T *const *ptr, int32_t n, int64_t &stride_bytes)
+{
+    if (n < 2) { stride_bytes = 0; return true; }
+    const int64_t s = reinterpret_cast<const char *>(ptr[1]) - reinterpret_cast<const char *>(ptr[0]);
+    if (s <= 0) return false;
+    for (int c = 2; c < n; c++)
+        if (reinterpret_cast<const char *>(ptr[c]) - reinterpret_cast<const char *>(ptr[c - 1]) != s) return false;
+    stride_bytes = s;
+    return true;
+}
+
+bool all_equal(const std::vector<int32_t> &v)
+{
+    for (size_t i = 1; i < v.size(); i++)
+        if (v[i] != v[0]) return false;
+    return true;
+}
+
+// Host -> device copy of every channel's bytes: one strided 2D copy when the caller's buffers form a slab,
+// else one copy per channel.
+template <typename T>
+int32_t copy_channels_in(char *d_base, const std::vector<int64_t> &d_off_bytes, T *const *h_ptr,
+                         const std::vector<int64_t> &bytes, cudaStream_t stream)
+{
+    const int32_t n = (int32_t)bytes.size();
+    if (n == 0) return VGB_OK;
+    bool same = true;
+    for (int c = 1; c < n; c++) same = same && bytes[c] == bytes[0];
+    int64_t hstride = 0;
+    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride)) {
+        const int64_t dstride = d_off_bytes[1] - d_off_bytes[0];
+        bool dsame = true;
+        for (int c = 2; c < n; c++) dsame = dsame && (d_off_bytes[c] - d_off_bytes[c - 1] == dstride);
+        if (dsame) {
+            CUDA_TRY(cudaMemcpy2DAsync(d_base + d_off_bytes[0], (size_t)dstride, h_ptr[0], (size_t)hstride,
+                                       (size_t)bytes[0], (size_t)n, cudaMemcpyHostToDevice, stream));
+            return VGB_OK;
+        }
+    }
+    for (int c = 0; c < n; c++)
+        if (bytes[c] > 0)
+            CUDA_TRY(cudaMemcpyAsync(d_base + d_off_bytes[c], h_ptr[c], (size_t)bytes[c], cudaMemcpyHostToDevice, stream));
+    return VGB_OK;
+}
+
+template <typename T>
+int32_t copy_channels_out(T *const *h_ptr, const char *d_base, const std::vector<int64_t> &d_off_bytes,
+                          const std::vector<int64_t> &bytes, cudaStream_t stream)
+{
+    const int32_t n = (int32_t)bytes.size();
+    if (n == 0) return VGB_OK;
+    bool same = true;
+    for (int c = 1; c < n; c++) same = same && bytes[c] == bytes[0];
+    int64_t hstride = 0;
+    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride)) {
+        const int64_t dstride = d_off_bytes[1] - d_off_bytes[0];
+        bool dsame = true;
+        for (int c = 2; c < n; c++) dsame = dsame && (d_off_bytes[c] - d_off_bytes[c - 1] == dstride);
+        if (dsame) {
+            CUDA_TRY(cudaMemcpy2DAsync(h_ptr[0], (size_t)hstride, d_base + d_off_bytes[0], (size_t)dstride,
+                                       (size_t)bytes[0], (size_t)n, cudaMemcpyDeviceToHost, stream));
+            return VGB_OK;
+        }
+    }
+    for (int c = 0; c < n; c++)
+        if (bytes[c] > 0)
+            CUDA_TRY(cudaMemcpyAsync(h_ptr[c], d_base + d_off_bytes[c], (size_t)bytes[c], cudaMemcpyDeviceToHost, stream));
+    return VGB_OK;
+}
+
+int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
+                         const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out, uint8_t *const *adpcm_out,
+                         vgb_progress_cb cb, void *user, bool do_encode)
+{
+    GcLayout lay;
+    VGB_TRY(layout_common(lay, n_samples, params, n_channels, false));
+    if (n_channels == 0) return VGB_OK;
+    if (!pcm) return fail(VGB_E_ARG, "pcm is NULL");
+    if (!coefs_out) return fail(VGB_E_ARG, "coefs_out is NULL");
+    if (do_encode && !adpcm_out) return fail(VGB_E_ARG, "adpcm_out is NULL");
+    for (int c = 0; c < n_channels; c++) {
+        if (!pcm[c] && lay.n_samples[c] > 0) return fail(VGB_E_ARG, "pcm[%d] is NULL", c);
+        if (do_encode && !adpcm_out[c] && lay.enc_count[c] > 0) return fail(VGB_E_ARG, "adpcm_out[%d] is NULL", c);
+    }
+    layout_pack_offsets(lay);
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const GcWorkspace w = carve(lay.rec_total, n_channels);
+    VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
+    VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
+    VGB_TRY(g_ctx.ws.reserve(w.total));
+
+    std::vector<int64_t> off_b(n_channels), len_b(n_channels);
+    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.pcm_off[c] * 2; len_b[c] = (int64_t)lay.n_samples[c] * 2; }
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), off_b, pcm, len_b, st));
+
+    int16_t *d_coefs_out = static_cast<int16_t *>(g_ctx.coefs.p);
+    int16_t *d_coefs_in = nullptr;
+    if (coefs_in) {
+        d_coefs_in = d_coefs_out + (size_t)n_channels * 16;
+        CUDA_TRY(cudaMemcpyAsync(d_coefs_in, coefs_in, (size_t)n_channels * 32, cudaMemcpyHostToDevice, st));
+    }
+    VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), lay, d_coefs_in, d_coefs_out,
+                          static_cast<uint8_t *>(g_ctx.adpcm.p), g_ctx.ws.p, w, st, do_encode));
+    CUDA_TRY(cudaMemcpyAsync(coefs_out, d_coefs_out, (size_t)n_channels * 32, cudaMemcpyDeviceToHost, st));
+    if (do_encode) {
+        for (int c = 0; c < n_channels; c++) {
+            off_b[c] = lay.adpcm_off[c];
+            len_b[c] = gc_sample_count_to_byte_count(lay.enc_count[c]);
+        }
+        VGB_TRY(copy_channels_out(adpcm_out, static_cast<const char *>(g_ctx.adpcm.p), off_b, len_b, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (cb && do_encode) cb(user, lay.total_frames);
+    return VGB_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================================
+// extern "C"
+// ==========================================================================================================
+extern "C" {
+
+int32_t vgb_abi_version(void) { return VGB_ABI_VERSION; }
+
+const char *vgb_last_error(void) { return g_err.c_str(); }
+
+int32_t vgb_init(int32_t device, uint32_t flags)
+{
+    (void)flags;
+    if (device < 0) return fail(VGB_E_ARG, "device must be >= 0 (got %d)", device);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    if (g_ctx.ready && g_ctx.device != device)
+        return fail(VGB_E_STATE, "already bound to device %d; call vgb_shutdown first", g_ctx.device);
+    g_ctx.device = device;
+    return ensure_ready_locked();
+}
+
+int32_t vgb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    if (!g_ctx.ready) return VGB_OK;
+    cudaSetDevice(g_ctx.device);
+    cudaStreamSynchronize(g_ctx.stream);
+    g_ctx.pcm.release();
+    g_ctx.adpcm.release();
+    g_ctx.coefs.release();
+    g_ctx.ws.release();
+    g_ctx.misc.release();
+    for (auto &ev : g_ctx.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+    g_ctx.ready = false;
+    return VGB_OK;
+}
+
+int32_t vgb_host_alloc(void **ptr_out, uint64_t bytes)
+{
+    if (!ptr_out) return fail(VGB_E_ARG, "ptr_out is NULL");
+    {
+        std::lock_guard<std::mutex> lock(g_ctx.mu);
+        VGB_TRY(ensure_ready_locked());
+    }
+    CUDA_TRY(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return VGB_OK;
+}
+
+int32_t vgb_host_free(void *ptr)
+{
+    if (!ptr) return VGB_OK;
+    CUDA_TRY(cudaFreeHost(ptr));
+    return VGB_OK;
+}
+
+int64_t vgb_kernel_launch_count(void) { return g_ctx.launches.load(); }
+
+int32_t vgb_gcadpcm_sample_count_to_byte_count(int32_t n) { return gc_sample_count_to_byte_count(n); }
+int32_t vgb_gcadpcm_byte_count_to_sample_count(int32_t b) { return gc_nibble_count_to_sample_count(b * 2); }
+int32_t vgb_gcadpcm_sample_count_to_nibble_count(int32_t n) { return gc_sample_count_to_nibble_count(n); }
+int32_t vgb_gcadpcm_nibble_count_to_sample_count(int32_t n) { return gc_nibble_count_to_sample_count(n); }
+int32_t vgb_gcadpcm_sample_to_nibble(int32_t s)
+{
+    return kGcFrameNibbles * (s / kGcFrameSamples) + s % kGcFrameSamples + 2;
+}
+int32_t vgb_gcadpcm_nibble_to_sample(int32_t nib)
+{
+    return kGcFrameSamples * (nib / kGcFrameNibbles) + nib % kGcFrameNibbles - 2;
+}
+
+int32_t vgb_gcadpcm_coefs_batch(const int16_t *const *pcm, const int32_t *n_samples, int32_t n_channels,
+                                int16_t *coefs_out)
+{
+    return host_encode_impl(pcm, n_samples, nullptr, nullptr, n_channels, coefs_out, nullptr, nullptr, nullptr, false);
+}
+
+int32_t vgb_gcadpcm_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
+                                 const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out,
+                                 uint8_t *const *adpcm_out, vgb_progress_cb cb, void *user)
+{
+    return host_encode_impl(pcm, n_samples, params, coefs_in, n_channels, coefs_out, adpcm_out, cb, user, true);
+}
+
+int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                 const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative (%d)", n_channels);
+    if (n_channels == 0) return VGB_OK;
+    if (!adpcm || !n_bytes || !coefs || !pcm_out) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<int32_t> counts(n_channels);
+    for (int c = 0; c < n_channels; c++) {
+        if (n_bytes[c] < 0) return fail(VGB_E_ARG, "channel %d: negative byte count", c);
+        int32_t want = (params && params[c].sample_count != -1) ? params[c].sample_count
+                                                                : gc_nibble_count_to_sample_count(n_bytes[c] * 2);
+        if (want < 0) return fail(VGB_E_ARG, "channel %d: negative sample count %d", c, want);
+        // GcAdpcmChannel.cs:33-36: "Audio array length is too short for the specified number of samples."
+        if (n_bytes[c] < gc_sample_count_to_byte_count(want))
+            return fail(VGB_E_ARG, "channel %d: audio array length %d is too short for %d samples", c, n_bytes[c], want);
+        if ((!adpcm[c] || !pcm_out[c]) && want > 0) return fail(VGB_E_ARG, "channel %d: NULL buffer", c);
+        counts[c] = want;
+    }
+    GcLayout lay;
+    VGB_TRY(layout_common(lay, counts.data(), params, n_channels, true));
+    layout_pack_offsets(lay);
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const GcWorkspace w = carve(32, n_channels);
+    VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
+    VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
+    VGB_TRY(g_ctx.ws.reserve(w.total));
+
+    std::vector<int64_t> off_b(n_channels), len_b(n_channels);
+    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.adpcm_off[c]; len_b[c] = gc_sample_count_to_byte_count(counts[c]); }
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), off_b, adpcm, len_b, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.coefs.p, coefs, (size_t)n_channels * 32, cudaMemcpyHostToDevice, st));
+    VGB_TRY(run_gc_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), lay, static_cast<const int16_t *>(g_ctx.coefs.p),
+                          static_cast<int16_t *>(g_ctx.pcm.p), g_ctx.ws.p, w, st));
+    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.pcm_off[c] * 2; len_b[c] = (int64_t)counts[c] * 2; }
+    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), off_b, len_b, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VGB_OK;
+}
+
+int32_t vgb_gcadpcm_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs,
+                                  int32_t n_frames, uint8_t *adpcm_out)
+{
+    if (n_frames < 0) return fail(VGB_E_ARG, "n_frames is negative");
+    if (n_frames == 0) return VGB_OK;
+    if (!pcm_in_out || !coefs || !adpcm_out) return fail(VGB_E_ARG, "NULL argument");
+    if (sample_count)
+        for (int f = 0; f < n_frames; f++)
+            if (sample_count[f] < 0 || sample_count[f] > 14)
+                return fail(VGB_E_ARG, "frame %d: sample_count %d outside 0..14", f, sample_count[f]);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const size_t n = (size_t)n_frames;
+    const size_t o_pcm = 0, o_coef = align_up(n * 32, 256), o_cnt = o_coef + align_up(n * 32, 256),
+                 o_out = o_cnt + align_up(n * 4, 256), total = o_out + align_up(n * 8, 256);
+    VGB_TRY(g_ctx.misc.reserve(total));
+    char *b = static_cast<char *>(g_ctx.misc.p);
+    CUDA_TRY(cudaMemcpyAsync(b + o_pcm, pcm_in_out, n * 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b + o_coef, coefs, n * 32, cudaMemcpyHostToDevice, st));
+    if (sample_count) CUDA_TRY(cudaMemcpyAsync(b + o_cnt, sample_count, n * 4, cudaMemcpyHostToDevice, st));
+    launch_gc_encode_frames(reinterpret_cast<int16_t *>(b + o_pcm),
+                            sample_count ? reinterpret_cast<const int32_t *>(b + o_cnt) : nullptr,
+                            reinterpret_cast<const int16_t *>(b + o_coef), n_frames,
+                            reinterpret_cast<uint8_t *>(b + o_out), st);
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(pcm_in_out, b + o_pcm, n * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(adpcm_out, b + o_out, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VGB_OK;
+}
+
+// ---- device-resident entry points --------------------------------------------------------------------------
+
+uint64_t vgb_gcadpcm_workspace_bytes(int64_t total_frames, int32_t n_channels)
+{
+    if (total_frames < 0 || n_channels < 0) return 0;
+    return carve(padded_rec_bound(total_frames, n_channels), n_channels).total;
+}
+
+static int32_t dev_layout(GcLayout &lay, const int64_t *pcm_offset, const int64_t *adpcm_offset,
+                          const int32_t *n_samples, const vgb_gc_params *params, int32_t n_channels, bool decode,
+                          bool need_adpcm)
+{
+    VGB_TRY(layout_common(lay, n_samples, params, n_channels, decode));
+    if (n_channels == 0) return VGB_OK;
+    if (!pcm_offset) return fail(VGB_E_ARG, "pcm_offset is NULL");
+    if (need_adpcm && !adpcm_offset) return fail(VGB_E_ARG, "adpcm_offset is NULL");
+    lay.pcm_off.assign(pcm_offset, pcm_offset + n_channels);
+    lay.adpcm_off.assign(n_channels, 0);
+    if (adpcm_offset) lay.adpcm_off.assign(adpcm_offset, adpcm_offset + n_channels);
+    for (int c = 0; c < n_channels; c++) {
+        if (lay.pcm_off[c] < 0 || (lay.pcm_off[c] & 7))
+            return fail(VGB_E_ARG, "pcm_offset[%d]=%lld must be a non-negative multiple of 8 samples", c,
+                        (long long)lay.pcm_off[c]);
+        if (lay.adpcm_off[c] < 0 || (lay.adpcm_off[c] & 15))
+            return fail(VGB_E_ARG, "adpcm_offset[%d]=%lld must be a non-negative multiple of 16 bytes", c,
+                        (long long)lay.adpcm_off[c]);
+    }
+    return VGB_OK;
+}
+
+int32_t vgb_gcadpcm_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples,
+                               const vgb_gc_params *params, int32_t n_channels, const int16_t *d_coefs_in,
+                               int16_t *d_coefs_out, uint8_t *d_adpcm, const int64_t *adpcm_offset, void *d_workspace,
+                               uint64_t workspace_bytes, void *cuda_stream)
+{
+    GcLayout lay;
+    VGB_TRY(dev_layout(lay, pcm_offset, adpcm_offset, n_samples, params, n_channels, false, true));
+    if (n_channels == 0) return VGB_OK;
+    if (!d_pcm || !d_coefs_out || !d_adpcm || !d_workspace) return fail(VGB_E_ARG, "NULL device pointer");
+    const GcWorkspace w = carve(lay.rec_total, n_channels);
+    if (w.total > workspace_bytes)
+        return fail(VGB_E_ARG, "workspace too small: need %zu bytes, got %llu", w.total, (unsigned long long)workspace_bytes);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    return run_gc_encode(d_pcm, lay, d_coefs_in, d_coefs_out, d_adpcm, d_workspace, w, static_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int32_t vgb_gcadpcm_coefs_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples,
+                              int32_t n_channels, int16_t *d_coefs_out, void *d_workspace, uint64_t workspace_bytes,
+                              void *cuda_stream)
+{
+    GcLayout lay;
+    VGB_TRY(dev_layout(lay, pcm_offset, nullptr, n_samples, nullptr, n_channels, false, false));
+    if (n_channels == 0) return VGB_OK;
+    if (!d_pcm || !d_coefs_out || !d_workspace) return fail(VGB_E_ARG, "NULL device pointer");
+    const GcWorkspace w = carve(lay.rec_total, n_channels);
+    if (w.total > workspace_bytes)
+        return fail(VGB_E_ARG, "workspace too small: need %zu bytes, got %llu", w.total, (unsigned long long)workspace_bytes);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    return run_gc_encode(d_pcm, lay, nullptr, d_coefs_out, nullptr, d_workspace, w, static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offset, const int16_t *d_coefs,
+                               const vgb_gc_params *params, int32_t n_channels, int16_t *d_pcm,
+                               const int64_t *pcm_offset, void *d_workspace, uint64_t workspace_bytes, void *cuda_stream)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
+    if (n_channels == 0) return VGB_OK;
+    if (!params) return fail(VGB_E_ARG, "params is NULL (sample counts are required)");
+    std::vector<int32_t> counts(n_channels);
+    for (int c = 0; c < n_channels; c++) {
+        if (params[c].sample_count < 0) return fail(VGB_E_ARG, "channel %d: sample_count must be >= 0", c);
+        counts[c] = params[c].sample_count;
+    }
+    GcLayout lay;
+    VGB_TRY(dev_layout(lay, pcm_offset, adpcm_offset, counts.data(), params, n_channels, true, true));
+    if (!d_pcm || !d_coefs || !d_adpcm || !d_workspace) return fail(VGB_E_ARG, "NULL device pointer");
+    const GcWorkspace w = carve(32, n_channels);
+    if (w.total > workspace_bytes)
+        return fail(VGB_E_ARG, "workspace too small: need %zu bytes, got %llu", w.total, (unsigned long long)workspace_bytes);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    return run_gc_decode(d_adpcm, lay, d_coefs, d_pcm, d_workspace, w, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int32_t vgb_set_kernel_timing(int32_t enabled)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    g_ctx.timing = enabled != 0;
+    for (auto &u : g_ctx.ev_used) u = false;
+    return VGB_OK;
+}
+
+int32_t vgb_last_kernel_ms(float *ms_out, int32_t n)
+{
+    if (!ms_out || n < 0) return fail(VGB_E_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    for (int i = 0; i < n; i++) ms_out[i] = 0.0f;
+    if (!g_ctx.ready) return VGB_OK;
+    for (int i = 0; i < n && i < kTimers; i++) {
+        if (!g_ctx.ev_used[i]) continue;
+        CUDA_TRY(cudaEventSynchronize(g_ctx.ev[2 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[i], g_ctx.ev[2 * i], g_ctx.ev[2 * i + 1]));
+        g_ctx.ev_used[i] = false;
+    }
+    return VGB_OK;
+}
+
+int32_t vgb_gcadpcm_debug_records(const int16_t *pcm, int32_t n_samples, double *dir_out, uint8_t *accepted_out)
+{
+    if (n_samples < 0 || (!pcm && n_samples > 0) || !dir_out || !accepted_out) return fail(VGB_E_ARG, "bad arguments");
+    GcLayout lay;
+    VGB_TRY(layout_common(lay, &n_samples, nullptr, 1, false));
+    layout_pack_offsets(lay);
+    const int frames = div_round_up(n_samples, kGcFrameSamples);
+    if (frames == 0) return VGB_OK;
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const GcWorkspace w = carve(lay.rec_total, 1);
+    VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
+    VGB_TRY(g_ctx.ws.reserve(w.total));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.pcm.p, pcm, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st));
+    VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, st));
+    GcChannelTable tab = table_view(g_ctx.ws.p, w, 1);
+    char *b = static_cast<char *>(g_ctx.ws.p);
+    launch_gc_coef_frames(static_cast<const int16_t *>(g_ctx.pcm.p), tab, reinterpret_cast<double2 *>(b + w.off_records),
+                          reinterpret_cast<uint32_t *>(b + w.off_mask), frames, 0, INT_MAX, st);
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> mask((size_t)frames / 32 + 1);
+    CUDA_TRY(cudaMemcpyAsync(dir_out, b + w.off_records, (size_t)frames * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(mask.data(), b + w.off_mask, mask.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int f = 0; f < frames; f++) accepted_out[f] = (mask[f >> 5] >> (f & 31)) & 1u;
+    return VGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (internal to libvgaudio_b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vgb {
+
+// gc_coefs.cu — GcAdpcmCoefficients.CalculateCoefficients (Codecs/GcAdpcm/GcAdpcmCoefficients.cs:9-110)
+void launch_gc_coef_frames(const int16_t *pcm, const GcChannelTable &tab, double2 *records, uint32_t *mask,
+                           int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
+void launch_gc_coef_refine(const GcChannelTable &tab, const double2 *records, const uint32_t *mask,
+                           int16_t *coefs_out, cudaStream_t stream);
+
+// gc_encode.cu — GcAdpcmEncoder.Encode / DspEncodeFrame / DspEncodeCoef (Codecs/GcAdpcm/GcAdpcmEncoder.cs:14-171)
+void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16_t *coefs, uint8_t *adpcm,
+                      int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
+void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs, int n_frames,
+                             uint8_t *adpcm_out, cudaStream_t stream);
+
+// gc_decode.cu — GcAdpcmDecoder.Decode (Codecs/GcAdpcm/GcAdpcmDecoder.cs:10-54)
+void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, int16_t *pcm,
+                      int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
+
+}  // namespace vgb
