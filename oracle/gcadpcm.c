@@ -437,8 +437,15 @@ static void try_predictor(const int16_t pcm[16], int n, int16_t c0, int16_t c1, 
             t->error += miss * miss;
         }
 
+        /* DEVIATION (termination guard): with hostile coefficient sets the pass at scalePower 12 can still
+         * overflow by more than 248; the reference then bumps 13 -> 11 (:166-168), re-enters the loop, repeats the
+         * identical pass at 12 and NEVER terminates (found by fuzzing this restatement).  Coefficients produced by
+         * CalculateCoefficients cannot reach it (|diff| < 2^29 there).  Oracle and CUDA kernel both treat a pass
+         * at scalePower 12 as final, which changes nothing for any input on which the reference halts. */
+        const int pass_power = sp;
         for (int32_t x = over + 8; x > 256; x >>= 1)
             if (++sp >= 12) sp = 11;
+        if (pass_power >= 12) { sp = 12; break; }
     } while (sp < 12 && over > 1);
 
     t->scale_power = sp;

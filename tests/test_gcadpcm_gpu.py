@@ -39,9 +39,14 @@ def test_edge_lengths_coefs_encode_decode(vg, oracle, n):
         assert np.array_equal(coefs[c], o_co), (n, c)
         o_ad = oracle.encode(pcm, o_co)
         assert adpcm[c].tobytes() == o_ad.tobytes(), (n, c)
-    dec = vg.gcadpcm.decode_batch(adpcm, coefs)
+    dec = vg.gcadpcm.decode_batch(adpcm, coefs, [vg.gcadpcm.GcAdpcmParameters(n)] * len(chans))
     for c, pcm in enumerate(chans):
         assert np.array_equal(dec[c], oracle.decode(adpcm[c], coefs[c], n)), (n, c)
+    # default sample count = ByteCountToSampleCount(len) (GcAdpcmDecoder.cs:12)
+    dflt = vg.gcadpcm.decode_batch(adpcm, coefs)
+    for c in range(len(chans)):
+        m = vg.gcadpcm.byte_count_to_sample_count(len(adpcm[c]))
+        assert np.array_equal(dflt[c], oracle.decode(adpcm[c], coefs[c], m)), (n, c)
 
 
 def test_every_residue_mod_14_and_mod_32(vg, oracle):
@@ -60,7 +65,7 @@ def test_batch_matches_oracle_seeded_set(vg, oracle):
     o_coefs, o_adpcm, _ = oracle.encode_batch(pcm)
     assert np.array_equal(coefs, o_coefs)
     assert np.array_equal(np.stack(adpcm), o_adpcm)
-    dec = vg.gcadpcm.decode_batch(np.stack(adpcm), coefs)
+    dec = vg.gcadpcm.decode_batch(np.stack(adpcm), coefs, [vg.gcadpcm.GcAdpcmParameters(48000)] * 48)
     o_dec, _ = oracle.decode_batch(o_adpcm, o_coefs, 48000)
     assert np.array_equal(np.stack(dec), o_dec)
 
@@ -82,12 +87,12 @@ def test_reference_test_properties_on_gpu(vg):
     for start in (0, 50, 200, 100):
         pcm = synth.reference_ramp(start, 112)
         coefs = vg.gcadpcm.calculate_coefficients(pcm)
-        dec = vg.gcadpcm.decode(vg.gcadpcm.encode(pcm, coefs), coefs)
+        dec = vg.gcadpcm.decode(vg.gcadpcm.encode(pcm, coefs), coefs, vg.gcadpcm.GcAdpcmParameters(112))
         assert [int(dec[49]), int(dec[48]), int(dec[99]), int(dec[98])] == [50 + start, 49 + start, 100 + start, 99 + start]
     n = 100 * 56 + 112
     pcm = synth.reference_sine(n, 1, 56)
     coefs = vg.gcadpcm.calculate_coefficients(pcm)
-    dec = vg.gcadpcm.decode(vg.gcadpcm.encode(pcm, coefs), coefs)
+    dec = vg.gcadpcm.decode(vg.gcadpcm.encode(pcm, coefs), coefs, vg.gcadpcm.GcAdpcmParameters(n))
     assert np.abs(dec[56: n - 14].astype(np.int32) - pcm[56: n - 14]).max() <= 2
 
 
@@ -112,7 +117,7 @@ def test_extreme_coefficients_wrap_like_int32(vg, oracle):
         got = vg.gcadpcm.encode(pcm, coefs)
         want = oracle.encode(pcm, coefs)
         assert got.tobytes() == want.tobytes(), trial
-        dec = vg.gcadpcm.decode(got, coefs)
+        dec = vg.gcadpcm.decode(got, coefs, vg.gcadpcm.GcAdpcmParameters(len(pcm)))
         assert np.array_equal(dec, oracle.decode(want, coefs, len(pcm)))
 
 

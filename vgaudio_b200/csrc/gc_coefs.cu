@@ -230,29 +230,31 @@ __device__ __forceinline__ int16_t gc_quantise_coef(double v)
 
 constexpr int kRefineWarps = 4;
 
+// One block of 32 records staged for the ordered accumulation: the two direct-form components in separate planes
+// so an accumulator lane streams its own component with 16-byte loads, and the bucket of every record.
 struct __align__(16) RefineSlot {
-    double2 v[32];   // direct-form pair of the 32 records in flight
-    int32_t idx[32]; // bucket of each record, -1 = not a record
+    double comp[2][32];
+    int32_t idx[32];  // bucket of each record, -1 = not a record
 };
 
 __global__ void __launch_bounds__(kRefineWarps * 32)
 gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, const uint32_t *__restrict__ accept_mask,
                       int16_t *__restrict__ coefs_out)
 {
-    __shared__ RefineSlot slots[kRefineWarps];
+    __shared__ RefineSlot slots[kRefineWarps][2];
     __shared__ double cent[kRefineWarps][8][3];  // centroids (1, c1, c2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = blockIdx.x * kRefineWarps + warp;
     if (ch >= tab.n_channels) return;  // whole warp leaves together
 
-    RefineSlot &slot = slots[warp];
     double (*best)[3] = cent[warp];
     const int n_frames = div_round_up(tab.n_samples[ch], kGcFrameSamples);
+    const int n_blocks = (n_frames + 31) >> 5;
     const double2 *rec = records + tab.rec_off[ch];
     const uint32_t *mask = accept_mask + (tab.rec_off[ch] >> 5);
 
-    const int my_bucket = lane >> 1, my_comp = lane & 1;  // accumulator lanes 0..15
+    const int my_bucket = lane >> 1, my_comp = lane & 1;  // accumulator lanes 0..15 (lanes 16..31 match nothing)
 
     // pass 0 is the plain ordered mean (:63-76, every record in bucket 0); passes 1..6 are FilterRecords rounds.
     int count = 1;
@@ -269,50 +271,79 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
         }
         // per-centroid constants of ContrastVectors (:338-340), kept in registers by every lane
         Centroid c[8];
-        if (pass > 0) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i < count) {
-                    double a0 = best[i][0], a1 = best[i][1], a2 = best[i][2];
-                    c[i].e0 = (a0 * a0) + (a1 * a1) + (a2 * a2);
-                    c[i].e1 = (a0 * a1) + (a1 * a2);
-                    c[i].e2 = a0 * a2;
-                }
+        for (int i = 0; i < 8; i++) {
+            c[i].e0 = c[i].e1 = c[i].e2 = 0.0;
+            if (pass > 0 && i < count) {
+                double a0 = best[i][0], a1 = best[i][1], a2 = best[i][2];
+                c[i].e0 = (a0 * a0) + (a1 * a1) + (a2 * a2);
+                c[i].e1 = (a0 * a1) + (a1 * a2);
+                c[i].e2 = a0 * a2;
             }
         }
 
-        double acc = 0.0;
-        int hits = 0;
-        for (int base = 0; base < n_frames; base += 32) {
-            const int f = base + lane;
-            const uint32_t bits = mask[base >> 5];
+        // classify block b (nearest centroid, parallel over the 32 records) and stage it in slot[b & 1]
+        auto stage = [&](int b, double2 r, uint32_t bits) {
+            const int f = b * 32 + lane;
             const bool ok = (f < n_frames) && ((bits >> lane) & 1u);
-            double2 r = make_double2(-0.0, -0.0);
-            if (ok) r = rec[f];
+            if (!ok) r = make_double2(-0.0, -0.0);  // x + (-0.0) == x for every x: a non-record adds nothing
             int pick = ok ? 0 : -1;
             if (pass > 0 && ok) {
-                // ContrastVectors (:335-342) with val = r.x and (-rec1*val - rec2) = r.y
+                // ContrastVectors (:335-342); its `val` is r.x and (-rec1*val - rec2) is r.y
                 const double ta = 2.0 * r.x, tb = 2.0 * r.y;
                 double least = 1.0e30;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (i < count) {
-                        double d = c[i].e0 + (ta * c[i].e1) + (tb * c[i].e2);
+                        const double d = c[i].e0 + (ta * c[i].e1) + (tb * c[i].e2);
                         if (d < least) { least = d; pick = i; }
                     }
                 }
             }
-            slot.v[lane] = r;
-            slot.idx[lane] = pick;
-            __syncwarp();
-            // ordered accumulation (:382-386 / :67-72): lane (bucket, comp) walks the 32 records in order
-            const double *vals = reinterpret_cast<const double *>(slot.v);
+            RefineSlot &sl = slots[warp][b & 1];
+            sl.comp[0][lane] = r.x;
+            sl.comp[1][lane] = r.y;
+            sl.idx[lane] = pick;
+        };
+        auto fetch = [&](int b, double2 &r, uint32_t &bits) {
+            r = make_double2(0.0, 0.0);
+            bits = 0;
+            if (b < n_blocks) {
+                bits = mask[b];
+                const int f = b * 32 + lane;
+                if (f < n_frames) r = rec[f];
+            }
+        };
+
+        double acc = 0.0;
+        int hits = 0;
+        double2 r_next;
+        uint32_t bits_next;
+        fetch(0, r_next, bits_next);
+        if (n_blocks > 0) stage(0, r_next, bits_next);
+        fetch(1, r_next, bits_next);
+        __syncwarp();
+
+        for (int b = 0; b < n_blocks; b++) {
+            // (1) classify and stage the NEXT block (independent of the chain below), prefetch the one after
+            if (b + 1 < n_blocks) stage(b + 1, r_next, bits_next);
+            fetch(b + 2, r_next, bits_next);
+
+            // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) walks the 32 records in
+            // order; unconditional vector loads, then a pure DADD chain (8 cycles per record)
+            const RefineSlot &sl = slots[warp][b & 1];
+            const int4 *idx4 = reinterpret_cast<const int4 *>(sl.idx);
+            const double2 *val2 = reinterpret_cast<const double2 *>(sl.comp[my_comp]);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const bool mine = slot.idx[j] == my_bucket;
-                const double add = mine ? vals[2 * j + my_comp] : -0.0;  // x + (-0.0) == x for every x
-                acc += add;
-                hits += mine ? 1 : 0;
+            for (int g = 0; g < 8; g++) {
+                const int4 id = idx4[g];
+                const double2 va = val2[2 * g], vb = val2[2 * g + 1];
+                const bool m0 = id.x == my_bucket, m1 = id.y == my_bucket, m2 = id.z == my_bucket, m3 = id.w == my_bucket;
+                acc += m0 ? va.x : -0.0;
+                acc += m1 ? va.y : -0.0;
+                acc += m2 ? vb.x : -0.0;
+                acc += m3 ? vb.y : -0.0;
+                hits += (int)m0 + (int)m1 + (int)m2 + (int)m3;
             }
             __syncwarp();
         }

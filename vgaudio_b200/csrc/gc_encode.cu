@@ -10,12 +10,25 @@
 // parallel and, for each, 4 consecutive scale powers are evaluated speculatively (every attempt is a pure function
 // of (samples, history, coefs, scalePower), so the do/while chain can be replayed over finished attempts; if the
 // chain would leave the 4-wide window or take the rare overflow "bump" (:166-168) the warp falls back to the
-// literal loop).  The argmin over predictors (strict <, first wins, :66-76) is two REDUX.MIN on an exact integer
-// key; the winner's two newest reconstructed samples are broadcast with one REDUX.OR.  PCM is staged through
+// literal loop).  The argmin over predictors (strict <, first wins, :66-76) is one REDUX.MIN on an exact integer
+// key; the winner's two newest reconstructed samples are broadcast with one REDUX.MAX.  PCM is staged through
 // shared memory 16 frames at a time with coalesced 16-byte loads (prefetched one chunk ahead), ADPCM bytes are
 // staged and written back 128 bytes at a time.
 //
-// The kernel is latency bound (a 14-step integer recurrence per frame), not HBM bound: see DESIGN.md §gc_encode.
+// The kernel is latency bound: the time of a channel is (frames) x (length of the dependent instruction chain of
+// one frame), so everything here is about shortening that chain:
+//   * the quantiser's int->float32->float64->int cast chain (:142-144) is replaced by an exactly equivalent
+//     integer expression (proved by enumeration, tools/quantiser_check.c): 6 dependent ALU ops per sample instead
+//     of 5 conversion-unit/fp64 ops (~55 cycles);
+//   * both clamps run as one VIADDMNMX.RELU each by carrying the samples with a +32768 bias and the nibbles with
+//     a +8 bias (the biases fold into the multiply-add constants);
+//   * the ">> 11" of the reconstruction is taken off the chain: (guess + q*2^K + 1024) >> 11 ==
+//     q*2^(K-11) + ((guess + 1024) >> 11) because K >= 11;
+//   * the residual pass against raw neighbours (:107-115) is software-pipelined one frame ahead for the 12 samples
+//     that do not depend on the reconstructed history.
+// The fast expression is exact while |diff| < 2^24 (float32 holds the difference exactly); every lane checks that
+// and otherwise the warp re-runs the frame through the general exact path (wrapping int32 arithmetic + the
+// float32-rounding-aware integer quantiser).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,6 +38,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kEncChunkFrames = 16;                                   // frames staged per chunk
 constexpr int kEncChunkSamples = kEncChunkFrames * kGcFrameSamples;   // 224 samples = 448 B = 28 x 16 B
 constexpr int kEncWarps = 2;                                          // channels per CTA
+constexpr uint32_t kErrSat = (1u << 27) - 1;                          // single-REDUX argmin while err < 2^27 - 1
 
 template <bool kGeneral>
 struct GcTrial {
@@ -35,24 +49,32 @@ struct GcTrial {
     int32_t recon[kGeneral ? 14 : 1];  // full reconstruction, only for the independent-frames entry point
 };
 
-// The reference's cast chain (:142-144): int -> float32, divide by the power-of-two scale in float32 (exact, so a
-// multiply by 2^-K gives the same float), widen, add/subtract the float32 literal 0.4999999f widened, truncate.
-__device__ __forceinline__ int32_t gc_quantise(int32_t diff, float inv_scale)
+// ---------------------------------------------------------------------------------------------------------
+// The reference's quantiser cast chain (:142-144)
+//     (int)((double)((float)diff / scale) +/- 0.4999999f)
+// as integer arithmetic.  scale = 2^shift (11 <= shift <= 23).  (float)diff rounds |diff| to 24 significant bits
+// (nearest-even); the division is exact; adding 0.4999999f (= 0.5 - 3*2^-25) in double is exact and the truncation
+// then rounds half toward zero.  With a = |diff| this is  m = (a + 2^(shift-1) - 1 - hs) >> shift  where
+// hs = 0 if a < 2^24, else half a float32 ulp of a = 2^(floor(log2 a) - 24).  Enumerated against the literal
+// chain for every shift in tools/quantiser_check.c.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t gc_quantise_exact(int32_t diff, int shift)
 {
-    const float ratio = __fmul_rn(__int2float_rn(diff), inv_scale);
-    const double wide = (double)ratio;
-    const double half = (double)0.4999999f;
-    return diff > 0 ? __double2int_rz(__dadd_rn(wide, half)) : __double2int_rz(__dsub_rn(wide, half));
+    const uint32_t a = diff < 0 ? (0u - (uint32_t)diff) : (uint32_t)diff;
+    const uint32_t top = a >> 24;
+    const uint32_t hs = top ? (0x80000000u >> __clz(top)) : 0u;  // largest power of two <= top
+    const uint32_t m = (a + (1u << (shift - 1)) - 1u - hs) >> shift;
+    return diff < 0 ? -(int32_t)m : (int32_t)m;
 }
 
-// One pass of the do/while body (:129-164) at a fixed scalePower.
+// One pass of the do/while body (:129-164) at a fixed scalePower — general exact form (any coefficients, any
+// history; int32 wrap-around like the reference, A.7).
 template <bool kGeneral>
-__device__ __forceinline__ void gc_attempt(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0, int32_t c1,
-                                           int sp, GcTrial<kGeneral> &t)
+__device__ __noinline__ void gc_attempt_exact(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0,
+                                              int32_t c1, int sp, GcTrial<kGeneral> &t)
 {
     const int shift = sp + 11;
-    const int32_t scale = (int32_t)(1u << shift);                    // (1 << scalePower) * 2048
-    const float inv_scale = __int_as_float((127 - shift) << 23);     // 2^-shift
+    const int32_t scale = (int32_t)(1u << shift);  // (1 << scalePower) * 2048
     int32_t r1 = h1, r2 = h2, over = 0;
     uint64_t err = 0;
     uint32_t w0 = 0, w1 = 0;
@@ -62,7 +84,7 @@ __device__ __forceinline__ void gc_attempt(const int32_t (&x)[14], int n, int32_
         const int32_t want = x[s] * 2048;
         const int32_t guess = wadd(wmul(r2, c1), wmul(r1, c0));
         const int32_t diff = wsub(want, guess);
-        const int32_t raw = gc_quantise(diff, inv_scale);
+        const int32_t raw = gc_quantise_exact(diff, shift);
         const int32_t q = clamp4(raw);
         over = max(over, abs(raw - q));
         const int32_t out = clamp16(wadd(wadd(guess, wmul(q, scale)), 1024) >> 11);
@@ -77,7 +99,80 @@ __device__ __forceinline__ void gc_attempt(const int32_t (&x)[14], int n, int32_
     t.w0 = w0; t.w1 = w1; t.r1 = r1; t.r2 = r2; t.over = over; t.err = err;
 }
 
+// a*b + c as ONE multiply-add the compiler may not re-associate (it would otherwise canonicalise the integer sums
+// and put two IMADs plus an add back on the dependent chain).  Wrapping arithmetic, like the reference.
+__device__ __forceinline__ int32_t imad(int32_t a, int32_t b, int32_t c)
+{
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// a >> k (arithmetic) the compiler may not commute with a later select.
+__device__ __forceinline__ int32_t sar(int32_t a, int k)
+{
+    int32_t d;
+    asm("shr.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(k));
+    return d;
+}
+
+// The same pass, shortest dependent chain.  Valid (and bit-identical) when every |diff| <= 2^24 - 1; returns false
+// otherwise and the caller redoes the frame with gc_attempt_exact.  Samples are carried biased by +32768 and nibbles
+// by +8 so that each clamp is a single VIADDMNMX.RELU.  Dependent chain per sample (from the previous biased
+// sample p1 to the next): IMAD -> SHF|ISETP -> SEL -> VIADDMNMX.RELU -> IMAD -> VIADDMNMX.RELU.
+__device__ __forceinline__ bool gc_attempt_fast(const int32_t (&x)[14], int32_t h1, int32_t h2, int32_t c0, int32_t c1,
+                                                int sp, GcTrial<false> &t)
+{
+    const int shift = sp + 11;
+    const int32_t half = (int32_t)(1u << (shift - 1));
+    const int32_t mul = (int32_t)(1u << sp);                    // 2^(shift-11)
+    const int32_t nc0 = -c0, nc1 = -c1;
+    // diff + half = want - c0*r1 - c1*r2 + half with r = p - 32768:
+    const int32_t base_t = wadd(wmul(32768, wadd(c0, c1)), half);
+    // (guess + 1024 - 8*2^shift) = c0*r1 + c1*r2 + 1024 - 8*2^shift:
+    const int32_t base_w = wsub(wsub(1024, (int32_t)(8u << shift)), wmul(32768, wadd(c0, c1)));
+    const uint32_t flag_add = (uint32_t)((1 << 24) - 1 - half);
+    int32_t p1 = h1 + 32768, p2 = h2 + 32768;
+    uint32_t flag = 0;
+    int32_t rmin = 0, rmax = 0;
+    uint64_t err = 0;
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int s = 0; s < 14; s++) {
+        // terms that only need the sample before last (p2): off the critical chain
+        const int32_t an = imad(p2, nc1, wadd(x[s] * 2048, base_t));   // tn = an - c0*p1
+        const int32_t gn = imad(p2, c1, base_w);                       // guess' = gn + c0*p1
+        // critical chain starts here (p1 is the newest reconstructed sample)
+        const int32_t tn = imad(p1, nc0, an);        // diff + half                (diff <= 0 rounding)
+        const int32_t tp = imad(p1, nc0, an - 1);    // diff + half - 1            (diff > 0 rounding)
+        const int32_t wfull = imad(p1, c0, gn);      // guess + 1024 - 8*2^shift
+        const int32_t rn = sar(tn, shift), rp = sar(tp, shift);  // both shifts BEFORE the select: one op less
+        const int32_t raw = tn > half ? rp : rn;     // round half toward zero
+        flag = __viaddmax_u32((uint32_t)tn, flag_add, flag);          // max of (diff + 2^24 - 1) as unsigned
+        const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);           // clamp4(raw) + 8
+        rmin = min(rmin, raw);
+        rmax = max(rmax, raw);
+        // (guess + (qb-8)*2^shift + 1024) >> 11: the multiple of 2^11 leaves the shift
+        const int32_t o = imad(qb, mul, wfull >> 11);
+        const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);      // clamp16(o) + 32768
+        const uint32_t miss = (uint32_t)(x[s] + 32768 - ob);
+        err += (uint64_t)(miss * miss);
+        const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
+        if (byte < 4) w0 += (uint32_t)qb << bit; else w1 += (uint32_t)qb << bit;  // disjoint fields: add == or
+        p2 = p1;
+        p1 = ob;
+    }
+    t.w0 = w0 ^ 0x88888800u;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8); byte 0 is the header
+    t.w1 = w1 ^ 0x88888888u;
+    t.r1 = p1 - 32768;
+    t.r2 = p2 - 32768;
+    t.over = max(max(rmax - 7, -8 - rmin), 0);
+    t.err = err;
+    return flag <= (uint32_t)((1 << 25) - 2);
+}
+
 // The literal do/while of DspEncodeCoef (:127-170), used when the speculative window does not cover the chain.
+// A pass at scalePower 12 is final: see the termination note in oracle/gcadpcm.c (the reference does not halt there).
 template <bool kGeneral>
 __device__ __noinline__ void gc_try_predictor_literal(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0,
                                                       int32_t c1, int sp_first, GcTrial<kGeneral> &t, int &sp_out)
@@ -85,9 +180,11 @@ __device__ __noinline__ void gc_try_predictor_literal(const int32_t (&x)[14], in
     int sp = sp_first - 1;
     do {
         sp++;
-        gc_attempt<kGeneral>(x, n, h1, h2, c0, c1, sp, t);
+        gc_attempt_exact<kGeneral>(x, n, h1, h2, c0, c1, sp, t);
+        const int pass_power = sp;
         for (int v = t.over + 8; v > 256; v >>= 1)
             if (++sp >= 12) sp = 11;
+        if (pass_power >= 12) { sp = 12; break; }
     } while (sp < 12 && t.over > 1);
     sp_out = sp;
 }
@@ -102,60 +199,81 @@ __device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, in
     return ((uint32_t)abs(diff) << 5) | ((uint32_t)(15 - s) << 1) | (diff < 0 ? 1u : 0u);
 }
 
-// DspEncodeFrame (:48-94) for one frame, executed by a full warp.  On return exactly one lane has is_winner set;
-// its trial `t` / sp_final / predictor (lane >> 2) describe the chosen encoding.
-template <bool kGeneral>
-__device__ __forceinline__ void gc_frame_search(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0,
-                                                int32_t c1, int lane, bool &is_winner, GcTrial<kGeneral> &t,
+// Keys of samples 2..13 of a frame: they only involve raw samples, so they are computed one frame ahead.
+__device__ __forceinline__ uint32_t gc_peak_key_rest(const int32_t (&x)[14], int32_t c0, int32_t c1)
+{
+    uint32_t key = 0;
+#pragma unroll
+    for (int s = 2; s < 14; s++) key = max(key, gc_peak_key(x[s - 2], x[s - 1], x[s], c0, c1, s));
+    return key;
+}
+
+// First value scalePower takes inside the do/while (:118-129), from the max-residual key.  Closed form of
+//   n = 0; while (n <= 12 && (peak > 7 || peak < -8)) { peak /= 2; n++; }   ("/" truncates toward zero)
+// positive peak: smallest n with peak < 8*2^n; negative peak -a: smallest n with a < 9*2^n (a <= 32768 so n <= 12).
+__device__ __forceinline__ int gc_first_scale_power(uint32_t key)
+{
+    const uint32_t a = key >> 5;
+    const int bits = 32 - __clz(a);  // 0 for a == 0
+    int n = max(bits - 3, 0);
+    if ((key & 1u) && n > 0 && (a >> (n - 1)) == 8u) n -= 1;  // negative: a in [8*2^(n-1), 9*2^(n-1)) needs one less
+    return n <= 1 ? 0 : n - 1;
+}
+
+// DspEncodeFrame (:48-94) for one frame of a channel, executed by a full warp: fast path.
+// key_rest = gc_peak_key_rest(x) computed earlier.  On return exactly one lane has is_winner set.
+__device__ __forceinline__ void gc_frame_search(const int32_t (&x)[14], uint32_t key_rest, int32_t h1, int32_t h2,
+                                                int32_t c0, int32_t c1, int lane, bool &is_winner, GcTrial<false> &t,
                                                 int &sp_final)
 {
     const int cand = lane & 3;
-
-    uint32_t key = 0;
-#pragma unroll
-    for (int s = 0; s < 14; s++) {
-        if (kGeneral && s >= n) break;
-        const int32_t older = s == 0 ? h2 : (s == 1 ? h1 : x[s >= 2 ? s - 2 : 0]);
-        const int32_t newer = s == 0 ? h1 : x[s >= 1 ? s - 1 : 0];
-        key = max(key, gc_peak_key(older, newer, x[s], c0, c1, s));
-    }
-    int32_t peak = (int32_t)(key >> 5);
-    if (key & 1u) peak = -peak;
-
-    // first scale guess (:118-124)
-    int halvings = 0;
-    while (halvings <= 12 && (peak > 7 || peak < -8)) {
-        peak /= 2;
-        halvings++;
-    }
-    const int sp_first = halvings <= 1 ? 0 : halvings - 1;  // value of scalePower in the first do/while pass
-
+    uint32_t key = max(key_rest, max(gc_peak_key(h2, h1, x[0], c0, c1, 0), gc_peak_key(h1, x[0], x[1], c0, c1, 1)));
+    const int sp_first = gc_first_scale_power(key);
     const int sp = sp_first + cand;
     const bool valid = sp <= 12;
-    gc_attempt<kGeneral>(x, n, h1, h2, c0, c1, valid ? sp : 12, t);
 
-    const bool terminal = valid && (t.over <= 1 || sp >= 12);  // the while condition (:170) fails here
-    const bool bump = valid && t.over > 248;                   // the overflow bump loop (:166-168) would run
-    const uint32_t term_bits = __ballot_sync(kFull, terminal);
-    const uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
-    const bool slow = __any_sync(kFull, bump || group == 0u);
+    const bool exact = gc_attempt_fast(x, h1, h2, c0, c1, valid ? sp : 12, t);
+    bool terminal = valid && (t.over <= 1 || sp >= 12);           // the while condition (:170) fails here
+    bool bump = valid && sp < 12 && t.over > 248;                 // the overflow bump loop (:166-168) would run
+    uint32_t term_bits = __ballot_sync(kFull, terminal);
+    uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
+    bool slow = __any_sync(kFull, bump || group == 0u || (valid && !exact));
 
     sp_final = sp;
     bool pred_winner;
     if (!slow) {
         pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;  // first candidate that ends the chain
     } else {
-        pred_winner = cand == 0;
-        if (pred_winner) gc_try_predictor_literal<kGeneral>(x, n, h1, h2, c0, c1, sp_first, t, sp_final);
+        // redo the speculative attempts with the general exact arithmetic, then replay / fall back as before
+        gc_attempt_exact<false>(x, 14, h1, h2, c0, c1, valid ? sp : 12, t);
+        terminal = valid && (t.over <= 1 || sp >= 12);
+        bump = valid && sp < 12 && t.over > 248;
+        term_bits = __ballot_sync(kFull, terminal);
+        group = (term_bits >> (lane & ~3)) & 0xFu;
+        if (!__any_sync(kFull, bump || group == 0u)) {
+            pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;
+        } else {
+            pred_winner = cand == 0;
+            if (pred_winner) gc_try_predictor_literal<false>(x, 14, h1, h2, c0, c1, sp_first, t, sp_final);
+        }
     }
 
-    // argmin of TotalDistance over the predictors, first minimum wins (:66-76): key = err * 8 + predictor
-    const uint64_t full_key = pred_winner ? ((t.err << 3) | (uint64_t)(lane >> 2)) : ~0ull;
-    const uint32_t hi = (uint32_t)(full_key >> 8);
-    const uint32_t min_hi = __reduce_min_sync(kFull, hi);
-    const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFu) : 0xFFFFFFFFu;
-    const uint32_t min_lo = __reduce_min_sync(kFull, lo);
-    is_winner = pred_winner && hi == min_hi && lo == min_lo;
+    // argmin of TotalDistance over the predictors, first minimum wins (:66-76).  lane = predictor*4 + candidate is
+    // monotone in the predictor, so min over (err, lane) picks the first minimal predictor.
+    const uint32_t e_sat = t.err < (uint64_t)kErrSat ? (uint32_t)t.err : kErrSat;
+    const uint32_t key32 = pred_winner ? ((e_sat << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
+    const uint32_t best = __reduce_min_sync(kFull, key32);
+    if ((best >> 5) < kErrSat) {
+        is_winner = key32 == best;
+    } else {
+        // errors too large for the 27-bit key: exact two-stage reduction on the full 64-bit value
+        const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
+        const uint32_t hi = (uint32_t)(full_key >> 16);
+        const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+        const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
+        const uint32_t min_lo = __reduce_min_sync(kFull, lo);
+        is_winner = pred_winner && hi == min_hi && lo == min_lo;
+    }
 }
 
 // grid: one warp per channel; encodes frames [frame_begin, frame_end) of every channel, carrying the history
@@ -164,7 +282,8 @@ __global__ void __launch_bounds__(kEncWarps * 32)
 gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
                  uint8_t *__restrict__ adpcm, int frame_begin, int frame_end)
 {
-    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][kEncChunkSamples];
+    // one extra zero frame behind each staging buffer so the one-frame-ahead residual pass may read past the chunk
+    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][kEncChunkSamples + 16];
     __shared__ __align__(16) uint8_t out_buf[kEncWarps][kEncChunkFrames * kGcFrameBytes];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,7 +303,8 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     const int32_t c1 = coefs[(int64_t)ch * 16 + 2 * pred + 1];
     int32_t h1 = tab.hist[2 * ch], h2 = tab.hist[2 * ch + 1];
 
-    // 16-byte vector `lane` of a chunk, zero beyond the encoded sample count (GcAdpcmEncoder.cs:32-34)
+    // 16-byte vector `lane` of a chunk (lanes 0..27 data, lanes 28..29 the zero tail), zero beyond the encoded
+    // sample count (GcAdpcmEncoder.cs:32-34)
     auto load_vec = [&](int chunk_frame) -> uint4 {
         uint4 q = make_uint4(0, 0, 0, 0);
         const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + lane * 8;
@@ -203,11 +323,23 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         }
         return q;
     };
+    auto read_frame = [&](int b, int i, int32_t (&x)[14]) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&in_buf[warp][b][i * kGcFrameSamples]);
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t u = w[j];  // same address in every lane: shared-memory broadcast
+            x[2 * j] = (int32_t)(int16_t)(u & 0xFFFFu);
+            x[2 * j + 1] = (int32_t)(int16_t)(u >> 16);
+        }
+    };
 
     int buf = 0;
     {
         const uint4 first = load_vec(frame_begin);
-        if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][0])[lane] = first;
+        if (lane < kEncChunkSamples / 8 + 2) {
+            reinterpret_cast<uint4 *>(in_buf[warp][0])[lane] = first;
+            reinterpret_cast<uint4 *>(in_buf[warp][1])[lane] = make_uint4(0, 0, 0, 0);
+        }
         __syncwarp();
     }
 
@@ -215,29 +347,34 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         const uint4 next = load_vec(cf + kEncChunkFrames);  // prefetch; consumed after this chunk
         const int frames_here = min(kEncChunkFrames, f_hi - cf);
 
+        int32_t x[14];
+        read_frame(buf, 0, x);
+        uint32_t key_rest = gc_peak_key_rest(x, c0, c1);
+
         for (int i = 0; i < frames_here; i++) {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(&in_buf[warp][buf][i * kGcFrameSamples]);
-            int32_t x[14];
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                const uint32_t u = w[j];  // same address in every lane: shared-memory broadcast
-                x[2 * j] = (int32_t)(int16_t)(u & 0xFFFFu);
-                x[2 * j + 1] = (int32_t)(int16_t)(u >> 16);
-            }
+            // next frame's samples and residual keys, independent of this frame's search (software pipelining)
+            int32_t xn[14];
+            read_frame(buf, i + 1, xn);  // i + 1 == 16 reads the zero tail; unused then
+            const uint32_t key_rest_next = gc_peak_key_rest(xn, c0, c1);
 
             bool is_winner;
             int sp_final;
             GcTrial<false> t;
-            gc_frame_search<false>(x, 14, h1, h2, c0, c1, lane, is_winner, t, sp_final);
+            gc_frame_search(x, key_rest, h1, h2, c0, c1, lane, is_winner, t, sp_final);
 
             if (is_winner) {
                 const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));  // CombineNibbles (:83)
                 *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(t.w0 | head, t.w1);
             }
-            const uint32_t packed = __reduce_or_sync(
-                kFull, is_winner ? (((uint32_t)t.r1 & 0xFFFFu) | ((uint32_t)t.r2 << 16)) : 0u);
-            h1 = (int32_t)(int16_t)(packed & 0xFFFFu);  // pcmBuffer[1] = pcmBuffer[15] (:41)
-            h2 = (int32_t)(int16_t)(packed >> 16);      // pcmBuffer[0] = pcmBuffer[14] (:40)
+            // pcmBuffer[0] = pcmBuffer[14]; pcmBuffer[1] = pcmBuffer[15] (:40-41): the winner's two newest samples
+            const uint32_t packed = __reduce_max_sync(
+                kFull, is_winner ? ((((uint32_t)t.r1 + 32768u) & 0xFFFFu) | (((uint32_t)t.r2 + 32768u) << 16)) : 0u);
+            h1 = (int32_t)(packed & 0xFFFFu) - 32768;
+            h2 = (int32_t)(packed >> 16) - 32768;
+
+#pragma unroll
+            for (int j = 0; j < 14; j++) x[j] = xn[j];
+            key_rest = key_rest_next;
         }
         __syncwarp();
 
@@ -265,7 +402,8 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     }
 }
 
-// DspEncodeFrame for independent frames: one warp per frame (IDspTool.DspEncodeFrame / GcAdpcmAlignment use).
+// DspEncodeFrame for independent frames with any sample count 0..14: one warp per frame, general exact path
+// (IDspTool.DspEncodeFrame / GcAdpcmAlignment use; not a throughput path).
 __global__ void __launch_bounds__(128)
 gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restrict__ sample_count,
                         const int16_t *__restrict__ coefs, int n_frames, uint8_t *__restrict__ adpcm_out)
@@ -279,13 +417,31 @@ gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restr
 #pragma unroll
     for (int j = 0; j < 14; j++) x[j] = io[2 + j];
     const int32_t h2 = io[0], h1 = io[1];
-    const int pred = lane >> 2;
+    const int pred = lane >> 2, cand = lane & 3;
     const int32_t c0 = coefs[(int64_t)f * 16 + 2 * pred], c1 = coefs[(int64_t)f * 16 + 2 * pred + 1];
 
-    bool is_winner;
-    int sp_final;
+    // residual pass (:107-115) over the first n samples
+    uint32_t key = 0;
+#pragma unroll
+    for (int s = 0; s < 14; s++) {
+        if (s >= n) break;
+        const int32_t older = s == 0 ? h2 : (s == 1 ? h1 : x[s >= 2 ? s - 2 : 0]);
+        const int32_t newer = s == 0 ? h1 : x[s >= 1 ? s - 1 : 0];
+        key = max(key, gc_peak_key(older, newer, x[s], c0, c1, s));
+    }
+    const int sp_first = gc_first_scale_power(key);
+
+    // one lane per predictor runs the literal loop; the other three lanes idle
     GcTrial<true> t;
-    gc_frame_search<true>(x, n, h1, h2, c0, c1, lane, is_winner, t, sp_final);
+    int sp_final = 0;
+    const bool pred_winner = cand == 0;
+    if (pred_winner) gc_try_predictor_literal<true>(x, n, h1, h2, c0, c1, sp_first, t, sp_final);
+    const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
+    const uint32_t hi = (uint32_t)(full_key >> 16);
+    const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+    const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
+    const uint32_t min_lo = __reduce_min_sync(kFull, lo);
+    const bool is_winner = pred_winner && hi == min_hi && lo == min_lo;
     __syncwarp();  // every lane has read io[] before the winner rewrites it
     if (is_winner) {
         const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));
