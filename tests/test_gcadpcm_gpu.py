@@ -183,3 +183,32 @@ def test_large_batch_property_round_trip(vg):
     err = dec.astype(np.int64) - pcm
     # the bursts are full-scale noise (unpredictable); outside them the codec tracks closely
     assert np.median(np.abs(err)) < 200
+
+
+def test_loud_signals_exercise_float32_rounding_regime(vg, oracle):
+    """Residuals above 2^24/2048 = 8192 make (float)distance inexact in the reference's quantiser
+    (GcAdpcmEncoder.cs:142-144); the integer fast path must still agree bit for bit (gc_attempt_fast exit test)."""
+    rng = np.random.default_rng(2024)
+    n = 14 * 1500
+    chans = []
+    for i in range(24):
+        kind = i % 4
+        if kind == 0:
+            x = rng.integers(-32768, 32768, n)                       # white, full scale
+        elif kind == 1:
+            x = 30000 * np.sign(np.sin(np.arange(n) * rng.uniform(0.2, 3.0))) + rng.integers(-2000, 2000, n)
+        elif kind == 2:
+            x = 32000 * np.sin(np.arange(n) * rng.uniform(2.0, 3.1)) + rng.normal(0, 500, n)  # near Nyquist
+        else:
+            x = np.cumsum(rng.integers(-9000, 9001, n)) % 65536 - 32768                      # sawtooth-like wraps
+        chans.append(np.clip(x, -32768, 32767).astype(np.int16))
+    pcm = np.stack(chans)
+    coefs, adpcm = vg.gcadpcm.encode_batch(pcm)
+    o_coefs, o_adpcm, _ = oracle.encode_batch(pcm)
+    assert np.array_equal(coefs, o_coefs)
+    assert np.array_equal(np.stack(adpcm), o_adpcm)
+    # same signals against arbitrary (not analysed) coefficient sets of natural magnitude
+    rand_coefs = rng.integers(-6000, 6001, (24, 16)).astype(np.int16)
+    _, adpcm2 = vg.gcadpcm.encode_batch(pcm, coefs=rand_coefs)
+    for c in range(24):
+        assert adpcm2[c].tobytes() == oracle.encode(pcm[c], rand_coefs[c]).tobytes(), c

@@ -317,35 +317,46 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
 
         double acc = 0.0;
         int hits = 0;
-        double2 r_next;
-        uint32_t bits_next;
-        fetch(0, r_next, bits_next);
-        if (n_blocks > 0) stage(0, r_next, bits_next);
-        fetch(1, r_next, bits_next);
+        // Records stream from HBM once per pass (1.6 MB per channel, no reuse), so the loads are issued kDepth
+        // blocks (~4 x 300 cycles) ahead of their use to cover DRAM latency; ring indices are compile-time.
+        constexpr int kDepth = 4;
+        double2 ring_r[kDepth];
+        uint32_t ring_bits[kDepth];
+#pragma unroll
+        for (int k = 0; k < kDepth; k++) fetch(k, ring_r[k], ring_bits[k]);
+        if (n_blocks > 0) stage(0, ring_r[0], ring_bits[0]);
+        fetch(kDepth, ring_r[0], ring_bits[0]);
         __syncwarp();
 
-        for (int b = 0; b < n_blocks; b++) {
-            // (1) classify and stage the NEXT block (independent of the chain below), prefetch the one after
-            if (b + 1 < n_blocks) stage(b + 1, r_next, bits_next);
-            fetch(b + 2, r_next, bits_next);
-
-            // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) walks the 32 records in
-            // order; unconditional vector loads, then a pure DADD chain (8 cycles per record)
-            const RefineSlot &sl = slots[warp][b & 1];
-            const int4 *idx4 = reinterpret_cast<const int4 *>(sl.idx);
-            const double2 *val2 = reinterpret_cast<const double2 *>(sl.comp[my_comp]);
+        for (int b0 = 0; b0 < n_blocks; b0 += kDepth) {
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const int4 id = idx4[g];
-                const double2 va = val2[2 * g], vb = val2[2 * g + 1];
-                const bool m0 = id.x == my_bucket, m1 = id.y == my_bucket, m2 = id.z == my_bucket, m3 = id.w == my_bucket;
-                acc += m0 ? va.x : -0.0;
-                acc += m1 ? va.y : -0.0;
-                acc += m2 ? vb.x : -0.0;
-                acc += m3 ? vb.y : -0.0;
-                hits += (int)m0 + (int)m1 + (int)m2 + (int)m3;
+            for (int k = 0; k < kDepth; k++) {
+                const int b = b0 + k;
+                if (b >= n_blocks) break;
+                // (1) classify and stage the NEXT block (independent of the chain below), refill its ring slot
+                const int slot_next = (k + 1) % kDepth;
+                if (b + 1 < n_blocks) stage(b + 1, ring_r[slot_next], ring_bits[slot_next]);
+                fetch(b + 1 + kDepth, ring_r[slot_next], ring_bits[slot_next]);
+
+                // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) walks the 32 records
+                // in order; unconditional vector loads, then a pure DADD chain (8 cycles per record)
+                const RefineSlot &sl = slots[warp][b & 1];
+                const int4 *idx4 = reinterpret_cast<const int4 *>(sl.idx);
+                const double2 *val2 = reinterpret_cast<const double2 *>(sl.comp[my_comp]);
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const int4 id = idx4[g];
+                    const double2 va = val2[2 * g], vb = val2[2 * g + 1];
+                    const bool m0 = id.x == my_bucket, m1 = id.y == my_bucket, m2 = id.z == my_bucket,
+                               m3 = id.w == my_bucket;
+                    acc += m0 ? va.x : -0.0;
+                    acc += m1 ? va.y : -0.0;
+                    acc += m2 ? vb.x : -0.0;
+                    acc += m3 ? vb.y : -0.0;
+                    hits += (int)m0 + (int)m1 + (int)m2 + (int)m3;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         // divide (:73-74 / :388-391) and rebuild the centroids (:76 / :393-394)

@@ -26,9 +26,10 @@
 //     q*2^(K-11) + ((guess + 1024) >> 11) because K >= 11;
 //   * the residual pass against raw neighbours (:107-115) is software-pipelined one frame ahead for the 12 samples
 //     that do not depend on the reconstructed history.
-// The fast expression is exact while |diff| < 2^24 (float32 holds the difference exactly); every lane checks that
-// and otherwise the warp re-runs the frame through the general exact path (wrapping int32 arithmetic + the
-// float32-rounding-aware integer quantiser).
+// The fast expression is exact while |diff| < 2^24 (float32 holds the difference exactly) and, beyond that, whenever
+// the float32 rounding provably cannot move the result (gc_attempt_fast's exit test); the few lanes that fail the
+// test recompute their pass with the general exact path (wrapping int32 arithmetic + the float32-rounding-aware
+// integer quantiser).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -38,7 +39,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kEncChunkFrames = 16;                                   // frames staged per chunk
 constexpr int kEncChunkSamples = kEncChunkFrames * kGcFrameSamples;   // 224 samples = 448 B = 28 x 16 B
 constexpr int kEncWarps = 2;                                          // channels per CTA
-constexpr uint32_t kErrSat = (1u << 27) - 1;                          // single-REDUX argmin while err < 2^27 - 1
+constexpr uint32_t kErrSat = (1u << 27) - 2;                          // single-REDUX argmin while err < 2^27 - 2
 
 template <bool kGeneral>
 struct GcTrial {
@@ -68,9 +69,10 @@ __device__ __forceinline__ int32_t gc_quantise_exact(int32_t diff, int shift)
 }
 
 // One pass of the do/while body (:129-164) at a fixed scalePower — general exact form (any coefficients, any
-// history; int32 wrap-around like the reference, A.7).
+// history; int32 wrap-around like the reference, A.7).  Out of line and fed from memory (the frame's 14 samples
+// at `frame`, shared or local) so the hot loop neither spills nor grows.
 template <bool kGeneral>
-__device__ __noinline__ void gc_attempt_exact(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0,
+__device__ __noinline__ void gc_attempt_exact(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
                                               int32_t c1, int sp, GcTrial<kGeneral> &t)
 {
     const int shift = sp + 11;
@@ -81,15 +83,16 @@ __device__ __noinline__ void gc_attempt_exact(const int32_t (&x)[14], int n, int
 #pragma unroll
     for (int s = 0; s < 14; s++) {
         if (kGeneral && s >= n) break;
-        const int32_t want = x[s] * 2048;
+        const int32_t xs = frame[s];
+        const int32_t want = xs * 2048;
         const int32_t guess = wadd(wmul(r2, c1), wmul(r1, c0));
         const int32_t diff = wsub(want, guess);
         const int32_t raw = gc_quantise_exact(diff, shift);
         const int32_t q = clamp4(raw);
         over = max(over, abs(raw - q));
         const int32_t out = clamp16(wadd(wadd(guess, wmul(q, scale)), 1024) >> 11);
-        const uint32_t miss = (uint32_t)(x[s] - out);
-        err += (uint64_t)(miss * miss);  // (x - out)^2 < 2^32: the wrapped 32-bit product is the true value
+        const int32_t miss = xs - out;
+        err += (uint64_t)((int64_t)miss * miss);
         const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
         if (byte < 4) w0 |= (uint32_t)(q & 15) << bit; else w1 |= (uint32_t)(q & 15) << bit;
         if (kGeneral) t.recon[s] = out;
@@ -116,10 +119,18 @@ __device__ __forceinline__ int32_t sar(int32_t a, int k)
     return d;
 }
 
-// The same pass, shortest dependent chain.  Valid (and bit-identical) when every |diff| <= 2^24 - 1; returns false
-// otherwise and the caller redoes the frame with gc_attempt_exact.  Samples are carried biased by +32768 and nibbles
-// by +8 so that each clamp is a single VIADDMNMX.RELU.  Dependent chain per sample (from the previous biased
-// sample p1 to the next): IMAD -> SHF|ISETP -> SEL -> VIADDMNMX.RELU -> IMAD -> VIADDMNMX.RELU.
+// The same pass with the shortest dependent chain and the fewest instructions; samples are carried biased by
+// +32768 and nibbles by +8 so that each clamp is a single VIADDMNMX.RELU.  Dependent chain per sample (from the
+// previous biased sample p1 to the next): IMAD -> ISETP -> SHF -> VIADDMNMX.RELU -> IMAD -> VIADDMNMX.RELU.
+//
+// Returns false when the result might differ from the reference, in which case the caller recomputes this lane
+// with gc_attempt_exact.  Exactness argument (tools/quantiser_check.c enumerates the quantiser identity):
+//   * every |diff| < 2^24: float32 holds diff exactly, the pass is bit-identical;
+//   * some |diff| >= 2^24 ("big"): the float32 rounding moves a quantiser threshold by hs <= 128, which changes
+//     `raw` only if (diff + half) lies within 128 of a multiple of 2^shift ("near"), and then by one - invisible
+//     to the clamped nibble when |raw| >= 15, but it could flip the overflow-bump test at 248 (`over >= 240`);
+//   * some |diff| >= 2^29 ("huge", hostile coefficients only): the biased sums could wrap - not handled here.
+// big/huge are detected conservatively from the range of `raw` (which is tracked anyway for maxOverflow).
 __device__ __forceinline__ bool gc_attempt_fast(const int32_t (&x)[14], int32_t h1, int32_t h2, int32_t c0, int32_t c1,
                                                 int sp, GcTrial<false> &t)
 {
@@ -127,36 +138,39 @@ __device__ __forceinline__ bool gc_attempt_fast(const int32_t (&x)[14], int32_t 
     const int32_t half = (int32_t)(1u << (shift - 1));
     const int32_t mul = (int32_t)(1u << sp);                    // 2^(shift-11)
     const int32_t nc0 = -c0, nc1 = -c1;
-    // diff + half = want - c0*r1 - c1*r2 + half with r = p - 32768:
-    const int32_t base_t = wadd(wmul(32768, wadd(c0, c1)), half);
-    // (guess + 1024 - 8*2^shift) = c0*r1 + c1*r2 + 1024 - 8*2^shift:
-    const int32_t base_w = wsub(wsub(1024, (int32_t)(8u << shift)), wmul(32768, wadd(c0, c1)));
-    const uint32_t flag_add = (uint32_t)((1 << 24) - 1 - half);
+    const int32_t bias_c = wmul(32768, wadd(c0, c1));           // undoes the +32768 bias of both history samples
+    const int32_t base_t = wadd(bias_c, half);                  // diff + half = x*2048 + base_t - c0*p1 - c1*p2
+    const int32_t base_s = wsub(wadd(half, 1024), (int32_t)(8u << shift));  // guess + 1024 - 8*2^shift = x*2048 + base_s - (diff + half)
+    const int lsh = 32 - shift;
+    const uint32_t near_c = 128u << lsh;
     int32_t p1 = h1 + 32768, p2 = h2 + 32768;
-    uint32_t flag = 0;
     int32_t rmin = 0, rmax = 0;
+    uint32_t nearmin = 0xFFFFFFFFu;
     uint64_t err = 0;
     uint32_t w0 = 0, w1 = 0;
+    int32_t raw_prev = 0;
 #pragma unroll
     for (int s = 0; s < 14; s++) {
-        // terms that only need the sample before last (p2): off the critical chain
-        const int32_t an = imad(p2, nc1, wadd(x[s] * 2048, base_t));   // tn = an - c0*p1
-        const int32_t gn = imad(p2, c1, base_w);                       // guess' = gn + c0*p1
+        const int32_t wt = imad(x[s], 2048, base_t);
+        const int32_t an = imad(p2, nc1, wt);        // needs only the sample before last: off the chain
         // critical chain starts here (p1 is the newest reconstructed sample)
-        const int32_t tn = imad(p1, nc0, an);        // diff + half                (diff <= 0 rounding)
-        const int32_t tp = imad(p1, nc0, an - 1);    // diff + half - 1            (diff > 0 rounding)
-        const int32_t wfull = imad(p1, c0, gn);      // guess + 1024 - 8*2^shift
-        const int32_t rn = sar(tn, shift), rp = sar(tp, shift);  // both shifts BEFORE the select: one op less
-        const int32_t raw = tn > half ? rp : rn;     // round half toward zero
-        flag = __viaddmax_u32((uint32_t)tn, flag_add, flag);          // max of (diff + 2^24 - 1) as unsigned
+        const int32_t tn = imad(p1, nc0, an);        // diff + half
+        const int32_t tp = tn - 1;
+        const int32_t rn = sar(tn, shift), rp = sar(tp, shift);
+        const int32_t raw = tn > half ? rp : rn;     // round half toward zero: (diff + half - (diff > 0)) >> shift
+        nearmin = __viaddmin_u32((uint32_t)tn << lsh, near_c, nearmin);
         const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);           // clamp4(raw) + 8
-        rmin = min(rmin, raw);
-        rmax = max(rmax, raw);
+        if (s & 1) {                                                  // range of raw, two samples per instruction
+            rmin = __vimin3_s32(rmin, raw_prev, raw);
+            rmax = __vimax3_s32(rmax, raw_prev, raw);
+        }
+        raw_prev = raw;
         // (guess + (qb-8)*2^shift + 1024) >> 11: the multiple of 2^11 leaves the shift
-        const int32_t o = imad(qb, mul, wfull >> 11);
+        const int32_t wsh = wsub(wadd(x[s] * 2048, base_s), tn) >> 11;
+        const int32_t o = imad(qb, mul, wsh);
         const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);      // clamp16(o) + 32768
-        const uint32_t miss = (uint32_t)(x[s] + 32768 - ob);
-        err += (uint64_t)(miss * miss);
+        const int32_t miss = x[s] + 32768 - ob;
+        err += (uint64_t)((int64_t)miss * miss);                      // one IMAD.WIDE accumulate
         const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
         if (byte < 4) w0 += (uint32_t)qb << bit; else w1 += (uint32_t)qb << bit;  // disjoint fields: add == or
         p2 = p1;
@@ -168,19 +182,24 @@ __device__ __forceinline__ bool gc_attempt_fast(const int32_t (&x)[14], int32_t 
     t.r2 = p2 - 32768;
     t.over = max(max(rmax - 7, -8 - rmin), 0);
     t.err = err;
-    return flag <= (uint32_t)((1 << 25) - 2);
+    const int32_t big_thr = 1 << (24 - shift + 0);   // |diff| >= 2^24  =>  raw >= 2^(24-shift) or raw <= -2^(24-shift)
+    const int32_t huge_thr = 1 << (29 - shift);
+    const bool big = rmax >= big_thr || rmin <= -big_thr;
+    const bool huge = rmax >= huge_thr || rmin <= -huge_thr;
+    const bool near = nearmin <= 2u * near_c;
+    return !(huge || (big && (near || t.over >= 240)));
 }
 
 // The literal do/while of DspEncodeCoef (:127-170), used when the speculative window does not cover the chain.
 // A pass at scalePower 12 is final: see the termination note in oracle/gcadpcm.c (the reference does not halt there).
 template <bool kGeneral>
-__device__ __noinline__ void gc_try_predictor_literal(const int32_t (&x)[14], int n, int32_t h1, int32_t h2, int32_t c0,
+__device__ __noinline__ void gc_try_predictor_literal(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
                                                       int32_t c1, int sp_first, GcTrial<kGeneral> &t, int &sp_out)
 {
     int sp = sp_first - 1;
     do {
         sp++;
-        gc_attempt_exact<kGeneral>(x, n, h1, h2, c0, c1, sp, t);
+        gc_attempt_exact<kGeneral>(frame, n, h1, h2, c0, c1, sp, t);
         const int pass_power = sp;
         for (int v = t.over + 8; v > 256; v >>= 1)
             if (++sp >= 12) sp = 11;
@@ -199,12 +218,17 @@ __device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, in
     return ((uint32_t)abs(diff) << 5) | ((uint32_t)(15 - s) << 1) | (diff < 0 ? 1u : 0u);
 }
 
-// Keys of samples 2..13 of a frame: they only involve raw samples, so they are computed one frame ahead.
-__device__ __forceinline__ uint32_t gc_peak_key_rest(const int32_t (&x)[14], int32_t c0, int32_t c1)
+// Keys of samples 2..13 of a frame only involve raw samples, so they are computed one frame ahead, and the four
+// candidate lanes of a predictor share the work: lane `cand` takes samples 2+3*cand .. 4+3*cand, then two
+// shuffle-xor steps inside the group of four combine them.
+__device__ __forceinline__ uint32_t gc_peak_key_rest(const int16_t *frame, int cand, int32_t c0, int32_t c1)
 {
-    uint32_t key = 0;
-#pragma unroll
-    for (int s = 2; s < 14; s++) key = max(key, gc_peak_key(x[s - 2], x[s - 1], x[s], c0, c1, s));
+    const int s0 = 2 + 3 * cand;
+    const int32_t a = frame[s0 - 2], b = frame[s0 - 1], c = frame[s0], d = frame[s0 + 1], e = frame[s0 + 2];
+    uint32_t key = max(gc_peak_key(a, b, c, c0, c1, s0), max(gc_peak_key(b, c, d, c0, c1, s0 + 1),
+                                                           gc_peak_key(c, d, e, c0, c1, s0 + 2)));
+    key = max(key, __shfl_xor_sync(kFull, key, 1));
+    key = max(key, __shfl_xor_sync(kFull, key, 2));
     return key;
 }
 
@@ -220,60 +244,54 @@ __device__ __forceinline__ int gc_first_scale_power(uint32_t key)
     return n <= 1 ? 0 : n - 1;
 }
 
-// DspEncodeFrame (:48-94) for one frame of a channel, executed by a full warp: fast path.
-// key_rest = gc_peak_key_rest(x) computed earlier.  On return exactly one lane has is_winner set.
-__device__ __forceinline__ void gc_frame_search(const int32_t (&x)[14], uint32_t key_rest, int32_t h1, int32_t h2,
-                                                int32_t c0, int32_t c1, int lane, bool &is_winner, GcTrial<false> &t,
-                                                int &sp_final)
+// DspEncodeFrame (:48-94) for one frame of a channel, executed by a full warp.  `frame` = the 14 samples in shared
+// memory (for the rare out-of-line paths), x = the same in registers, key_rest = gc_peak_key_rest of this frame.
+// On return exactly one lane has is_winner set.
+__device__ __forceinline__ void gc_frame_search(const int16_t *frame, const int32_t (&x)[14], uint32_t key_rest,
+                                                int32_t h1, int32_t h2, int32_t c0, int32_t c1, int lane,
+                                                bool &is_winner, GcTrial<false> &t, int &sp_final)
 {
     const int cand = lane & 3;
-    uint32_t key = max(key_rest, max(gc_peak_key(h2, h1, x[0], c0, c1, 0), gc_peak_key(h1, x[0], x[1], c0, c1, 1)));
+    const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(h2, h1, x[0], c0, c1, 0), gc_peak_key(h1, x[0], x[1], c0, c1, 1));
     const int sp_first = gc_first_scale_power(key);
     const int sp = sp_first + cand;
     const bool valid = sp <= 12;
 
     const bool exact = gc_attempt_fast(x, h1, h2, c0, c1, valid ? sp : 12, t);
-    bool terminal = valid && (t.over <= 1 || sp >= 12);           // the while condition (:170) fails here
-    bool bump = valid && sp < 12 && t.over > 248;                 // the overflow bump loop (:166-168) would run
-    uint32_t term_bits = __ballot_sync(kFull, terminal);
-    uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
-    bool slow = __any_sync(kFull, bump || group == 0u || (valid && !exact));
+    // rare (see gc_attempt_fast): only the affected lanes recompute with the general exact arithmetic
+    if (valid && !exact) gc_attempt_exact<false>(frame, 14, h1, h2, c0, c1, sp, t);
+    const bool terminal = valid && (t.over <= 1 || sp >= 12);     // the while condition (:170) fails here
+    const bool bump = valid && sp < 12 && t.over > 248;           // the overflow bump loop (:166-168) would run
+    const uint32_t term_bits = __ballot_sync(kFull, terminal);
+    const uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
+    // a predictor whose four candidates all failed to end the chain leaves the window: every lane sees it in the ballot
+    const uint32_t any4 = term_bits | (term_bits >> 1) | (term_bits >> 2) | (term_bits >> 3);
+    const bool window_miss = (any4 & 0x11111111u) != 0x11111111u;
 
     sp_final = sp;
-    bool pred_winner;
-    if (!slow) {
-        pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;  // first candidate that ends the chain
-    } else {
-        // redo the speculative attempts with the general exact arithmetic, then replay / fall back as before
-        gc_attempt_exact<false>(x, 14, h1, h2, c0, c1, valid ? sp : 12, t);
-        terminal = valid && (t.over <= 1 || sp >= 12);
-        bump = valid && sp < 12 && t.over > 248;
-        term_bits = __ballot_sync(kFull, terminal);
-        group = (term_bits >> (lane & ~3)) & 0xFu;
-        if (!__any_sync(kFull, bump || group == 0u)) {
-            pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;
-        } else {
-            pred_winner = cand == 0;
-            if (pred_winner) gc_try_predictor_literal<false>(x, 14, h1, h2, c0, c1, sp_first, t, sp_final);
-        }
-    }
+    bool pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;  // first candidate that ends the chain
 
     // argmin of TotalDistance over the predictors, first minimum wins (:66-76).  lane = predictor*4 + candidate is
-    // monotone in the predictor, so min over (err, lane) picks the first minimal predictor.
+    // monotone in the predictor, so min over (err, lane) picks the first minimal predictor.  Key 0 is reserved:
+    // a lane that would take the overflow bump posts it so the whole warp learns about it from the same REDUX.
     const uint32_t e_sat = t.err < (uint64_t)kErrSat ? (uint32_t)t.err : kErrSat;
-    const uint32_t key32 = pred_winner ? ((e_sat << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
+    const uint32_t key32 = bump ? 0u : (pred_winner ? (((e_sat + 1u) << 5) | (uint32_t)lane) : 0xFFFFFFFFu);
     const uint32_t best = __reduce_min_sync(kFull, key32);
-    if ((best >> 5) < kErrSat) {
+    if (!window_miss && best != 0u && (best >> 5) <= kErrSat) {
         is_winner = key32 == best;
-    } else {
-        // errors too large for the 27-bit key: exact two-stage reduction on the full 64-bit value
-        const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
-        const uint32_t hi = (uint32_t)(full_key >> 16);
-        const uint32_t min_hi = __reduce_min_sync(kFull, hi);
-        const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
-        const uint32_t min_lo = __reduce_min_sync(kFull, lo);
-        is_winner = pred_winner && hi == min_hi && lo == min_lo;
+        return;
     }
+    // ---- rare: replay the literal loop (bump / window miss) and/or reduce on the full 64-bit error ----
+    if (window_miss || best == 0u) {
+        pred_winner = cand == 0;
+        if (pred_winner) gc_try_predictor_literal<false>(frame, 14, h1, h2, c0, c1, sp_first, t, sp_final);
+    }
+    const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
+    const uint32_t hi = (uint32_t)(full_key >> 16);
+    const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+    const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
+    const uint32_t min_lo = __reduce_min_sync(kFull, lo);
+    is_winner = pred_winner && hi == min_hi && lo == min_lo;
 }
 
 // grid: one warp per channel; encodes frames [frame_begin, frame_end) of every channel, carrying the history
@@ -298,7 +316,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
 
     const int16_t *src = pcm + tab.pcm_off[ch];
     uint8_t *dst = adpcm + tab.adpcm_off[ch];
-    const int pred = lane >> 2;
+    const int pred = lane >> 2, cand = lane & 3;
     const int32_t c0 = coefs[(int64_t)ch * 16 + 2 * pred];
     const int32_t c1 = coefs[(int64_t)ch * 16 + 2 * pred + 1];
     int32_t h1 = tab.hist[2 * ch], h2 = tab.hist[2 * ch + 1];
@@ -323,15 +341,6 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         }
         return q;
     };
-    auto read_frame = [&](int b, int i, int32_t (&x)[14]) {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(&in_buf[warp][b][i * kGcFrameSamples]);
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint32_t u = w[j];  // same address in every lane: shared-memory broadcast
-            x[2 * j] = (int32_t)(int16_t)(u & 0xFFFFu);
-            x[2 * j + 1] = (int32_t)(int16_t)(u >> 16);
-        }
-    };
 
     int buf = 0;
     {
@@ -346,21 +355,24 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     for (int cf = frame_begin; cf < f_hi; cf += kEncChunkFrames) {
         const uint4 next = load_vec(cf + kEncChunkFrames);  // prefetch; consumed after this chunk
         const int frames_here = min(kEncChunkFrames, f_hi - cf);
+        const int16_t *chunk = in_buf[warp][buf];
 
-        int32_t x[14];
-        read_frame(buf, 0, x);
-        uint32_t key_rest = gc_peak_key_rest(x, c0, c1);
+        uint32_t key_rest = gc_peak_key_rest(chunk, cand, c0, c1);
 
         for (int i = 0; i < frames_here; i++) {
-            // next frame's samples and residual keys, independent of this frame's search (software pipelining)
-            int32_t xn[14];
-            read_frame(buf, i + 1, xn);  // i + 1 == 16 reads the zero tail; unused then
-            const uint32_t key_rest_next = gc_peak_key_rest(xn, c0, c1);
+            const int16_t *frame = chunk + i * kGcFrameSamples;
+            int32_t x[14];
+#pragma unroll
+            for (int j = 0; j < 14; j++) x[j] = frame[j];  // same address in every lane: shared-memory broadcast
+
+            // next frame's residual keys, independent of this frame's search (software pipelining);
+            // i + 1 == 16 reads the zero tail behind the chunk and the result is unused then
+            const uint32_t key_rest_next = gc_peak_key_rest(frame + kGcFrameSamples, cand, c0, c1);
 
             bool is_winner;
             int sp_final;
             GcTrial<false> t;
-            gc_frame_search(x, key_rest, h1, h2, c0, c1, lane, is_winner, t, sp_final);
+            gc_frame_search(frame, x, key_rest, h1, h2, c0, c1, lane, is_winner, t, sp_final);
 
             if (is_winner) {
                 const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));  // CombineNibbles (:83)
@@ -371,9 +383,6 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 kFull, is_winner ? ((((uint32_t)t.r1 + 32768u) & 0xFFFFu) | (((uint32_t)t.r2 + 32768u) << 16)) : 0u);
             h1 = (int32_t)(packed & 0xFFFFu) - 32768;
             h2 = (int32_t)(packed >> 16) - 32768;
-
-#pragma unroll
-            for (int j = 0; j < 14; j++) x[j] = xn[j];
             key_rest = key_rest_next;
         }
         __syncwarp();
@@ -408,15 +417,16 @@ __global__ void __launch_bounds__(128)
 gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restrict__ sample_count,
                         const int16_t *__restrict__ coefs, int n_frames, uint8_t *__restrict__ adpcm_out)
 {
-    const int lane = threadIdx.x & 31;
-    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int16_t stage[4][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * (blockDim.x >> 5) + warp;
     if (f >= n_frames) return;
     int16_t *io = pcm_in_out + (int64_t)f * 16;
     const int n = sample_count ? min(max(sample_count[f], 0), 14) : 14;
-    int32_t x[14];
-#pragma unroll
-    for (int j = 0; j < 14; j++) x[j] = io[2 + j];
-    const int32_t h2 = io[0], h1 = io[1];
+    if (lane < 16) stage[warp][lane] = io[lane];
+    __syncwarp();
+    const int16_t *frame = &stage[warp][2];
+    const int32_t h2 = stage[warp][0], h1 = stage[warp][1];
     const int pred = lane >> 2, cand = lane & 3;
     const int32_t c0 = coefs[(int64_t)f * 16 + 2 * pred], c1 = coefs[(int64_t)f * 16 + 2 * pred + 1];
 
@@ -425,24 +435,24 @@ gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restr
 #pragma unroll
     for (int s = 0; s < 14; s++) {
         if (s >= n) break;
-        const int32_t older = s == 0 ? h2 : (s == 1 ? h1 : x[s >= 2 ? s - 2 : 0]);
-        const int32_t newer = s == 0 ? h1 : x[s >= 1 ? s - 1 : 0];
-        key = max(key, gc_peak_key(older, newer, x[s], c0, c1, s));
+        const int32_t older = s == 0 ? h2 : (s == 1 ? h1 : (int32_t)frame[s >= 2 ? s - 2 : 0]);
+        const int32_t newer = s == 0 ? h1 : (int32_t)frame[s >= 1 ? s - 1 : 0];
+        key = max(key, gc_peak_key(older, newer, frame[s], c0, c1, s));
     }
     const int sp_first = gc_first_scale_power(key);
 
     // one lane per predictor runs the literal loop; the other three lanes idle
     GcTrial<true> t;
+    t.err = 0;
     int sp_final = 0;
     const bool pred_winner = cand == 0;
-    if (pred_winner) gc_try_predictor_literal<true>(x, n, h1, h2, c0, c1, sp_first, t, sp_final);
+    if (pred_winner) gc_try_predictor_literal<true>(frame, n, h1, h2, c0, c1, sp_first, t, sp_final);
     const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
     const uint32_t hi = (uint32_t)(full_key >> 16);
     const uint32_t min_hi = __reduce_min_sync(kFull, hi);
     const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
     const uint32_t min_lo = __reduce_min_sync(kFull, lo);
     const bool is_winner = pred_winner && hi == min_hi && lo == min_lo;
-    __syncwarp();  // every lane has read io[] before the winner rewrites it
     if (is_winner) {
         const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));
         uint32_t w[2] = {t.w0 | head, t.w1};
