@@ -39,7 +39,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kEncChunkFrames = 16;                                   // frames staged per chunk
 constexpr int kEncChunkSamples = kEncChunkFrames * kGcFrameSamples;   // 224 samples = 448 B = 28 x 16 B
 constexpr int kEncWarps = 2;                                          // channels per CTA
-constexpr uint32_t kErrSat = (1u << 27) - 2;                          // single-REDUX argmin while err < 2^27 - 2
+constexpr uint32_t kErrSat = (1u << 27) - 1;                          // single-REDUX argmin while err < 2^27 - 1
 
 template <bool kGeneral>
 struct GcTrial {
@@ -69,10 +69,10 @@ __device__ __forceinline__ int32_t gc_quantise_exact(int32_t diff, int shift)
 }
 
 // One pass of the do/while body (:129-164) at a fixed scalePower — general exact form (any coefficients, any
-// history; int32 wrap-around like the reference, A.7).  Out of line and fed from memory (the frame's 14 samples
-// at `frame`, shared or local) so the hot loop neither spills nor grows.
+// history; int32 wrap-around like the reference, A.7).  Fed from memory (the frame's 14 samples at `frame`) and only
+// reached through the out-of-line wrappers below, so the hot loop neither spills nor grows.
 template <bool kGeneral>
-__device__ __noinline__ void gc_attempt_exact(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
+__device__ __forceinline__ void gc_attempt_exact(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
                                               int32_t c1, int sp, GcTrial<kGeneral> &t)
 {
     const int shift = sp + 11;
@@ -119,82 +119,11 @@ __device__ __forceinline__ int32_t sar(int32_t a, int k)
     return d;
 }
 
-// The same pass with the shortest dependent chain and the fewest instructions; samples are carried biased by
-// +32768 and nibbles by +8 so that each clamp is a single VIADDMNMX.RELU.  Dependent chain per sample (from the
-// previous biased sample p1 to the next): IMAD -> ISETP -> SHF -> VIADDMNMX.RELU -> IMAD -> VIADDMNMX.RELU.
-//
-// Returns false when the result might differ from the reference, in which case the caller recomputes this lane
-// with gc_attempt_exact.  Exactness argument (tools/quantiser_check.c enumerates the quantiser identity):
-//   * every |diff| < 2^24: float32 holds diff exactly, the pass is bit-identical;
-//   * some |diff| >= 2^24 ("big"): the float32 rounding moves a quantiser threshold by hs <= 128, which changes
-//     `raw` only if (diff + half) lies within 128 of a multiple of 2^shift ("near"), and then by one - invisible
-//     to the clamped nibble when |raw| >= 15, but it could flip the overflow-bump test at 248 (`over >= 240`);
-//   * some |diff| >= 2^29 ("huge", hostile coefficients only): the biased sums could wrap - not handled here.
-// big/huge are detected conservatively from the range of `raw` (which is tracked anyway for maxOverflow).
-__device__ __forceinline__ bool gc_attempt_fast(const int32_t (&x)[14], int32_t h1, int32_t h2, int32_t c0, int32_t c1,
-                                                int sp, GcTrial<false> &t)
-{
-    const int shift = sp + 11;
-    const int32_t half = (int32_t)(1u << (shift - 1));
-    const int32_t mul = (int32_t)(1u << sp);                    // 2^(shift-11)
-    const int32_t nc0 = -c0, nc1 = -c1;
-    const int32_t bias_c = wmul(32768, wadd(c0, c1));           // undoes the +32768 bias of both history samples
-    const int32_t base_t = wadd(bias_c, half);                  // diff + half = x*2048 + base_t - c0*p1 - c1*p2
-    const int32_t base_s = wsub(wadd(half, 1024), (int32_t)(8u << shift));  // guess + 1024 - 8*2^shift = x*2048 + base_s - (diff + half)
-    const int lsh = 32 - shift;
-    const uint32_t near_c = 128u << lsh;
-    int32_t p1 = h1 + 32768, p2 = h2 + 32768;
-    int32_t rmin = 0, rmax = 0;
-    uint32_t nearmin = 0xFFFFFFFFu;
-    uint64_t err = 0;
-    uint32_t w0 = 0, w1 = 0;
-    int32_t raw_prev = 0;
-#pragma unroll
-    for (int s = 0; s < 14; s++) {
-        const int32_t wt = imad(x[s], 2048, base_t);
-        const int32_t an = imad(p2, nc1, wt);        // needs only the sample before last: off the chain
-        // critical chain starts here (p1 is the newest reconstructed sample)
-        const int32_t tn = imad(p1, nc0, an);        // diff + half
-        const int32_t tp = tn - 1;
-        const int32_t rn = sar(tn, shift), rp = sar(tp, shift);
-        const int32_t raw = tn > half ? rp : rn;     // round half toward zero: (diff + half - (diff > 0)) >> shift
-        nearmin = __viaddmin_u32((uint32_t)tn << lsh, near_c, nearmin);
-        const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);           // clamp4(raw) + 8
-        if (s & 1) {                                                  // range of raw, two samples per instruction
-            rmin = __vimin3_s32(rmin, raw_prev, raw);
-            rmax = __vimax3_s32(rmax, raw_prev, raw);
-        }
-        raw_prev = raw;
-        // (guess + (qb-8)*2^shift + 1024) >> 11: the multiple of 2^11 leaves the shift
-        const int32_t wsh = wsub(wadd(x[s] * 2048, base_s), tn) >> 11;
-        const int32_t o = imad(qb, mul, wsh);
-        const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);      // clamp16(o) + 32768
-        const int32_t miss = x[s] + 32768 - ob;
-        err += (uint64_t)((int64_t)miss * miss);                      // one IMAD.WIDE accumulate
-        const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
-        if (byte < 4) w0 += (uint32_t)qb << bit; else w1 += (uint32_t)qb << bit;  // disjoint fields: add == or
-        p2 = p1;
-        p1 = ob;
-    }
-    t.w0 = w0 ^ 0x88888800u;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8); byte 0 is the header
-    t.w1 = w1 ^ 0x88888888u;
-    t.r1 = p1 - 32768;
-    t.r2 = p2 - 32768;
-    t.over = max(max(rmax - 7, -8 - rmin), 0);
-    t.err = err;
-    const int32_t big_thr = 1 << (24 - shift + 0);   // |diff| >= 2^24  =>  raw >= 2^(24-shift) or raw <= -2^(24-shift)
-    const int32_t huge_thr = 1 << (29 - shift);
-    const bool big = rmax >= big_thr || rmin <= -big_thr;
-    const bool huge = rmax >= huge_thr || rmin <= -huge_thr;
-    const bool near = nearmin <= 2u * near_c;
-    return !(huge || (big && (near || t.over >= 240)));
-}
-
 // The literal do/while of DspEncodeCoef (:127-170), used when the speculative window does not cover the chain.
 // A pass at scalePower 12 is final: see the termination note in oracle/gcadpcm.c (the reference does not halt there).
 template <bool kGeneral>
-__device__ __noinline__ void gc_try_predictor_literal(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
-                                                      int32_t c1, int sp_first, GcTrial<kGeneral> &t, int &sp_out)
+__device__ __forceinline__ void gc_try_predictor_literal(const int16_t *frame, int n, int32_t h1, int32_t h2, int32_t c0,
+                                                         int32_t c1, int sp_first, GcTrial<kGeneral> &t, int &sp_out)
 {
     int sp = sp_first - 1;
     do {
@@ -210,98 +139,80 @@ __device__ __noinline__ void gc_try_predictor_literal(const int16_t *frame, int 
 
 // Residual of one sample against the RAW neighbours (:107-115) folded into an order-preserving key:
 // larger |distance| wins, then the EARLIER sample (the reference keeps the first maximum: strict '>'), and the
-// sign rides in bit 0 so the signed maxDistance can be rebuilt.
-__device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, int32_t cur, int32_t c0, int32_t c1, int s)
+// sign rides in bit 0 so the signed maxDistance can be rebuilt.  `neg_bias` is added to the prediction sum
+// before the division (0 for raw samples, -32768*(c0+c1) when older/newer carry the +32768 bias).
+__device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, int32_t cur, int32_t c0, int32_t c1, int s,
+                                                int32_t neg_bias = 0)
 {
-    const int32_t guess = wadd(wmul(older, c1), wmul(newer, c0)) / 2048;  // truncates toward zero (A.6)
+    const int32_t guess = imad(newer, c0, imad(older, c1, neg_bias)) / 2048;  // truncates toward zero (A.6)
     const int32_t diff = clamp16(wsub(cur, guess));
-    return ((uint32_t)abs(diff) << 5) | ((uint32_t)(15 - s) << 1) | (diff < 0 ? 1u : 0u);
-}
-
-// Keys of samples 2..13 of a frame only involve raw samples, so they are computed one frame ahead, and the four
-// candidate lanes of a predictor share the work: lane `cand` takes samples 2+3*cand .. 4+3*cand, then two
-// shuffle-xor steps inside the group of four combine them.
-__device__ __forceinline__ uint32_t gc_peak_key_rest(const int16_t *frame, int cand, int32_t c0, int32_t c1)
-{
-    const int s0 = 2 + 3 * cand;
-    const int32_t a = frame[s0 - 2], b = frame[s0 - 1], c = frame[s0], d = frame[s0 + 1], e = frame[s0 + 2];
-    uint32_t key = max(gc_peak_key(a, b, c, c0, c1, s0), max(gc_peak_key(b, c, d, c0, c1, s0 + 1),
-                                                           gc_peak_key(c, d, e, c0, c1, s0 + 2)));
-    key = max(key, __shfl_xor_sync(kFull, key, 1));
-    key = max(key, __shfl_xor_sync(kFull, key, 2));
-    return key;
+    return ((uint32_t)abs(diff) << 5) | ((uint32_t)(15 - s) << 1) | ((uint32_t)diff >> 31);
 }
 
 // First value scalePower takes inside the do/while (:118-129), from the max-residual key.  Closed form of
 //   n = 0; while (n <= 12 && (peak > 7 || peak < -8)) { peak /= 2; n++; }   ("/" truncates toward zero)
-// positive peak: smallest n with peak < 8*2^n; negative peak -a: smallest n with a < 9*2^n (a <= 32768 so n <= 12).
+// positive peak a: smallest n with a < 8*2^n; negative peak -a: smallest n with a < 9*2^n (a <= 32768 so n <= 12).
+// The key holds a in bits 5.., so bitlength(a) = bitlength(key) - 5.
 __device__ __forceinline__ int gc_first_scale_power(uint32_t key)
 {
-    const uint32_t a = key >> 5;
-    const int bits = 32 - __clz(a);  // 0 for a == 0
-    int n = max(bits - 3, 0);
-    if ((key & 1u) && n > 0 && (a >> (n - 1)) == 8u) n -= 1;  // negative: a in [8*2^(n-1), 9*2^(n-1)) needs one less
-    return n <= 1 ? 0 : n - 1;
+    const int n = max(24 - __clz(key), 0);                       // max(bitlength(a) - 3, 0)
+    // negative peak with a in [8,9) * 2^(n-1) needs one halving less (only meaningful for n > 0)
+    const int one_less = (int)(key & 1u) & (int)((key >> ((n + 4) & 31)) == 8u) & (int)(n > 0);
+    return max(n - one_less - 1, 0);                             // n <= 1 ? 0 : n - 1
 }
 
-// DspEncodeFrame (:48-94) for one frame of a channel, executed by a full warp.  `frame` = the 14 samples in shared
-// memory (for the rare out-of-line paths), x = the same in registers, key_rest = gc_peak_key_rest of this frame.
-// On return exactly one lane has is_winner set.
-__device__ __forceinline__ void gc_frame_search(const int16_t *frame, const int32_t (&x)[14], uint32_t key_rest,
-                                                int32_t h1, int32_t h2, int32_t c0, int32_t c1, int lane,
-                                                bool &is_winner, GcTrial<false> &t, int &sp_final)
+// DspEncodeFrame (:48-94) for one frame by a full warp with the general exact arithmetic and the literal scale loop:
+// the rare path of the channel encoder (a lane failed the exactness test, a scale chain left the speculative window,
+// an overflow bump, or an error too large for the 27-bit argmin key).  Warp-uniform call.  The winner writes the 8
+// frame bytes to out8; returns the winner's biased newest two samples packed like the hot path does.
+__device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1, int32_t h2, int32_t c0, int32_t c1,
+                                               int sp_first, int lane, uint8_t *out8)
 {
-    const int cand = lane & 3;
-    const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(h2, h1, x[0], c0, c1, 0), gc_peak_key(h1, x[0], x[1], c0, c1, 1));
-    const int sp_first = gc_first_scale_power(key);
-    const int sp = sp_first + cand;
-    const bool valid = sp <= 12;
-
-    const bool exact = gc_attempt_fast(x, h1, h2, c0, c1, valid ? sp : 12, t);
-    // rare (see gc_attempt_fast): only the affected lanes recompute with the general exact arithmetic
-    if (valid && !exact) gc_attempt_exact<false>(frame, 14, h1, h2, c0, c1, sp, t);
-    const bool terminal = valid && (t.over <= 1 || sp >= 12);     // the while condition (:170) fails here
-    const bool bump = valid && sp < 12 && t.over > 248;           // the overflow bump loop (:166-168) would run
-    const uint32_t term_bits = __ballot_sync(kFull, terminal);
-    const uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
-    // a predictor whose four candidates all failed to end the chain leaves the window: every lane sees it in the ballot
-    const uint32_t any4 = term_bits | (term_bits >> 1) | (term_bits >> 2) | (term_bits >> 3);
-    const bool window_miss = (any4 & 0x11111111u) != 0x11111111u;
-
-    sp_final = sp;
-    bool pred_winner = terminal && (group & ((1u << cand) - 1u)) == 0u;  // first candidate that ends the chain
-
-    // argmin of TotalDistance over the predictors, first minimum wins (:66-76).  lane = predictor*4 + candidate is
-    // monotone in the predictor, so min over (err, lane) picks the first minimal predictor.  Key 0 is reserved:
-    // a lane that would take the overflow bump posts it so the whole warp learns about it from the same REDUX.
-    const uint32_t e_sat = t.err < (uint64_t)kErrSat ? (uint32_t)t.err : kErrSat;
-    const uint32_t key32 = bump ? 0u : (pred_winner ? (((e_sat + 1u) << 5) | (uint32_t)lane) : 0xFFFFFFFFu);
-    const uint32_t best = __reduce_min_sync(kFull, key32);
-    if (!window_miss && best != 0u && (best >> 5) <= kErrSat) {
-        is_winner = key32 == best;
-        return;
-    }
-    // ---- rare: replay the literal loop (bump / window miss) and/or reduce on the full 64-bit error ----
-    if (window_miss || best == 0u) {
-        pred_winner = cand == 0;
-        if (pred_winner) gc_try_predictor_literal<false>(frame, 14, h1, h2, c0, c1, sp_first, t, sp_final);
-    }
-    const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;
+    const int pred = lane >> 2, cand = lane & 3;
+    GcTrial<false> t;
+    t.err = 0; t.r1 = 0; t.r2 = 0; t.w0 = 0; t.w1 = 0;
+    int sp_final = 0;
+    if (cand == 0) gc_try_predictor_literal<false>(frame, 14, h1, h2, c0, c1, sp_first, t, sp_final);
+    const bool pred_winner = cand == 0;
+    const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;  // first minimum wins (:66-76)
     const uint32_t hi = (uint32_t)(full_key >> 16);
     const uint32_t min_hi = __reduce_min_sync(kFull, hi);
     const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
     const uint32_t min_lo = __reduce_min_sync(kFull, lo);
-    is_winner = pred_winner && hi == min_hi && lo == min_lo;
+    const bool is_winner = pred_winner && hi == min_hi && lo == min_lo;
+    if (is_winner) {
+        const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));  // CombineNibbles (:83)
+        *reinterpret_cast<uint2 *>(out8) = make_uint2(t.w0 | head, t.w1);
+    }
+    return __reduce_max_sync(kFull, is_winner ? ((uint32_t)(t.r1 + 32768) | ((uint32_t)(t.r2 + 32768) << 16)) : 0u);
 }
 
 // grid: one warp per channel; encodes frames [frame_begin, frame_end) of every channel, carrying the history
 // in tab.hist between launches (frame_begin must be a multiple of 16).
+//
+// The per-frame code below is DspEncodeFrame (:48-94) for a full warp, written as one software-pipelined block:
+//   head     residual keys of samples 0,1 (they need the reconstructed history) + the 12 keys computed one frame
+//            ahead -> first scalePower -> this lane's candidate scale and its constants
+//   phase A  the 14-step recurrence at that scale; per sample the dependent chain is
+//            IMAD -> LEA.HI -> SHF -> VIADDMNMX.RELU -> IMAD -> VIADDMNMX.RELU  (no predicate on the chain:
+//            the sign-dependent rounding uses the sign BIT of a second multiply-add; samples are biased +32768 and
+//            nibbles +8 so each clamp is one instruction; the ">> 11" is folded:
+//            (guess + q*2^K + 1024) >> 11 == q*2^(K-11) + ((guess + 1024) >> 11) since K >= 11).
+//            The next frame's loads / residual keys ride along as independent work.
+//   phase B  range of raw (maxOverflow), exactness test, squared error, nibble packing
+//   tail     two ballots (chain ends / exactness), one REDUX.MIN for the argmin, one REDUX.MAX to broadcast the
+//            winner's two newest samples; anything unusual re-runs the frame in gc_slow_frame.
+// Exactness of phase A (tools/quantiser_check.c enumerates the quantiser identity):
+//   * every |diff| < 2^24: float32 holds diff exactly, the pass is bit-identical to the reference cast chain;
+//   * some |diff| >= 2^24 ("big"): the float32 rounding moves a quantiser threshold by hs <= 128, which changes
+//     `raw` only if (diff + half) lies within 128 of a multiple of 2^shift ("near"), and then by one - invisible
+//     to the clamped nibble when |raw| >= 15, but it could flip the overflow-bump test at 248 (`over >= 240`);
+//   * some |diff| >= 2^29 ("huge", hostile coefficients only): the biased sums could wrap.
 __global__ void __launch_bounds__(kEncWarps * 32)
 gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
                  uint8_t *__restrict__ adpcm, int frame_begin, int frame_end)
 {
-    // one extra zero frame behind each staging buffer so the one-frame-ahead residual pass may read past the chunk
-    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][kEncChunkSamples + 16];
+    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][kEncChunkSamples];
     __shared__ __align__(16) uint8_t out_buf[kEncWarps][kEncChunkFrames * kGcFrameBytes];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,10 +230,11 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     const int pred = lane >> 2, cand = lane & 3;
     const int32_t c0 = coefs[(int64_t)ch * 16 + 2 * pred];
     const int32_t c1 = coefs[(int64_t)ch * 16 + 2 * pred + 1];
-    int32_t h1 = tab.hist[2 * ch], h2 = tab.hist[2 * ch + 1];
+    const int32_t nc0 = -c0, nc1 = -c1;
+    const int32_t bias_c = wmul(32768, wadd(c0, c1));  // undoes the +32768 bias of both history samples
+    int32_t p1 = tab.hist[2 * ch] + 32768, p2 = tab.hist[2 * ch + 1] + 32768;  // biased history (newest, older)
 
-    // 16-byte vector `lane` of a chunk (lanes 0..27 data, lanes 28..29 the zero tail), zero beyond the encoded
-    // sample count (GcAdpcmEncoder.cs:32-34)
+    // 16-byte vector `lane` of a chunk (lanes 0..27), zero beyond the encoded sample count (GcAdpcmEncoder.cs:32-34)
     auto load_vec = [&](int chunk_frame) -> uint4 {
         uint4 q = make_uint4(0, 0, 0, 0);
         const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + lane * 8;
@@ -341,48 +253,154 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         }
         return q;
     };
+    // residual keys of samples 2..13 (raw samples only).  The four candidate lanes of a predictor share the work:
+    // lane `cand` takes samples 2+3*cand .. 4+3*cand, two shuffle-xor steps inside the group of four combine them.
+    auto key_rest_partial = [&](const int16_t *frame) -> uint32_t {
+        const int s0 = 2 + 3 * cand;
+        const int32_t a = frame[s0 - 2], b = frame[s0 - 1], c = frame[s0], d = frame[s0 + 1], e = frame[s0 + 2];
+        return __vimax3_u32(gc_peak_key(a, b, c, c0, c1, s0), gc_peak_key(b, c, d, c0, c1, s0 + 1),
+                            gc_peak_key(c, d, e, c0, c1, s0 + 2));
+    };
 
     int buf = 0;
     {
         const uint4 first = load_vec(frame_begin);
-        if (lane < kEncChunkSamples / 8 + 2) {
-            reinterpret_cast<uint4 *>(in_buf[warp][0])[lane] = first;
-            reinterpret_cast<uint4 *>(in_buf[warp][1])[lane] = make_uint4(0, 0, 0, 0);
-        }
+        if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][0])[lane] = first;
         __syncwarp();
     }
+    // pipeline prologue: samples and residual keys of the first frame
+    int32_t x[14];
+#pragma unroll
+    for (int j = 0; j < 14; j++) x[j] = in_buf[warp][0][j];
+    uint32_t key_rest = key_rest_partial(in_buf[warp][0]);
+    key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 1));
+    key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 2));
 
     for (int cf = frame_begin; cf < f_hi; cf += kEncChunkFrames) {
-        const uint4 next = load_vec(cf + kEncChunkFrames);  // prefetch; consumed after this chunk
+        const uint4 next = load_vec(cf + kEncChunkFrames);  // prefetch; staged into the other buffer at mid-chunk
         const int frames_here = min(kEncChunkFrames, f_hi - cf);
         const int16_t *chunk = in_buf[warp][buf];
-
-        uint32_t key_rest = gc_peak_key_rest(chunk, cand, c0, c1);
+        const int16_t *other = in_buf[warp][buf ^ 1];
 
         for (int i = 0; i < frames_here; i++) {
-            const int16_t *frame = chunk + i * kGcFrameSamples;
-            int32_t x[14];
-#pragma unroll
-            for (int j = 0; j < 14; j++) x[j] = frame[j];  // same address in every lane: shared-memory broadcast
-
-            // next frame's residual keys, independent of this frame's search (software pipelining);
-            // i + 1 == 16 reads the zero tail behind the chunk and the result is unused then
-            const uint32_t key_rest_next = gc_peak_key_rest(frame + kGcFrameSamples, cand, c0, c1);
-
-            bool is_winner;
-            int sp_final;
-            GcTrial<false> t;
-            gc_frame_search(frame, x, key_rest, h1, h2, c0, c1, lane, is_winner, t, sp_final);
-
-            if (is_winner) {
-                const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));  // CombineNibbles (:83)
-                *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(t.w0 | head, t.w1);
+            if (i == kEncChunkFrames / 2) {  // the other buffer was last read 8 frames ago: refill it now
+                if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][buf ^ 1])[lane] = next;
+                __syncwarp();
             }
+            const int16_t *frame = chunk + i * kGcFrameSamples;
+            const int16_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
+            const int32_t p1_in = p1, p2_in = p2;
+
+            // ---------------- head ----------------
+            const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(p2, p1, x[0], c0, c1, 0, -bias_c),
+                                              gc_peak_key(p1, x[0] + 32768, x[1], c0, c1, 1, -bias_c));
+            const int sp_first = gc_first_scale_power(key);
+            const int sp_raw = sp_first + cand;
+            const int sp = min(sp_raw, 12);
+            const uint32_t valid = sp_raw <= 12 ? 1u : 0u;
+            const int shift = sp + 11;
+            const int32_t half = (int32_t)(1u << (shift - 1));
+            const int32_t mul = (int32_t)(1u << sp);                             // 2^(shift-11)
+            // tm1 = diff + half - 1 = x*2048 + base_m - c0*p1 - c1*p2 ;  e1 = tm1 - half (its sign bit = diff <= 0)
+            const int32_t base_m = wadd(bias_c, half) - 1;
+            // guess + 1024 - 8*2^shift = c0*p1 + c1*p2 + base_g
+            const int32_t base_g = wsub(wsub(1024, (int32_t)(8u << shift)), bias_c);
+            const int lsh = 32 - shift;
+            const uint32_t near_c = 128u << lsh;
+            const uint32_t near_k = (1u << lsh) + near_c;   // (tn << lsh) + near_c with tn = tm1 + 1
+
+            // ---------------- phase A: recurrence ----------------
+            int32_t tmv[14], rawv[14], qbv[14], obv[14];
+            int32_t xn[14];
+            uint32_t key_rest_next = 0;
+#pragma unroll
+            for (int s = 0; s < 14; s++) {
+                const int32_t wt = imad(x[s], 2048, base_m);
+                const int32_t an = imad(p2, nc1, wt);          // p2 terms: one step off the chain
+                const int32_t ah = an - half;
+                const int32_t gn = imad(p2, c1, base_g);
+                const int32_t tm1 = imad(p1, nc0, an);         // diff + half - 1          <- chain
+                const int32_t e1 = imad(p1, nc0, ah);          // diff - 1: negative iff diff <= 0
+                const int32_t wf = imad(p1, c0, gn);           // guess + 1024 - 8*2^shift
+                // round half toward zero: (diff + half - (diff > 0)) >> shift = (tm1 + (diff <= 0)) >> shift
+                const int32_t t2 = tm1 + (int32_t)((uint32_t)e1 >> 31);
+                const int32_t raw = sar(t2, shift);
+                const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);        // clamp4(raw) + 8
+                const int32_t o = imad(qb, mul, wf >> 11);
+                const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);   // clamp16(o) + 32768
+                tmv[s] = tm1; rawv[s] = raw; qbv[s] = qb; obv[s] = ob;
+                p2 = p1;
+                p1 = ob;
+                // independent work for the NEXT frame rides along (software pipelining)
+                if (s == 1) {
+#pragma unroll
+                    for (int j = 0; j < 14; j++) xn[j] = frame_next[j];  // same address in every lane: broadcast
+                }
+                if (s == 4) key_rest_next = key_rest_partial(frame_next);
+                if (s == 8) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 1));
+                if (s == 12) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 2));
+            }
+
+            // ---------------- phase B ----------------
+            int32_t rmin = 0, rmax = 0;
+            uint32_t nearmin = 0xFFFFFFFFu;
+#pragma unroll
+            for (int s = 0; s < 14; s += 2) {
+                rmin = __vimin3_s32(rmin, rawv[s], rawv[s + 1]);
+                rmax = __vimax3_s32(rmax, rawv[s], rawv[s + 1]);
+            }
+#pragma unroll
+            for (int s = 0; s < 14; s++) nearmin = __viaddmin_u32((uint32_t)tmv[s] << lsh, near_k, nearmin);
+            const int32_t over = max(max(rmax - 7, -8 - rmin), 0);
+            // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical path
+            const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
+            const uint32_t big = (uint32_t)(rmax >= big_thr) | (uint32_t)(rmin <= -big_thr);     // some |diff| >= 2^24
+            const uint32_t huge = (uint32_t)(rmax >= huge_thr) | (uint32_t)(rmin <= -huge_thr);  // some |diff| >= 2^29
+            const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | (uint32_t)(over >= 240);
+            const uint32_t inexact = valid & (huge | (big & near));
+            const uint32_t terminal = valid & ((uint32_t)(over <= 1) | (uint32_t)(sp >= 12));  // while (:170) fails
+            const uint32_t bump = valid & (uint32_t)(sp < 12) & (uint32_t)(over > 248);        // bump loop (:166-168)
+            const uint32_t term_bits = __ballot_sync(kFull, terminal != 0u);
+            const uint32_t trouble_bits = __ballot_sync(kFull, (inexact | bump) != 0u);
+
+            // squared error (four partial sums) and nibble packing
+            uint64_t e0 = 0, e1s = 0, e2 = 0, e3 = 0;
+            uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+            for (int s = 0; s < 14; s++) {
+                const int32_t miss = x[s] + 32768 - obv[s];
+                const uint64_t sq = (uint64_t)((int64_t)miss * miss);  // exact; the sum stays below 2^36
+                if ((s & 3) == 0) e0 += sq; else if ((s & 3) == 1) e1s += sq; else if ((s & 3) == 2) e2 += sq; else e3 += sq;
+                const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
+                if (byte < 4) w0 += (uint32_t)qbv[s] << bit; else w1 += (uint32_t)qbv[s] << bit;  // disjoint fields
+            }
+            const uint64_t err = (e0 + e1s) + (e2 + e3);
+            w0 ^= 0x88888800u;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8); byte 0 is the header
+            w1 ^= 0x88888888u;
+
+            // ---------------- tail: replay the scale chain, argmin over predictors ----------------
+            const uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
+            // a predictor whose four candidates all failed to end the chain leaves the window (all lanes see it)
+            const uint32_t any4 = term_bits | (term_bits >> 1) | (term_bits >> 2) | (term_bits >> 3);
+            const uint32_t pred_winner = terminal & (uint32_t)((group & ((1u << cand) - 1u)) == 0u);  // first that ends
+            // first minimum wins (:66-76): lane = predictor*4 + candidate is monotone in the predictor
+            const uint32_t e_sat = err < (uint64_t)kErrSat ? (uint32_t)err : kErrSat;
+            const uint32_t key32 = pred_winner ? ((e_sat << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
+            const uint32_t best = __reduce_min_sync(kFull, key32);
+            const bool is_winner = key32 == best;
+            const uint32_t head = (uint32_t)((pred << 4) | sp);  // CombineNibbles (:83)
+            if (is_winner) *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(w0 | head, w1);
             // pcmBuffer[0] = pcmBuffer[14]; pcmBuffer[1] = pcmBuffer[15] (:40-41): the winner's two newest samples
-            const uint32_t packed = __reduce_max_sync(
-                kFull, is_winner ? ((((uint32_t)t.r1 + 32768u) & 0xFFFFu) | (((uint32_t)t.r2 + 32768u) << 16)) : 0u);
-            h1 = (int32_t)(packed & 0xFFFFu) - 32768;
-            h2 = (int32_t)(packed >> 16) - 32768;
+            uint32_t packed = __reduce_max_sync(kFull, is_winner ? ((uint32_t)p1 | ((uint32_t)p2 << 16)) : 0u);
+            // anything unusual (warp-uniform, rare): redo the frame with the exact arithmetic and the literal loop
+            if (trouble_bits != 0u || (any4 & 0x11111111u) != 0x11111111u || (best >> 5) >= kErrSat)
+                packed = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane,
+                                       &out_buf[warp][i * kGcFrameBytes]);
+            p1 = (int32_t)(packed & 0xFFFFu);
+            p2 = (int32_t)(packed >> 16);
+
+#pragma unroll
+            for (int j = 0; j < 14; j++) x[j] = xn[j];
             key_rest = key_rest_next;
         }
         __syncwarp();
@@ -400,14 +418,13 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 }
             }
         }
-        buf ^= 1;
-        if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][buf])[lane] = next;
         __syncwarp();
+        buf ^= 1;
     }
 
     if (lane == 0) {
-        tab.hist[2 * ch] = (int16_t)h1;
-        tab.hist[2 * ch + 1] = (int16_t)h2;
+        tab.hist[2 * ch] = (int16_t)(p1 - 32768);
+        tab.hist[2 * ch + 1] = (int16_t)(p2 - 32768);
     }
 }
 
