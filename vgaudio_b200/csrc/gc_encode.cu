@@ -155,10 +155,14 @@ __device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, in
 // The key holds a in bits 5.., so bitlength(a) = bitlength(key) - 5.
 __device__ __forceinline__ int gc_first_scale_power(uint32_t key)
 {
-    const int n = max(24 - __clz(key), 0);                       // max(bitlength(a) - 3, 0)
-    // negative peak with a in [8,9) * 2^(n-1) needs one halving less (only meaningful for n > 0)
-    const int one_less = (int)(key & 1u) & (int)((key >> ((n + 4) & 31)) == 8u) & (int)(n > 0);
-    return max(n - one_less - 1, 0);                             // n <= 1 ? 0 : n - 1
+    int top;  // index of the highest set bit, -1 for key == 0
+    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(key));
+    const int n = max(top - 7, 0);                               // max(bitlength(a) - 3, 0)
+    // negative peak with a in [8,9) * 2^(n-1) needs one halving less.  For n > 0 the four bits key >> (n+4) are
+    // 8..15, so "== 8" is "< 9"; everything stays in integer registers (a predicate costs ~13 cycles of latency).
+    const uint32_t t = key >> ((n + 4) & 31);
+    const uint32_t one_less = ((t - 9u) >> 31) & key & ((uint32_t)(-n) >> 31);
+    return max(n - 1 - (int)one_less, 0);                        // n <= 1 ? 0 : n - 1
 }
 
 // DspEncodeFrame (:48-94) for one frame by a full warp with the general exact arithmetic and the literal scale loop:
@@ -351,15 +355,18 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             }
 #pragma unroll
             for (int s = 0; s < 14; s++) nearmin = __viaddmin_u32((uint32_t)tmv[s] << lsh, near_k, nearmin);
-            const int32_t over = max(max(rmax - 7, -8 - rmin), 0);
-            // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical path
+            // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical path.
+            // maxOverflow (:147-151) is max(rmax - 7, -8 - rmin, 0); only its comparisons are needed.
             const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
             const uint32_t big = (uint32_t)(rmax >= big_thr) | (uint32_t)(rmin <= -big_thr);     // some |diff| >= 2^24
             const uint32_t huge = (uint32_t)(rmax >= huge_thr) | (uint32_t)(rmin <= -huge_thr);  // some |diff| >= 2^29
-            const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | (uint32_t)(over >= 240);
+            const uint32_t over_ge_240 = (uint32_t)(rmax >= 247) | (uint32_t)(rmin <= -248);
+            const uint32_t over_gt_248 = (uint32_t)(rmax > 255) | (uint32_t)(rmin < -256);
+            const uint32_t over_le_1 = (uint32_t)(rmax <= 8) & (uint32_t)(rmin >= -9);
+            const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | over_ge_240;
             const uint32_t inexact = valid & (huge | (big & near));
-            const uint32_t terminal = valid & ((uint32_t)(over <= 1) | (uint32_t)(sp >= 12));  // while (:170) fails
-            const uint32_t bump = valid & (uint32_t)(sp < 12) & (uint32_t)(over > 248);        // bump loop (:166-168)
+            const uint32_t terminal = valid & (over_le_1 | (uint32_t)(sp >= 12));  // the while condition (:170) fails
+            const uint32_t bump = valid & (uint32_t)(sp < 12) & over_gt_248;       // the bump loop (:166-168) would run
             const uint32_t term_bits = __ballot_sync(kFull, terminal != 0u);
             const uint32_t trouble_bits = __ballot_sync(kFull, (inexact | bump) != 0u);
 
@@ -386,14 +393,22 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             // first minimum wins (:66-76): lane = predictor*4 + candidate is monotone in the predictor
             const uint32_t e_sat = err < (uint64_t)kErrSat ? (uint32_t)err : kErrSat;
             const uint32_t key32 = pred_winner ? ((e_sat << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
-            const uint32_t best = __reduce_min_sync(kFull, key32);
-            const bool is_winner = key32 == best;
+            uint32_t best = __reduce_min_sync(kFull, key32);
+            if ((best >> 5) >= kErrSat) {
+                // loud frame (warp-uniform): every candidate error is >= 2^27 - 1, reduce on the full 64-bit value
+                const uint64_t full_key = pred_winner ? ((err << 5) | (uint64_t)lane) : ~0ull;
+                const uint32_t hi = (uint32_t)(full_key >> 16);
+                const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+                const uint32_t lo = hi == min_hi ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
+                best = __reduce_min_sync(kFull, lo);  // low 5 bits = winning lane
+            }
+            const int best_lane = (int)(best & 31u);
             const uint32_t head = (uint32_t)((pred << 4) | sp);  // CombineNibbles (:83)
-            if (is_winner) *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(w0 | head, w1);
+            if (lane == best_lane) *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(w0 | head, w1);
             // pcmBuffer[0] = pcmBuffer[14]; pcmBuffer[1] = pcmBuffer[15] (:40-41): the winner's two newest samples
-            uint32_t packed = __reduce_max_sync(kFull, is_winner ? ((uint32_t)p1 | ((uint32_t)p2 << 16)) : 0u);
+            uint32_t packed = __shfl_sync(kFull, (uint32_t)p1 | ((uint32_t)p2 << 16), best_lane);
             // anything unusual (warp-uniform, rare): redo the frame with the exact arithmetic and the literal loop
-            if (trouble_bits != 0u || (any4 & 0x11111111u) != 0x11111111u || (best >> 5) >= kErrSat)
+            if (trouble_bits != 0u || (any4 & 0x11111111u) != 0x11111111u)
                 packed = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane,
                                        &out_buf[warp][i * kGcFrameBytes]);
             p1 = (int32_t)(packed & 0xFFFFu);
