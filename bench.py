@@ -350,6 +350,10 @@ def main():
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
         else:
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_gc_encode_full.json")
+        if os.path.exists(prof) and n_ch == 1024 and n == 1440000:
+            traffic = json.load(open(prof)).get("dram_bytes_total")  # ncu --set full, same launch shape
         enc_ms = float(kernel_ms[2])
         achieved = samples_per_step * ALG_BYTES_PER_SAMPLE / (enc_ms / 1e3) / 1e9 if enc_ms > 0 else None
         line = {
@@ -363,7 +367,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gc_encode_kernel", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/r01_gc_encode_full.json (ncu dram__bytes_read+write, per launch)" if traffic else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(samples_per_step * ALG_BYTES_PER_SAMPLE),
                          "note": "latency/issue bound by the serial 14-sample recurrence, not by HBM (DESIGN.md)"},
             "kernel_ms": {"gc_coef_frames": round(float(kernel_ms[0]), 3), "gc_coef_refine": round(float(kernel_ms[1]), 3),

@@ -15,7 +15,9 @@
 //   gc_coef_refine_kernel   phase 2 (:63-108): one WARP per channel.  Nearest-centroid search is parallel over
 //                           32 records; the fp64 accumulations are applied strictly in record order
 //                            by 16 accumulator lanes (8 buckets x 2 components), because any
-//                           tree reduction would change the roundings and can flip a 16-bit coefficient.
+//                           tree reduction would change the roundings and can flip a 16-bit coefficient.  Records
+//                           are compacted per bucket (ballot + popc) so each lane's DADD chain only contains its
+//                           own bucket's records.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -230,18 +232,117 @@ __device__ __forceinline__ int16_t gc_quantise_coef(double v)
 
 constexpr int kRefineWarps = 4;
 
-// One block of 32 records staged for the ordered accumulation: the two direct-form components in separate planes
-// so an accumulator lane streams its own component with 16-byte loads, and the bucket of every record.
-struct __align__(16) RefineSlot {
-    double comp[2][32];
-    int32_t idx[32];  // bucket of each record, -1 = not a record
+// Per-bucket queues of one block of 32 records: record lanes append their direct-form pair to the queue of the
+// bucket they were assigned to (rank = number of earlier records of the block in the same bucket, from a ballot),
+// so an accumulator lane walks ONLY its bucket's records, still in record order.
+struct __align__(16) RefineQueues {
+    double2 q[8][32];
 };
+
+// One pass over all records of a channel with COUNT centroids (COUNT == 0: the plain ordered mean of :63-76, every
+// record goes to bucket 0).  On return lane (bucket*2 + comp), bucket < max(COUNT,1), holds the ordered sum of that
+// component over the bucket's records in `acc` and the record count in `hits`.
+template <int COUNT>
+__device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blocks, const double2 *__restrict__ rec,
+                                               const uint32_t *__restrict__ mask, RefineQueues *queues,
+                                               const double (*best)[3], double &acc, int &hits)
+{
+    constexpr int NB = COUNT > 0 ? COUNT : 1;
+    const int my_bucket = lane >> 1, my_comp = lane & 1;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+
+    // per-centroid constants of ContrastVectors (:338-340)
+    double e0[NB], e1[NB], e2[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const double a0 = best[i][0], a1 = best[i][1], a2 = best[i][2];
+        e0[i] = (a0 * a0) + (a1 * a1) + (a2 * a2);
+        e1[i] = (a0 * a1) + (a1 * a2);
+        e2[i] = a0 * a2;
+    }
+
+    // classify block b (nearest centroid, parallel over its 32 records) and append to the bucket queues of slot b&1;
+    // bits[k] = which lanes went to bucket k
+    auto stage = [&](int b, double2 r, uint32_t okbits, uint32_t (&bits)[NB]) {
+        const bool ok = ((okbits >> lane) & 1u) && (b * 32 + lane < n_frames);
+        int pick = 0;
+        if (COUNT > 1) {
+            // ContrastVectors (:335-342); its `val` is r.x and (-rec1*val - rec2) is r.y
+            const double ta = 2.0 * r.x, tb = 2.0 * r.y;
+            double least = 1.0e30;
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const double d = e0[i] + (ta * e1[i]) + (tb * e2[i]);
+                const bool better = d < least;  // strict: the first minimum wins (:376-380)
+                least = better ? d : least;
+                pick = better ? i : pick;
+            }
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            bits[k] = __ballot_sync(0xFFFFFFFFu, ok && pick == k);
+            mine = pick == k ? bits[k] : mine;
+        }
+        if (ok) queues[b & 1].q[pick][__popc(mine & lanes_below)] = r;
+    };
+    auto fetch = [&](int b, double2 &r, uint32_t &okbits) {
+        r = make_double2(0.0, 0.0);
+        okbits = 0;
+        if (b < n_blocks) {
+            okbits = mask[b];
+            const int f = b * 32 + lane;
+            if (f < n_frames) r = rec[f];
+        }
+    };
+
+    acc = 0.0;
+    hits = 0;
+    // Records stream from HBM once per pass (1.6 MB per channel, no reuse): loads are issued kDepth blocks ahead of
+    // their use to cover DRAM latency; ring indices are compile-time.
+    constexpr int kDepth = 4;
+    double2 ring_r[kDepth];
+    uint32_t ring_ok[kDepth];
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) fetch(k, ring_r[k], ring_ok[k]);
+    uint32_t cur_bits[NB], next_bits[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) cur_bits[k] = next_bits[k] = 0;
+    if (n_blocks > 0) stage(0, ring_r[0], ring_ok[0], cur_bits);
+    fetch(kDepth, ring_r[0], ring_ok[0]);
+    __syncwarp();
+
+    for (int b0 = 0; b0 < n_blocks; b0 += kDepth) {
+#pragma unroll
+        for (int k = 0; k < kDepth; k++) {
+            const int b = b0 + k;
+            if (b >= n_blocks) break;
+            // (1) classify and queue the NEXT block (independent of the chain below), refill its ring slot
+            const int slot_next = (k + 1) % kDepth;
+            if (b + 1 < n_blocks) stage(b + 1, ring_r[slot_next], ring_ok[slot_next], next_bits);
+            fetch(b + 1 + kDepth, ring_r[slot_next], ring_ok[slot_next]);
+
+            // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) adds its bucket's records
+            // in record order - a pure DADD chain over exactly those records
+            uint32_t mine = 0;
+#pragma unroll
+            for (int kk = 0; kk < NB; kk++) mine = my_bucket == kk ? cur_bits[kk] : mine;
+            const int n_mine = __popc(mine);
+            const double *col = reinterpret_cast<const double *>(queues[b & 1].q[my_bucket & 7]) + my_comp;
+            for (int j = 0; j < n_mine; j++) acc += col[2 * j];
+            hits += n_mine;
+#pragma unroll
+            for (int kk = 0; kk < NB; kk++) cur_bits[kk] = next_bits[kk];
+            __syncwarp();
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kRefineWarps * 32)
 gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, const uint32_t *__restrict__ accept_mask,
                       int16_t *__restrict__ coefs_out)
 {
-    __shared__ RefineSlot slots[kRefineWarps][2];
+    __shared__ RefineQueues queues[kRefineWarps][2];
     __shared__ double cent[kRefineWarps][8][3];  // centroids (1, c1, c2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,9 +355,11 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
     const double2 *rec = records + tab.rec_off[ch];
     const uint32_t *mask = accept_mask + (tab.rec_off[ch] >> 5);
 
-    const int my_bucket = lane >> 1, my_comp = lane & 1;  // accumulator lanes 0..15 (lanes 16..31 match nothing)
+    if (lane < 8) { best[lane][0] = 1.0; best[lane][1] = 0.0; best[lane][2] = 0.0; }
+    __syncwarp();
 
-    // pass 0 is the plain ordered mean (:63-76, every record in bucket 0); passes 1..6 are FilterRecords rounds.
+    // pass 0 is the plain ordered mean (:63-76); passes 1..6 are the FilterRecords rounds (:79-91): split, then two
+    // rounds of reassign + average with 2, 4, 8 centroids.
     int count = 1;
     for (int pass = 0; pass < 7; pass++) {
         if (pass == 1 || pass == 3 || pass == 5) {
@@ -269,95 +372,12 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
             count *= 2;
             __syncwarp();
         }
-        // per-centroid constants of ContrastVectors (:338-340), kept in registers by every lane
-        Centroid c[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            c[i].e0 = c[i].e1 = c[i].e2 = 0.0;
-            if (pass > 0 && i < count) {
-                double a0 = best[i][0], a1 = best[i][1], a2 = best[i][2];
-                c[i].e0 = (a0 * a0) + (a1 * a1) + (a2 * a2);
-                c[i].e1 = (a0 * a1) + (a1 * a2);
-                c[i].e2 = a0 * a2;
-            }
-        }
-
-        // classify block b (nearest centroid, parallel over the 32 records) and stage it in slot[b & 1]
-        auto stage = [&](int b, double2 r, uint32_t bits) {
-            const int f = b * 32 + lane;
-            const bool ok = (f < n_frames) && ((bits >> lane) & 1u);
-            if (!ok) r = make_double2(-0.0, -0.0);  // x + (-0.0) == x for every x: a non-record adds nothing
-            int pick = ok ? 0 : -1;
-            if (pass > 0 && ok) {
-                // ContrastVectors (:335-342); its `val` is r.x and (-rec1*val - rec2) is r.y
-                const double ta = 2.0 * r.x, tb = 2.0 * r.y;
-                double least = 1.0e30;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (i < count) {
-                        const double d = c[i].e0 + (ta * c[i].e1) + (tb * c[i].e2);
-                        if (d < least) { least = d; pick = i; }
-                    }
-                }
-            }
-            RefineSlot &sl = slots[warp][b & 1];
-            sl.comp[0][lane] = r.x;
-            sl.comp[1][lane] = r.y;
-            sl.idx[lane] = pick;
-        };
-        auto fetch = [&](int b, double2 &r, uint32_t &bits) {
-            r = make_double2(0.0, 0.0);
-            bits = 0;
-            if (b < n_blocks) {
-                bits = mask[b];
-                const int f = b * 32 + lane;
-                if (f < n_frames) r = rec[f];
-            }
-        };
-
-        double acc = 0.0;
-        int hits = 0;
-        // Records stream from HBM once per pass (1.6 MB per channel, no reuse), so the loads are issued kDepth
-        // blocks (~4 x 300 cycles) ahead of their use to cover DRAM latency; ring indices are compile-time.
-        constexpr int kDepth = 4;
-        double2 ring_r[kDepth];
-        uint32_t ring_bits[kDepth];
-#pragma unroll
-        for (int k = 0; k < kDepth; k++) fetch(k, ring_r[k], ring_bits[k]);
-        if (n_blocks > 0) stage(0, ring_r[0], ring_bits[0]);
-        fetch(kDepth, ring_r[0], ring_bits[0]);
-        __syncwarp();
-
-        for (int b0 = 0; b0 < n_blocks; b0 += kDepth) {
-#pragma unroll
-            for (int k = 0; k < kDepth; k++) {
-                const int b = b0 + k;
-                if (b >= n_blocks) break;
-                // (1) classify and stage the NEXT block (independent of the chain below), refill its ring slot
-                const int slot_next = (k + 1) % kDepth;
-                if (b + 1 < n_blocks) stage(b + 1, ring_r[slot_next], ring_bits[slot_next]);
-                fetch(b + 1 + kDepth, ring_r[slot_next], ring_bits[slot_next]);
-
-                // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) walks the 32 records
-                // in order; unconditional vector loads, then a pure DADD chain (8 cycles per record)
-                const RefineSlot &sl = slots[warp][b & 1];
-                const int4 *idx4 = reinterpret_cast<const int4 *>(sl.idx);
-                const double2 *val2 = reinterpret_cast<const double2 *>(sl.comp[my_comp]);
-#pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const int4 id = idx4[g];
-                    const double2 va = val2[2 * g], vb = val2[2 * g + 1];
-                    const bool m0 = id.x == my_bucket, m1 = id.y == my_bucket, m2 = id.z == my_bucket,
-                               m3 = id.w == my_bucket;
-                    acc += m0 ? va.x : -0.0;
-                    acc += m1 ? va.y : -0.0;
-                    acc += m2 ? vb.x : -0.0;
-                    acc += m3 ? vb.y : -0.0;
-                    hits += (int)m0 + (int)m1 + (int)m2 + (int)m3;
-                }
-                __syncwarp();
-            }
-        }
+        double acc;
+        int hits;
+        if (pass == 0) gc_refine_pass<0>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
+        else if (count == 2) gc_refine_pass<2>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
+        else if (count == 4) gc_refine_pass<4>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
+        else gc_refine_pass<8>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
 
         // divide (:73-74 / :388-391) and rebuild the centroids (:76 / :393-394)
         double mean;
@@ -366,6 +386,7 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
         const double m1 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2);
         const double m2 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2 + 1);
         const int h = __shfl_sync(0xFFFFFFFFu, hits, (lane & 7) * 2);
+        __syncwarp();
         if (lane < count) {
             const double m0 = (pass == 0) ? 1.0 : (h > 0 ? 1.0 : 0.0);  // sum of h ones divided by h
             double o1, o2;
