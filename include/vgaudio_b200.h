@@ -138,9 +138,46 @@ int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offs
 int32_t vgb_set_kernel_timing(int32_t enabled);
 int32_t vgb_last_kernel_ms(float *ms_out, int32_t n);
 
+/* Device timeline of the last host GC-ADPCM encode call, ms since its first copy was enqueued: per channel group
+ * [H2D landed, kernels finished, D2H finished] (evidence of the copy/compute overlap; bench.py reports it). */
+int32_t vgb_debug_last_timeline(float *ms_out, int32_t n);
+
 /* Debug/test taps (tests/ only): run coefficient phase 1 and return, per frame, the direct-form pair and the
  * accept flag the refinement consumes.  Host buffers; dir_out [frames][2] doubles, accepted_out [frames] bytes. */
 int32_t vgb_gcadpcm_debug_records(const int16_t *pcm, int32_t n_samples, double *dir_out, uint8_t *accepted_out);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CRI ADX (Codecs/CriAdx/CriAdxCodec.cs), host buffers.  One call replaces one Parallel.For over channels
+ * (Formats/CriAdx/CriAdxFormat.cs:67-81 encode, :37-49 decode).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Mirror of CriAdxParameters : CodecParameters (Codecs/CriAdx/CriAdxParameters.cs:3-13).
+ * type: 2 = Fixed, 3 = Linear, 4 = Exponential (CriAdxType.cs:3-8). */
+typedef struct vgb_adx_params {
+    int32_t sample_rate;         /* default 48000 */
+    int32_t highpass_frequency;  /* default 500 (decode only; Encode hard-codes 500, CriAdxCodec.cs:63) */
+    int32_t frame_size;          /* default 18 */
+    int32_t version;             /* default 4 */
+    int32_t history;             /* decode: initial hist1 = hist2 (CriAdxCodec.cs:16-17) */
+    int32_t padding;
+    int32_t type;                /* default 3 (Linear) */
+    int32_t filter;              /* Fixed only: 0..3 */
+} vgb_adx_params;
+
+/* frameCount * FrameSize of CriAdxCodec.Encode (CriAdxCodec.cs:59-61,67) */
+int32_t vgb_adx_encoded_byte_count(int32_t pcm_length, int32_t padding, int32_t frame_size);
+
+/* CriAdxCodec.Encode(short[] pcm, CriAdxParameters config) (CriAdxCodec.cs:56-105) for every channel.
+ * params is [n_channels]; history_out[c] receives the value the reference writes back into config.History (:73,
+ * read by CriAdxFormat.cs:80); adpcm_out[c] receives vgb_adx_encoded_byte_count(...) bytes. */
+int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
+                             int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out,
+                             vgb_progress_cb cb, void *user);
+
+/* CriAdxCodec.Decode(byte[] adpcm, int sampleCount, CriAdxParameters config) (CriAdxCodec.cs:9-54).
+ * n_bytes[c] = length of adpcm[c]; pcm_out[c] receives sample_count[c] samples. */
+int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
+                             const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out);
 
 #ifdef __cplusplus
 }

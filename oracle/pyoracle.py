@@ -49,6 +49,14 @@ def lib() -> C.CDLL:
         L.vgo_gc_decode.restype = None
         L.vgo_gc_encode_batch.argtypes = [vp, i64, i32, i32, vp, vp, i64, i32]
         L.vgo_gc_decode_batch.argtypes = [vp, i64, vp, i32, i32, vp, i64, i32]
+        L.vgo_adx_calculate_coefficients.argtypes = [i32, i32, vp]
+        L.vgo_adx_calculate_coefficients.restype = None
+        L.vgo_adx_encoded_byte_count.argtypes = [i32, i32, i32]
+        L.vgo_adx_encode_frame.argtypes = [vp, vp, vp, i32, i32, i32]
+        L.vgo_adx_encode_frame.restype = None
+        L.vgo_adx_encode.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp]
+        L.vgo_adx_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+        L.vgo_adx_decode.restype = None
         _lib = L
     return _lib
 
@@ -117,3 +125,40 @@ def decode_batch(adpcm2d: np.ndarray, coefs: np.ndarray, sample_count: int, n_th
     used = lib().vgo_gc_decode_batch(adpcm2d.ctypes.data, nb, coefs.ctypes.data, n_ch, sample_count, out.ctypes.data,
                                      sample_count, n_threads)
     return out, used
+
+
+# ---- CRI ADX (oracle/criadx.c; parity unpinned, see vgoracle.h) ----------------------------------------------------
+ADX_FIXED, ADX_LINEAR, ADX_EXPONENTIAL = 2, 3, 4
+
+
+def adx_coefficients(highpass_freq: int, sample_rate: int) -> np.ndarray:
+    co = np.zeros(2, dtype=np.int16)
+    lib().vgo_adx_calculate_coefficients(highpass_freq, sample_rate, co.ctypes.data)
+    return co
+
+
+def adx_encode(pcm, sample_rate=48000, frame_size=18, version=4, padding=0, type=ADX_LINEAR, filter=0):
+    """CriAdxCodec.Encode -> (adpcm bytes, History written back into the config)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    out = np.zeros(lib().vgo_adx_encoded_byte_count(len(pcm), padding, frame_size), dtype=np.uint8)
+    hist = lib().vgo_adx_encode(pcm.ctypes.data, len(pcm), sample_rate, frame_size, version, padding, type, filter,
+                                out.ctypes.data)
+    return out, hist
+
+
+def adx_decode(adpcm, sample_count, sample_rate=48000, highpass_freq=500, frame_size=18, version=4, history=0,
+               padding=0, type=ADX_LINEAR):
+    adpcm = np.ascontiguousarray(adpcm, dtype=np.uint8)
+    out = np.zeros(sample_count, dtype=np.int16)
+    lib().vgo_adx_decode(adpcm.ctypes.data, sample_count, sample_rate, highpass_freq, frame_size, version, history,
+                         padding, type, out.ctypes.data)
+    return out
+
+
+def adx_encode_frame(pcm_in_out: np.ndarray, coefs, samples_per_frame=32, type=ADX_LINEAR, version=4) -> np.ndarray:
+    assert pcm_in_out.dtype == np.int16 and pcm_in_out.flags.c_contiguous and pcm_in_out.size == samples_per_frame + 2
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    out = np.zeros(samples_per_frame // 2 + 2, dtype=np.uint8)
+    lib().vgo_adx_encode_frame(pcm_in_out.ctypes.data, out.ctypes.data, coefs.ctypes.data, samples_per_frame, type,
+                               version)
+    return out

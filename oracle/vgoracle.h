@@ -69,6 +69,19 @@ int vgo_gc_encode_batch(const int16_t *pcm, int64_t pcm_stride, int n_channels, 
 int vgo_gc_decode_batch(const uint8_t *adpcm, int64_t adpcm_stride, const int16_t *coefs, int n_channels,
                         int sample_count, int16_t *pcm_out, int64_t pcm_stride, int n_threads);
 
+/* ---- CRI ADX (Codecs/CriAdx/CriAdxCodec.cs) — PARITY UNPINNED: the reference has no ADX test at all ---- */
+/* type: 2 Fixed, 3 Linear, 4 Exponential (CriAdxType.cs:3-8) */
+void vgo_adx_calculate_coefficients(int highpass_freq, int sample_rate, int16_t coefs_out[2]); /* :173-184 */
+int vgo_adx_encoded_byte_count(int pcm_length, int padding, int frame_size);
+void vgo_adx_encode_frame(int16_t *pcm, uint8_t *adpcm_out, const int16_t coefs[2], int samples_per_frame, int type,
+                          int version); /* :107-147 */
+/* Encode :56-105; returns the History value the reference writes back into the config (:73) */
+int vgo_adx_encode(const int16_t *pcm, int pcm_length, int sample_rate, int frame_size, int version, int padding,
+                   int type, int filter, uint8_t *adpcm_out);
+/* Decode :9-54 */
+void vgo_adx_decode(const uint8_t *adpcm, int sample_count, int sample_rate, int highpass_freq, int frame_size,
+                    int version, int history, int padding, int type, int16_t *pcm_out);
+
 #ifdef __cplusplus
 }
 #endif

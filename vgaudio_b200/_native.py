@@ -21,6 +21,14 @@ class VgbGcParams(C.Structure):
     _fields_ = [("sample_count", C.c_int32), ("history1", C.c_int16), ("history2", C.c_int16)]
 
 
+class VgbAdxParams(C.Structure):
+    """Mirror of CriAdxParameters (Codecs/CriAdx/CriAdxParameters.cs:3-13)."""
+
+    _fields_ = [("sample_rate", C.c_int32), ("highpass_frequency", C.c_int32), ("frame_size", C.c_int32),
+                ("version", C.c_int32), ("history", C.c_int32), ("padding", C.c_int32), ("type", C.c_int32),
+                ("filter", C.c_int32)]
+
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64)
 
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against include/vgaudio_b200.h
@@ -60,8 +68,13 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
          C.c_void_p],
     ),
+    "vgb_adx_encoded_byte_count": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "vgb_adx_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "vgb_adx_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_gcadpcm_debug_records": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

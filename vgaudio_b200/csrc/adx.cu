@@ -1,0 +1,180 @@
+// adx.cu — CRI ADX 4-bit ADPCM encode / decode on sm_100a.
+//
+// Replaces CriAdxCodec.Encode / EncodeFrame / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171).  Like GC-ADPCM the codec
+// is a serial recurrence per channel (the next frame starts from the reconstructed last two samples, :98-99,:137),
+// but there is no predictor search, so one THREAD owns one channel and the batch supplies the parallelism.  Each
+// frame: residual range against raw neighbours (:112-118), CalculateScale (:149-165), then the quantise /
+// reconstruct recurrence with its one fp64 multiply + truncation per sample (:126).
+// Latency bound (one fp64 multiply, two conversions and ~10 integer ops per sample on the dependent chain);
+// algorithmic traffic 2 B/sample in + frame_size/samples_per_frame B/sample out (2.5625 B/sample at 18-byte frames).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vgb {
+
+// (int)double on x64 is cvttsd2si: out-of-range and NaN give 0x80000000; CUDA's cvt saturates.
+__device__ __forceinline__ int32_t cast_double_to_int_x64(double v)
+{
+    return (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : INT32_MIN;
+}
+
+// ScaleShortToNibble (:167-171): (s + 2340*sign(s)) / 4681 truncating, Clamp4
+__device__ __forceinline__ int32_t adx_short_to_nibble(int32_t s)
+{
+    const int32_t sgn = (s > 0) - (s < 0);
+    return clamp4((s + 2340 * sgn) / 4681);
+}
+
+__global__ void __launch_bounds__(64)
+adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict__ tab, int n_channels,
+                  uint8_t *__restrict__ adpcm, int16_t *__restrict__ history_out)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_channels) return;
+    const AdxChannel c = tab[ch];
+    const int16_t *src = pcm + c.pcm_off;
+    uint8_t *dst = adpcm + c.adpcm_off;
+    const int spf = (c.frame_size - 2) * 2;
+    const int sample_count = c.n_samples + c.padding;            // :59
+    const int frame_count = div_round_up(sample_count, spf);     // :61
+    const int32_t c0 = c.coef0, c1 = c.coef1;
+    const bool v4 = c.version == 4;
+    const bool exponential = c.type == 4;
+
+    int32_t h2 = 0, h1 = 0;  // pcmBuffer[0], pcmBuffer[1]
+    int16_t hist_cfg = 0;
+    if (v4 && c.padding == 0 && c.n_samples > 0) {  // :69-74
+        h2 = h1 = src[0];
+        hist_cfg = src[0];
+    }
+    if (history_out) history_out[ch] = hist_cfg;
+
+    int padding_remaining = c.padding;
+    for (int f = 0; f < frame_count; f++) {
+        int to_copy = min(sample_count - f * spf, spf);  // :78
+        int lead = 0;                                    // zero samples in front (pcmBufferStart - 2)
+        if (padding_remaining != 0) {                    // :80-89
+            const int eat = min(padding_remaining, to_copy);
+            padding_remaining -= eat;
+            to_copy -= eat;
+            lead = eat;
+        }
+        uint8_t *out = dst + (int64_t)f * c.frame_size;
+        if (to_copy == 0 && lead > 0) {  // `continue`: the frame stays all-zero and the history is untouched
+            for (int b = 0; b < c.frame_size; b++) out[b] = 0;
+            continue;
+        }
+        const int64_t first = max((int64_t)f * spf - c.padding, (int64_t)0);  // :90
+        auto sample_at = [&](int i) -> int32_t {  // pcmBuffer[i + 2]
+            const int k = i - lead;
+            return (k >= 0 && k < to_copy) ? (int32_t)__ldg(src + first + k) : 0;
+        };
+
+        // pass 1 (:112-118): neighbours are the RAW samples except for the two history slots
+        int32_t max_distance = 0;
+        {
+            int32_t p0 = h2, p1 = h1;
+            for (int i = 0; i < spf; i++) {
+                const int32_t cur = sample_at(i);
+                const int32_t predicted = (wmul(p1, c0) >> 12) + (wmul(p0, c1) >> 12);
+                const int32_t distance = abs(clamp16(cur - predicted));
+                max_distance = max(max_distance, distance);
+                p0 = p1;
+                p1 = cur;
+            }
+        }
+        // CalculateScale (:149-165)
+        int32_t scale = (max_distance - 1) / 7 + 1;
+        if (scale > 0x1000) scale = 0x1000;
+        int32_t scale_out = scale - 1;
+        if (exponential) {
+            const int power = scale_out == 0 ? 0 : (31 - __clz(scale_out)) + 1;  // Helpers.Log2 = floor(log2)
+            scale = 1 << power;
+            scale_out = 12 - power;
+            max_distance = 8 * scale - 1;
+        }
+        const double gain = max_distance == 0 ? 0.0 : __ddiv_rn(32767.0, (double)max_distance);
+
+        // pass 2 (:122-138): quantise + reconstruct, feeding the reconstruction back
+        uint32_t pair = 0;
+        out[0] = (uint8_t)(((scale_out >> 8) & 0x1f) | (c.type == 2 ? (c.filter << 5) : 0));  // :140, :95
+        out[1] = (uint8_t)scale_out;                                                           // :141
+        for (int i = 0; i < spf; i++) {
+            const int32_t cur = sample_at(i);
+            int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
+            const int32_t raw = cur - predicted;
+            const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
+            const int32_t q = adx_short_to_nibble(scaled);
+            const int32_t decoded_distance = clamp16(wmul(scale, q));
+            if (v4) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
+            const int32_t recon = clamp16(decoded_distance + predicted);
+            h2 = h1;
+            h1 = recon;
+            if (i & 1) out[2 + (i >> 1)] = (uint8_t)(pair | (uint32_t)(q & 0xF));  // CombineNibbles (:145)
+            else pair = (uint32_t)(q << 4) & 0xF0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64)
+adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restrict__ tab, int n_channels,
+                  int16_t *__restrict__ pcm)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_channels) return;
+    const AdxChannel c = tab[ch];
+    const uint8_t *src = adpcm + c.adpcm_off;
+    int16_t *dst = pcm + c.pcm_off;
+    const int spf = (c.frame_size - 2) * 2;
+    const int sample_count = c.n_samples;
+    const int frame_count = div_round_up(sample_count, spf);
+    const bool v4 = c.version == 4;
+    int32_t hist1 = c.history, hist2 = c.history;  // :16-17
+    int current = 0;
+    int start_sample = c.padding > 0 ? c.padding % spf : 0;       // :21
+    int64_t in = (int64_t)(c.padding / spf) * c.frame_size;      // :22
+
+    for (int f = 0; f < frame_count; f++) {
+        const uint32_t b0 = src[in], b1 = src[in + 1];
+        const int filter_num = (int)((b0 >> 4) & 0xF) >> 1;  // :26
+        int32_t c0 = c.coef0, c1 = c.coef1;
+        if (c.type == 2) {  // CriAdxCodec.Coefs (:186-191); the reference throws for filter numbers 4..7
+            const int k = filter_num & 3;
+            c0 = k == 0 ? 0 : (k == 1 ? 0x0F00 : (k == 2 ? 0x1CC0 : 0x1880));
+            c1 = k == 0 ? 0 : (k == 1 ? 0 : (k == 2 ? (int16_t)0xF300 : (int16_t)0xF240));
+        }
+        int32_t scale = (int16_t)(((b0 << 8) | b1) & 0x1FFF);                         // :27
+        scale = (int16_t)(c.type == 4 ? (1 << ((12 - scale) & 31)) : scale + 1);      // :28 (C# masks the shift count)
+        in += 2 + start_sample / 2;
+        const int to_read = min(spf, sample_count - current);
+        for (int s = start_sample; s < to_read; s++) {
+            const uint32_t byte = src[in];
+            int32_t sample = (s & 1) == 0 ? ((int32_t)(byte << 24) >> 28) : ((int32_t)(byte << 28) >> 28);
+            if (s & 1) in++;
+            if (v4) sample = wadd(wmul(scale, sample), wadd(wmul(hist1, c0), wmul(hist2, c1)) >> 12);
+            else sample = wadd(wadd(wmul(scale, sample), wmul(hist1, c0) >> 12), wmul(hist2, c1) >> 12);
+            const int32_t out = clamp16(sample);
+            hist2 = hist1;
+            hist1 = out;
+            dst[current++] = (int16_t)out;
+        }
+        start_sample = 0;
+    }
+    // `new short[sampleCount]` is zero-initialised: samples the padding logic never produces stay 0 (:14,:31-33)
+    for (; current < sample_count; current++) dst[current] = 0;
+}
+
+void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
+                       cudaStream_t stream)
+{
+    if (n_channels <= 0) return;
+    adx_encode_kernel<<<(n_channels + 63) / 64, 64, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out);
+}
+
+void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream)
+{
+    if (n_channels <= 0) return;
+    adx_decode_kernel<<<(n_channels + 63) / 64, 64, 0, stream>>>(adpcm, tab, n_channels, pcm);
+}
+
+}  // namespace vgb

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -84,12 +85,16 @@ struct DevBuf {
 };
 
 constexpr int kTimers = 4;  // 0 coef phase 1, 1 coef refine, 2 encode, 3 decode
+constexpr int kMaxGroups = 4;  // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
 
 struct Context {
     std::mutex mu;
     bool ready = false;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[kMaxGroups] = {};
+    cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_out[kMaxGroups] = {}, ev_t0 = nullptr;
+    int last_groups = 0;
     DevBuf pcm, adpcm, coefs, ws, misc;
     bool timing = false;
     cudaEvent_t ev[2 * kTimers] = {};
@@ -115,6 +120,15 @@ int32_t ensure_ready_locked()
     if (g_ctx.device >= count) return fail(VGB_E_ARG, "device %d out of range (%d devices)", g_ctx.device, count);
     CUDA_TRY(cudaSetDevice(g_ctx.device));
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_out, cudaStreamNonBlocking));
+    for (int g = 0; g < kMaxGroups; g++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_comp[g], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&g_ctx.ev_in[g]));
+        CUDA_TRY(cudaEventCreate(&g_ctx.ev_done[g]));
+        CUDA_TRY(cudaEventCreate(&g_ctx.ev_out[g]));
+    }
+    CUDA_TRY(cudaEventCreate(&g_ctx.ev_t0));
     for (auto &ev : g_ctx.ev) CUDA_TRY(cudaEventCreate(&ev));
     g_ctx.ready = true;
     return VGB_OK;
@@ -258,9 +272,13 @@ void layout_pack_offsets(GcLayout &lay)
 
 // Kernel sequence of one encode call on `stream` (device pointers only).
 int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *d_coefs_in, int16_t *d_coefs_out,
-                      uint8_t *d_adpcm, void *d_ws, const GcWorkspace &w, cudaStream_t stream, bool do_encode)
+                      uint8_t *d_adpcm, void *d_ws, const GcWorkspace &w, cudaStream_t stream, bool do_encode,
+                      bool timed = true, bool tables_uploaded = false)
 {
-    VGB_TRY(upload_tables(lay, w, d_ws, stream));
+    const bool was_timing = g_ctx.timing;
+    if (!timed) g_ctx.timing = false;  // the kernel timers describe single-stream (_dev) calls only
+    struct Restore { bool v; ~Restore() { g_ctx.timing = v; } } restore{was_timing};
+    if (!tables_uploaded) VGB_TRY(upload_tables(lay, w, d_ws, stream));
     if (lay.n_channels == 0) return VGB_OK;
     GcChannelTable tab = table_view(d_ws, w, lay.n_channels);
     char *b = static_cast<char *>(d_ws);
@@ -374,6 +392,33 @@ int32_t copy_channels_out(T *const *h_ptr, const char *d_base, const std::vector
     return VGB_OK;
 }
 
+// Sub-batch of channels [c0, c1) of a validated full layout; offsets stay absolute into the shared slabs, the record
+// slab of the group is its own.
+GcLayout sub_layout(const GcLayout &full, int c0, int c1)
+{
+    GcLayout g;
+    g.n_channels = c1 - c0;
+    g.pcm_off.assign(full.pcm_off.begin() + c0, full.pcm_off.begin() + c1);
+    g.adpcm_off.assign(full.adpcm_off.begin() + c0, full.adpcm_off.begin() + c1);
+    g.n_samples.assign(full.n_samples.begin() + c0, full.n_samples.begin() + c1);
+    g.enc_count.assign(full.enc_count.begin() + c0, full.enc_count.begin() + c1);
+    g.hist.assign(full.hist.begin() + 2 * c0, full.hist.begin() + 2 * c1);
+    g.rec_off.resize(g.n_channels);
+    int64_t rec = 0;
+    for (int c = 0; c < g.n_channels; c++) {
+        const int32_t frames = div_round_up(g.n_samples[c], kGcFrameSamples);
+        g.rec_off[c] = rec;
+        rec += (int64_t)align_up((size_t)frames, 32);
+        if (frames > g.max_frames) g.max_frames = frames;
+        g.total_frames += div_round_up(g.enc_count[c], kGcFrameSamples);
+    }
+    g.rec_total = rec + 32;
+    return g;
+}
+
+// One host call = up to kMaxGroups channel groups pipelined over three kinds of streams: the H2D copy of group g+1,
+// the kernels of group g and the D2H copy of group g-1 overlap (a channel cannot be split in time - its coefficients
+// need all of its samples - but channels are independent).
 int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
                          const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out, uint8_t *const *adpcm_out,
                          vgb_progress_cb cb, void *user, bool do_encode)
@@ -390,37 +435,92 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     }
     layout_pack_offsets(lay);
 
+    // channel groups with roughly equal sample totals (boundaries on channel indices, order preserved)
+    int n_groups = n_channels >= 64 ? kMaxGroups : 1;
+    std::vector<int> bound(n_groups + 1, n_channels);
+    bound[0] = 0;
+    {
+        int64_t total = 0;
+        for (int c = 0; c < n_channels; c++) total += lay.n_samples[c];
+        int64_t run = 0;
+        int g = 1;
+        for (int c = 0; c < n_channels && g < n_groups; c++) {
+            run += lay.n_samples[c];
+            if (run * n_groups >= total * g) bound[g++] = c + 1;
+        }
+    }
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = g_ctx.stream;
-    const GcWorkspace w = carve(lay.rec_total, n_channels);
+    std::vector<GcLayout> glay(n_groups);
+    std::vector<GcWorkspace> gws(n_groups);
+    std::vector<size_t> ws_at(n_groups);
+    size_t ws_total = 0;
+    for (int g = 0; g < n_groups; g++) {
+        glay[g] = sub_layout(lay, bound[g], bound[g + 1]);
+        gws[g] = carve(glay[g].rec_total, glay[g].n_channels);
+        ws_at[g] = ws_total;
+        ws_total += align_up(gws[g].total, 256);
+    }
     VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
     VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
-    VGB_TRY(g_ctx.ws.reserve(w.total));
-
-    std::vector<int64_t> off_b(n_channels), len_b(n_channels);
-    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.pcm_off[c] * 2; len_b[c] = (int64_t)lay.n_samples[c] * 2; }
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), off_b, pcm, len_b, st));
+    VGB_TRY(g_ctx.ws.reserve(ws_total));
+    // make sure nothing of a previous call is still using the buffers
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
 
     int16_t *d_coefs_out = static_cast<int16_t *>(g_ctx.coefs.p);
-    int16_t *d_coefs_in = nullptr;
-    if (coefs_in) {
-        d_coefs_in = d_coefs_out + (size_t)n_channels * 16;
-        CUDA_TRY(cudaMemcpyAsync(d_coefs_in, coefs_in, (size_t)n_channels * 32, cudaMemcpyHostToDevice, st));
+    int16_t *d_coefs_in = coefs_in ? d_coefs_out + (size_t)n_channels * 16 : nullptr;
+
+    CUDA_TRY(cudaEventRecord(g_ctx.ev_t0, g_ctx.s_in));
+    g_ctx.last_groups = n_groups;
+    // stage 1: all H2D copies, in group order, on the input stream (the small tables first, while it is idle, so
+    // that enqueuing the kernels below never has to wait for a pageable-memory copy behind a PCM transfer)
+    for (int g = 0; g < n_groups; g++)
+        VGB_TRY(upload_tables(glay[g], gws[g], static_cast<char *>(g_ctx.ws.p) + ws_at[g], g_ctx.s_in));
+    for (int g = 0; g < n_groups; g++) {
+        const int c0 = bound[g], n = bound[g + 1] - bound[g];
+        std::vector<int64_t> off_b(n), len_b(n);
+        for (int c = 0; c < n; c++) { off_b[c] = lay.pcm_off[c0 + c] * 2; len_b[c] = (int64_t)lay.n_samples[c0 + c] * 2; }
+        VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), off_b, pcm + c0, len_b, g_ctx.s_in));
+        if (coefs_in && n > 0)
+            CUDA_TRY(cudaMemcpyAsync(d_coefs_in + (size_t)c0 * 16, coefs_in + (size_t)c0 * 16, (size_t)n * 32,
+                                     cudaMemcpyHostToDevice, g_ctx.s_in));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_in[g], g_ctx.s_in));
     }
-    VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), lay, d_coefs_in, d_coefs_out,
-                          static_cast<uint8_t *>(g_ctx.adpcm.p), g_ctx.ws.p, w, st, do_encode));
-    CUDA_TRY(cudaMemcpyAsync(coefs_out, d_coefs_out, (size_t)n_channels * 32, cudaMemcpyDeviceToHost, st));
-    if (do_encode) {
-        for (int c = 0; c < n_channels; c++) {
-            off_b[c] = lay.adpcm_off[c];
-            len_b[c] = gc_sample_count_to_byte_count(lay.enc_count[c]);
+    // stage 2: kernels of each group on its own stream, as soon as its PCM has landed
+    for (int g = 0; g < n_groups; g++) {
+        const int c0 = bound[g];
+        cudaStream_t st = g_ctx.s_comp[g];
+        CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_in[g], 0));
+        VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), glay[g],
+                              d_coefs_in ? d_coefs_in + (size_t)c0 * 16 : nullptr, d_coefs_out + (size_t)c0 * 16,
+                              static_cast<uint8_t *>(g_ctx.adpcm.p), static_cast<char *>(g_ctx.ws.p) + ws_at[g], gws[g],
+                              st, do_encode, /*timed=*/false, /*tables_uploaded=*/true));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_done[g], st));
+    }
+    // stage 3: D2H of each group's results on the output stream
+    for (int g = 0; g < n_groups; g++) {
+        const int c0 = bound[g], n = bound[g + 1] - bound[g];
+        CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_done[g], 0));
+        if (n > 0)
+            CUDA_TRY(cudaMemcpyAsync(coefs_out + (size_t)c0 * 16, d_coefs_out + (size_t)c0 * 16, (size_t)n * 32,
+                                     cudaMemcpyDeviceToHost, g_ctx.s_out));
+        if (do_encode) {
+            std::vector<int64_t> off_b(n), len_b(n);
+            for (int c = 0; c < n; c++) {
+                off_b[c] = lay.adpcm_off[c0 + c];
+                len_b[c] = gc_sample_count_to_byte_count(lay.enc_count[c0 + c]);
+            }
+            VGB_TRY(copy_channels_out(adpcm_out + c0, static_cast<const char *>(g_ctx.adpcm.p), off_b, len_b, g_ctx.s_out));
         }
-        VGB_TRY(copy_channels_out(adpcm_out, static_cast<const char *>(g_ctx.adpcm.p), off_b, len_b, st));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_out[g], g_ctx.s_out));
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (cb && do_encode) cb(user, lay.total_frames);
+    // the calling thread reports progress as the groups complete (IProgressReport.ReportAdd deltas sum to SetTotal)
+    for (int g = 0; g < n_groups; g++) {
+        CUDA_TRY(cudaEventSynchronize(g_ctx.ev_out[g]));
+        if (cb && do_encode && glay[g].total_frames > 0) cb(user, glay[g].total_frames);
+    }
     return VGB_OK;
 }
 
@@ -463,6 +563,14 @@ int32_t vgb_shutdown(void)
     }
     cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
+    cudaStreamDestroy(g_ctx.s_in);
+    cudaStreamDestroy(g_ctx.s_out);
+    for (int g = 0; g < kMaxGroups; g++) {
+        cudaStreamDestroy(g_ctx.s_comp[g]);
+        cudaEventDestroy(g_ctx.ev_in[g]);
+        cudaEventDestroy(g_ctx.ev_done[g]);
+        cudaEventDestroy(g_ctx.ev_out[g]);
+    }
     g_ctx.ready = false;
     return VGB_OK;
 }
@@ -698,6 +806,22 @@ int32_t vgb_last_kernel_ms(float *ms_out, int32_t n)
     return VGB_OK;
 }
 
+/* Device timeline of the last host encode call (ms since its first copy was enqueued): for each channel group
+ * [H2D landed, kernels finished, D2H finished].  bench.py prints it as evidence of the copy/compute overlap. */
+int32_t vgb_debug_last_timeline(float *ms_out, int32_t n)
+{
+    if (!ms_out || n < 0) return fail(VGB_E_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    for (int i = 0; i < n; i++) ms_out[i] = -1.0f;
+    if (!g_ctx.ready) return VGB_OK;
+    for (int g = 0; g < g_ctx.last_groups && 3 * g + 2 < n; g++) {
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[3 * g], g_ctx.ev_t0, g_ctx.ev_in[g]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[3 * g + 1], g_ctx.ev_t0, g_ctx.ev_done[g]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[3 * g + 2], g_ctx.ev_t0, g_ctx.ev_out[g]));
+    }
+    return VGB_OK;
+}
+
 int32_t vgb_gcadpcm_debug_records(const int16_t *pcm, int32_t n_samples, double *dir_out, uint8_t *accepted_out)
 {
     if (n_samples < 0 || (!pcm && n_samples > 0) || !dir_out || !accepted_out) return fail(VGB_E_ARG, "bad arguments");
@@ -725,6 +849,146 @@ int32_t vgb_gcadpcm_debug_records(const int16_t *pcm, int32_t n_samples, double 
     CUDA_TRY(cudaMemcpyAsync(mask.data(), b + w.off_mask, mask.size() * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int f = 0; f < frames; f++) accepted_out[f] = (mask[f >> 5] >> (f & 31)) & 1u;
+    return VGB_OK;
+}
+
+// ---- CRI ADX --------------------------------------------------------------------------------------------------
+
+int32_t vgb_adx_encoded_byte_count(int32_t pcm_length, int32_t padding, int32_t frame_size)
+{
+    if (pcm_length < 0 || padding < 0 || frame_size < 3) return 0;
+    const int32_t spf = (frame_size - 2) * 2;
+    return (int32_t)(((int64_t)pcm_length + padding + spf - 1) / spf) * frame_size;
+}
+
+}  // extern "C"
+
+namespace {
+
+// CriAdxCodec.CalculateCoefficients (CriAdxCodec.cs:173-184): host double math, once per distinct (freq, rate).
+// (short)(double) goes through (int) truncation like the oracle.
+void adx_calc_coefs(int highpass, int rate, int16_t &c0, int16_t &c1)
+{
+    const double sqrt2 = std::sqrt(2.0);
+    const double a = sqrt2 - std::cos(2.0 * 3.14159265358979323846 * highpass / rate);
+    const double b = sqrt2 - 1;
+    const double c = (a - std::sqrt((a + b) * (a - b))) / b;
+    c0 = (int16_t)(int32_t)(c * 8192);
+    c1 = (int16_t)(int32_t)(c * c * -4096);
+}
+
+int32_t adx_validate(const vgb_adx_params &p, int c)
+{
+    if (p.frame_size < 3 || p.frame_size > 255) return fail(VGB_E_ARG, "channel %d: frame_size %d outside 3..255", c, p.frame_size);
+    if (p.type != 2 && p.type != 3 && p.type != 4) return fail(VGB_E_ARG, "channel %d: unknown CriAdxType %d", c, p.type);
+    if (p.type == 2 && (p.filter < 0 || p.filter > 3)) return fail(VGB_E_ARG, "channel %d: filter %d outside 0..3", c, p.filter);
+    if (p.padding < 0) return fail(VGB_E_ARG, "channel %d: negative padding", c);
+    if (p.sample_rate <= 0) return fail(VGB_E_ARG, "channel %d: sample_rate must be positive", c);
+    return VGB_OK;
+}
+
+const int16_t kAdxFixed[4][2] = {{0, 0}, {0x0F00, 0}, {0x1CC0, (int16_t)0xF300}, {0x1880, (int16_t)0xF240}};
+
+}  // namespace
+
+extern "C" {
+
+int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
+                             int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out, vgb_progress_cb cb,
+                             void *user)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
+    if (n_channels == 0) return VGB_OK;
+    if (!pcm || !n_samples || !params || !adpcm_out) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<AdxChannel> tab(n_channels);
+    std::vector<int64_t> in_off(n_channels), in_len(n_channels), out_off(n_channels), out_len(n_channels);
+    int64_t ps = 0, ab = 0, frames_total = 0;
+    for (int c = 0; c < n_channels; c++) {
+        const vgb_adx_params &p = params[c];
+        VGB_TRY(adx_validate(p, c));
+        if (n_samples[c] < 0) return fail(VGB_E_ARG, "channel %d: negative sample count", c);
+        // CriAdxCodec.cs:69-74 reads pcm[0]: an empty array throws IndexOutOfRangeException there
+        if (p.version == 4 && p.padding == 0 && n_samples[c] == 0)
+            return fail(VGB_E_ARG, "channel %d: version 4 without padding needs at least one sample", c);
+        if (!pcm[c] && n_samples[c] > 0) return fail(VGB_E_ARG, "pcm[%d] is NULL", c);
+        AdxChannel &t = tab[c];
+        t.pcm_off = ps; t.adpcm_off = ab; t.n_samples = n_samples[c];
+        t.frame_size = p.frame_size; t.version = p.version; t.padding = p.padding; t.type = p.type; t.filter = p.filter;
+        t.history = 0;
+        if (p.type == 2) { t.coef0 = kAdxFixed[p.filter][0]; t.coef1 = kAdxFixed[p.filter][1]; }
+        else adx_calc_coefs(500, p.sample_rate, t.coef0, t.coef1);  // Encode hard-codes 500 (:63)
+        const int32_t bytes = vgb_adx_encoded_byte_count(n_samples[c], p.padding, p.frame_size);
+        if (!adpcm_out[c] && bytes > 0) return fail(VGB_E_ARG, "adpcm_out[%d] is NULL", c);
+        in_off[c] = ps * 2; in_len[c] = (int64_t)n_samples[c] * 2; out_off[c] = ab; out_len[c] = bytes;
+        ps += (int64_t)align_up((size_t)n_samples[c], 8);
+        ab += (int64_t)align_up((size_t)bytes, 16);
+        frames_total += bytes / p.frame_size;
+    }
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
+    VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
+    VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 2));
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
+    launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
+                      static_cast<uint8_t *>(g_ctx.adpcm.p), static_cast<int16_t *>(g_ctx.coefs.p), st);
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (history_out) CUDA_TRY(cudaMemcpyAsync(history_out, g_ctx.coefs.p, (size_t)n_channels * 2, cudaMemcpyDeviceToHost, st));
+    VGB_TRY(copy_channels_out(adpcm_out, static_cast<const char *>(g_ctx.adpcm.p), out_off, out_len, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (cb) cb(user, frames_total);
+    return VGB_OK;
+}
+
+int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
+                             const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
+    if (n_channels == 0) return VGB_OK;
+    if (!adpcm || !n_bytes || !sample_count || !params || !pcm_out) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<AdxChannel> tab(n_channels);
+    std::vector<int64_t> in_off(n_channels), in_len(n_channels), out_off(n_channels), out_len(n_channels);
+    int64_t ps = 0, ab = 0;
+    for (int c = 0; c < n_channels; c++) {
+        const vgb_adx_params &p = params[c];
+        VGB_TRY(adx_validate(p, c));
+        if (sample_count[c] < 0 || n_bytes[c] < 0) return fail(VGB_E_ARG, "channel %d: negative length", c);
+        const int32_t spf = (p.frame_size - 2) * 2;
+        // the reference would index past the array (IndexOutOfRangeException) on a short buffer
+        const int64_t frames = ((int64_t)sample_count[c] + spf - 1) / spf;
+        const int64_t need = ((int64_t)(p.padding / spf) + frames) * p.frame_size;
+        if (sample_count[c] > 0 && n_bytes[c] < need)
+            return fail(VGB_E_ARG, "channel %d: %d bytes of ADX data, %lld needed for %d samples", c, n_bytes[c],
+                        (long long)need, sample_count[c]);
+        if ((!adpcm[c] || !pcm_out[c]) && sample_count[c] > 0) return fail(VGB_E_ARG, "channel %d: NULL buffer", c);
+        AdxChannel &t = tab[c];
+        t.pcm_off = ps; t.adpcm_off = ab; t.n_samples = sample_count[c];
+        t.frame_size = p.frame_size; t.version = p.version; t.padding = p.padding; t.type = p.type; t.filter = p.filter;
+        t.history = (int16_t)p.history;
+        if (p.type == 2) { t.coef0 = 0; t.coef1 = 0; }
+        else adx_calc_coefs(p.highpass_frequency, p.sample_rate, t.coef0, t.coef1);
+        in_off[c] = ab; in_len[c] = sample_count[c] > 0 ? n_bytes[c] : 0; out_off[c] = ps * 2; out_len[c] = (int64_t)sample_count[c] * 2;
+        ps += (int64_t)align_up((size_t)sample_count[c], 8);
+        ab += (int64_t)align_up((size_t)n_bytes[c], 16);
+    }
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
+    VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, adpcm, in_len, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
+    launch_adx_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
+                      static_cast<int16_t *>(g_ctx.pcm.p), st);
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return VGB_OK;
 }
 

@@ -55,4 +55,14 @@ struct GcChannelTable {
     int32_t n_channels;
 };
 
+// One channel of a CRI ADX batch (mirror of CriAdxParameters, Codecs/CriAdx/CriAdxParameters.cs:3-13, plus layout).
+struct AdxChannel {
+    int64_t pcm_off;     // sample offset in the PCM slab
+    int64_t adpcm_off;   // byte offset in the ADPCM slab
+    int32_t n_samples;   // encode: pcm.Length; decode: sampleCount
+    int32_t frame_size, version, padding, type, filter;
+    int32_t history;     // decode only (CriAdxParameters.History)
+    int16_t coef0, coef1;  // fixed-table pair or CalculateCoefficients (host, once per distinct sample rate)
+};
+
 }  // namespace vgb

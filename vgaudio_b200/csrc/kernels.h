@@ -24,4 +24,9 @@ void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, c
 void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, int16_t *pcm,
                       int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
 
+// adx.cu — CriAdxCodec.Encode / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171)
+void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
+                       cudaStream_t stream);
+void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream);
+
 }  // namespace vgb
