@@ -6,14 +6,15 @@
 // RECONSTRUCTED last two samples of frame k, :40-41,:80), channels are independent, and inside a frame the eight
 // predictors are independent while the scale attempts of one predictor form a short chain (:127-170).
 //
-// Mapping: ONE WARP OWNS ONE CHANNEL.  Lane = predictor * 4 + candidate: the 8 predictors are searched in
-// parallel and, for each, 4 consecutive scale powers are evaluated speculatively (every attempt is a pure function
-// of (samples, history, coefs, scalePower), so the do/while chain can be replayed over finished attempts; if the
-// chain would leave the 4-wide window or take the rare overflow "bump" (:166-168) the warp falls back to the
-// literal loop).  The argmin over predictors (strict <, first wins, :66-76) is one REDUX.MIN on an exact integer
-// key; the winner's two newest reconstructed samples are broadcast with one REDUX.MAX.  PCM is staged through
-// shared memory 16 frames at a time with coalesced 16-byte loads (prefetched one chunk ahead), ADPCM bytes are
-// staged and written back 128 bytes at a time.
+// Mapping: ONE HALF-WARP OWNS ONE CHANNEL (two channels per warp).  Lane16 = predictor * 2 + candidate: the 8
+// predictors are searched in parallel and, for each, 2 consecutive scale powers are evaluated speculatively (every
+// attempt is a pure function of (samples, history, coefs, scalePower), so the do/while chain can be replayed over
+// finished attempts; a second round covers two more powers; the rare overflow "bump" (:166-168) falls back to the
+// literal loop).  The argmin over predictors (strict <, first wins, :66-76) is a REDUX.MIN/REDUX.MAX pair on an
+// exact integer key (one per half); the winner's two newest reconstructed samples are broadcast with one SHFL.
+// PCM is staged through shared memory 16 frames at a time with coalesced 16-byte loads (prefetched one chunk
+// ahead), ADPCM bytes are staged and written back 128 bytes at a time.  Two channels per warp halves the instruction
+// issue per channel: 1024 channels occupy 512 warps, at most one per SM sub-partition.
 //
 // The kernel is latency bound: the time of a channel is (frames) x (length of the dependent instruction chain of
 // one frame), so everything here is about shortening that chain:
@@ -165,36 +166,60 @@ __device__ __forceinline__ int gc_first_scale_power(uint32_t key)
     return max(n - 1 - (int)one_less, 0);                        // n <= 1 ? 0 : n - 1
 }
 
-// DspEncodeFrame (:48-94) for one frame by a full warp with the general exact arithmetic and the literal scale loop:
-// the rare path of the channel encoder (a lane failed the exactness test, a scale chain left the speculative window,
-// an overflow bump, or an error too large for the 27-bit argmin key).  Warp-uniform call.  The winner writes the 8
-// frame bytes to out8; returns the winner's biased newest two samples packed like the hot path does.
-__device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1, int32_t h2, int32_t c0, int32_t c1,
-                                               int sp_first, int lane, uint8_t *out8)
+// Per-half-warp reductions.  A warp holds two channels (lanes 0-15 / 16-31); REDUX is warp wide, so the two halves
+// ride on a MIN and a MAX issued back to back with neutral elements for the other half - no divergence, and the
+// second instruction overlaps the first.
+__device__ __forceinline__ void half_min_u32_both(uint32_t v, int half, uint32_t &min0, uint32_t &min1)
 {
-    const int pred = lane >> 2, cand = lane & 3;
+    min0 = __reduce_min_sync(kFull, half == 0 ? v : 0xFFFFFFFFu);  // every lane learns both results, so conditions
+    min1 = ~__reduce_max_sync(kFull, half == 1 ? ~v : 0u);         // on them are warp-uniform without a vote
+}
+__device__ __forceinline__ uint32_t half_min_u32(uint32_t v, int half)
+{
+    uint32_t a, b;
+    half_min_u32_both(v, half, a, b);
+    return half == 0 ? a : b;
+}
+
+// DspEncodeFrame (:48-94) for one frame of each of the warp's two channels with the general exact arithmetic and the
+// literal scale loop: the rare path of the channel encoder (a lane failed the exactness test, a scale chain left the
+// speculative window, an overflow bump).  Warp-uniform call; lane16 = predictor*2 + candidate.  A half with `commit`
+// set writes its 8 frame bytes to out8 and gets its winner's biased newest two samples back (packed like the hot
+// path); the other half's return value is unspecified.
+__device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1, int32_t h2, int32_t c0, int32_t c1,
+                                               int sp_first, int lane, bool commit, uint8_t *out8)
+{
+    const int half = lane >> 4, l16 = lane & 15, pred = l16 >> 1, cand = l16 & 1;
     GcTrial<false> t;
     t.err = 0; t.r1 = 0; t.r2 = 0; t.w0 = 0; t.w1 = 0;
     int sp_final = 0;
-    if (cand == 0) gc_try_predictor_literal<false>(frame, 14, h1, h2, c0, c1, sp_first, t, sp_final);
     const bool pred_winner = cand == 0;
-    const uint64_t full_key = pred_winner ? ((t.err << 5) | (uint64_t)lane) : ~0ull;  // first minimum wins (:66-76)
+    if (pred_winner) gc_try_predictor_literal<false>(frame, 14, h1, h2, c0, c1, sp_first, t, sp_final);
+    const uint64_t full_key = pred_winner ? ((t.err << 4) | (uint64_t)l16) : ~0ull;  // first minimum wins (:66-76)
     const uint32_t hi = (uint32_t)(full_key >> 16);
-    const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+    const uint32_t min_hi = half_min_u32(hi, half);
     const uint32_t lo = (pred_winner && hi == min_hi) ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
-    const uint32_t min_lo = __reduce_min_sync(kFull, lo);
+    const uint32_t min_lo = half_min_u32(lo, half);
     const bool is_winner = pred_winner && hi == min_hi && lo == min_lo;
-    if (is_winner) {
+    if (is_winner && commit) {
         const uint32_t head = (uint32_t)((pred << 4) | (sp_final & 0xF));  // CombineNibbles (:83)
         *reinterpret_cast<uint2 *>(out8) = make_uint2(t.w0 | head, t.w1);
     }
-    return __reduce_max_sync(kFull, is_winner ? ((uint32_t)(t.r1 + 32768) | ((uint32_t)(t.r2 + 32768) << 16)) : 0u);
+    const uint32_t mine = (uint32_t)(t.r1 + 32768) | ((uint32_t)(t.r2 + 32768) << 16);
+    return __shfl_sync(kFull, mine, half * 16 + (int)(min_lo & 15u));
 }
 
-// grid: one warp per channel; encodes frames [frame_begin, frame_end) of every channel, carrying the history
-// in tab.hist between launches (frame_begin must be a multiple of 16).
+// grid: one HALF-WARP per channel (two channels per warp); encodes frames [frame_begin, frame_end) of every channel,
+// carrying the history in tab.hist between launches (frame_begin must be a multiple of 16).
 //
-// The per-frame code below is DspEncodeFrame (:48-94) for a full warp, written as one software-pipelined block:
+// Lane16 = predictor*2 + candidate: the 8 predictors of a channel are searched in parallel and, for each, two
+// consecutive scale powers are evaluated speculatively (every pass is a pure function of (samples, history, coefs,
+// scalePower), so the reference's do/while chain :127-170 is replayed over finished passes).  The reference's first
+// guess is deliberately one power low, so on real signals the chain ends at the first pass in ~11 % and at the
+// second in ~88.6 % of predictor-frames; when a predictor needs a third or fourth pass the warp runs a second round
+// with the candidates moved up by two.
+//
+// The per-frame code is DspEncodeFrame (:48-94), written as one software-pipelined block:
 //   head     residual keys of samples 0,1 (they need the reconstructed history) + the 12 keys computed one frame
 //            ahead -> first scalePower -> this lane's candidate scale and its constants
 //   phase A  the 14-step recurrence at that scale; per sample the dependent chain is
@@ -204,7 +229,7 @@ __device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1,
 //            (guess + q*2^K + 1024) >> 11 == q*2^(K-11) + ((guess + 1024) >> 11) since K >= 11).
 //            The next frame's loads / residual keys ride along as independent work.
 //   phase B  range of raw (maxOverflow), exactness test, squared error, nibble packing
-//   tail     two ballots (chain ends / exactness), one REDUX.MIN for the argmin, one REDUX.MAX to broadcast the
+//   tail     two ballots (chain ends / trouble), MIN+MAX REDUX pair for the two argmins, one SHFL to broadcast each
 //            winner's two newest samples; anything unusual re-runs the frame in gc_slow_frame.
 // Exactness of phase A (tools/quantiser_check.c enumerates the quantiser identity):
 //   * every |diff| < 2^24: float32 holds diff exactly, the pass is bit-identical to the reference cast chain;
@@ -216,33 +241,37 @@ __global__ void __launch_bounds__(kEncWarps * 32)
 gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
                  uint8_t *__restrict__ adpcm, int frame_begin, int frame_end)
 {
-    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][kEncChunkSamples];
-    __shared__ __align__(16) uint8_t out_buf[kEncWarps][kEncChunkFrames * kGcFrameBytes];
+    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][2][kEncChunkSamples];   // [warp][half][buffer]
+    __shared__ __align__(16) uint8_t out_buf[kEncWarps][2][kEncChunkFrames * kGcFrameBytes];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * kEncWarps + warp;
-    if (ch >= tab.n_channels) return;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int pred = l16 >> 1, cand = l16 & 1;
+    const int ch_raw = (blockIdx.x * kEncWarps + warp) * 2 + half;
+    if ((blockIdx.x * kEncWarps + warp) * 2 >= tab.n_channels) return;  // whole warp beyond the batch
+    const bool live = ch_raw < tab.n_channels;                          // odd channel count: upper half idles
+    const int ch = live ? ch_raw : tab.n_channels - 1;
 
-    const int n_enc = tab.enc_count[ch];
+    const int n_enc = live ? tab.enc_count[ch] : 0;
     const int n_frames = div_round_up(n_enc, kGcFrameSamples);
-    const int f_hi = min(frame_end, n_frames);
-    if (frame_begin >= f_hi) return;
+    const int f_hi = min(frame_end, n_frames);                          // this half's end
+    const int f_hi_warp = max(f_hi, __shfl_xor_sync(kFull, f_hi, 16));  // the warp runs until both halves are done
+    if (frame_begin >= f_hi_warp) return;
     const int total_bytes = gc_sample_count_to_byte_count(n_enc);
 
     const int16_t *src = pcm + tab.pcm_off[ch];
     uint8_t *dst = adpcm + tab.adpcm_off[ch];
-    const int pred = lane >> 2, cand = lane & 3;
     const int32_t c0 = coefs[(int64_t)ch * 16 + 2 * pred];
     const int32_t c1 = coefs[(int64_t)ch * 16 + 2 * pred + 1];
     const int32_t nc0 = -c0, nc1 = -c1;
     const int32_t bias_c = wmul(32768, wadd(c0, c1));  // undoes the +32768 bias of both history samples
     int32_t p1 = tab.hist[2 * ch] + 32768, p2 = tab.hist[2 * ch + 1] + 32768;  // biased history (newest, older)
 
-    // 16-byte vector `lane` of a chunk (lanes 0..27), zero beyond the encoded sample count (GcAdpcmEncoder.cs:32-34)
-    auto load_vec = [&](int chunk_frame) -> uint4 {
+    // 16-byte vector v (0..27) of a chunk, zero beyond the encoded sample count (GcAdpcmEncoder.cs:32-34)
+    auto load_vec = [&](int chunk_frame, int v) -> uint4 {
         uint4 q = make_uint4(0, 0, 0, 0);
-        const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + lane * 8;
-        if (lane < kEncChunkSamples / 8 && chunk_frame < f_hi && s < n_enc) {
+        const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + v * 8;
+        if (v < kEncChunkSamples / 8 && chunk_frame < f_hi && s < n_enc) {
             q = __ldg(reinterpret_cast<const uint4 *>(src + s));
             const int valid = (int)min((int64_t)8, (int64_t)n_enc - s);
             if (valid < 8) {
@@ -257,40 +286,63 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         }
         return q;
     };
-    // residual keys of samples 2..13 (raw samples only).  The four candidate lanes of a predictor share the work:
-    // lane `cand` takes samples 2+3*cand .. 4+3*cand, two shuffle-xor steps inside the group of four combine them.
+    auto store_chunk = [&](int b, uint4 va, uint4 vb) {
+        uint4 *d = reinterpret_cast<uint4 *>(in_buf[warp][half][b]);
+        d[l16] = va;
+        if (l16 + 16 < kEncChunkSamples / 8) d[l16 + 16] = vb;
+    };
+    // residual keys of samples 2..13 (raw samples only).  The two candidate lanes of a predictor share the work:
+    // lane `cand` takes samples 2+6*cand .. 7+6*cand, one shuffle-xor combines them.
     auto key_rest_partial = [&](const int16_t *frame) -> uint32_t {
-        const int s0 = 2 + 3 * cand;
-        const int32_t a = frame[s0 - 2], b = frame[s0 - 1], c = frame[s0], d = frame[s0 + 1], e = frame[s0 + 2];
-        return __vimax3_u32(gc_peak_key(a, b, c, c0, c1, s0), gc_peak_key(b, c, d, c0, c1, s0 + 1),
-                            gc_peak_key(c, d, e, c0, c1, s0 + 2));
+        const int s0 = 2 + 6 * cand;
+        int32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = frame[s0 - 2 + j];
+        uint32_t k = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j += 2)
+            k = __vimax3_u32(k, gc_peak_key(v[j], v[j + 1], v[j + 2], c0, c1, s0 + j),
+                             gc_peak_key(v[j + 1], v[j + 2], v[j + 3], c0, c1, s0 + j + 1));
+        return k;
     };
 
     int buf = 0;
-    {
-        const uint4 first = load_vec(frame_begin);
-        if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][0])[lane] = first;
-        __syncwarp();
-    }
+    store_chunk(0, load_vec(frame_begin, l16), load_vec(frame_begin, l16 + 16));
+    __syncwarp();
     // pipeline prologue: samples and residual keys of the first frame
     int32_t x[14];
 #pragma unroll
-    for (int j = 0; j < 14; j++) x[j] = in_buf[warp][0][j];
-    uint32_t key_rest = key_rest_partial(in_buf[warp][0]);
+    for (int j = 0; j < 14; j++) x[j] = in_buf[warp][half][0][j];
+    uint32_t key_rest = key_rest_partial(in_buf[warp][half][0]);
     key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 1));
-    key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 2));
 
-    for (int cf = frame_begin; cf < f_hi; cf += kEncChunkFrames) {
-        const uint4 next = load_vec(cf + kEncChunkFrames);  // prefetch; staged into the other buffer at mid-chunk
-        const int frames_here = min(kEncChunkFrames, f_hi - cf);
-        const int16_t *chunk = in_buf[warp][buf];
-        const int16_t *other = in_buf[warp][buf ^ 1];
+    for (int cf = frame_begin; cf < f_hi_warp; cf += kEncChunkFrames) {
+        // next chunk: pull it into L2 now (no registers held), load it one frame before it is staged into the other
+        // buffer at mid-chunk - the compiler otherwise sinks an early load to its use and exposes DRAM latency
+        {
+            const int64_t s_next = (int64_t)(cf + kEncChunkFrames) * kGcFrameSamples + l16 * 8;
+            if (cf + kEncChunkFrames < f_hi && s_next < n_enc) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + s_next));
+                if (l16 + 16 < kEncChunkSamples / 8 && s_next + 128 < n_enc)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + s_next + 128));
+            }
+        }
+        uint4 next_a = make_uint4(0, 0, 0, 0), next_b = make_uint4(0, 0, 0, 0);
+        const int frames_warp = min(kEncChunkFrames, f_hi_warp - cf);
+        const int frames_here = max(min(kEncChunkFrames, f_hi - cf), 0);  // this half's share
+        const int16_t *chunk = in_buf[warp][half][buf];
+        const int16_t *other = in_buf[warp][half][buf ^ 1];
 
-        for (int i = 0; i < frames_here; i++) {
+        for (int i = 0; i < frames_warp; i++) {
+            if (i == kEncChunkFrames / 2 - 1) {
+                next_a = load_vec(cf + kEncChunkFrames, l16);
+                next_b = load_vec(cf + kEncChunkFrames, l16 + 16);
+            }
             if (i == kEncChunkFrames / 2) {  // the other buffer was last read 8 frames ago: refill it now
-                if (lane < kEncChunkSamples / 8) reinterpret_cast<uint4 *>(in_buf[warp][buf ^ 1])[lane] = next;
+                store_chunk(buf ^ 1, next_a, next_b);
                 __syncwarp();
             }
+            const bool active = i < frames_here;  // a shorter channel idles while its warp mate finishes
             const int16_t *frame = chunk + i * kGcFrameSamples;
             const int16_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
             const int32_t p1_in = p1, p2_in = p2;
@@ -299,120 +351,162 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(p2, p1, x[0], c0, c1, 0, -bias_c),
                                               gc_peak_key(p1, x[0] + 32768, x[1], c0, c1, 1, -bias_c));
             const int sp_first = gc_first_scale_power(key);
-            const int sp_raw = sp_first + cand;
-            const int sp = min(sp_raw, 12);
-            const uint32_t valid = sp_raw <= 12 ? 1u : 0u;
-            const int shift = sp + 11;
-            const int32_t half = (int32_t)(1u << (shift - 1));
-            const int32_t mul = (int32_t)(1u << sp);                             // 2^(shift-11)
-            // tm1 = diff + half - 1 = x*2048 + base_m - c0*p1 - c1*p2 ;  e1 = tm1 - half (its sign bit = diff <= 0)
-            const int32_t base_m = wadd(bias_c, half) - 1;
-            // guess + 1024 - 8*2^shift = c0*p1 + c1*p2 + base_g
-            const int32_t base_g = wsub(wsub(1024, (int32_t)(8u << shift)), bias_c);
-            const int lsh = 32 - shift;
-            const uint32_t near_c = 128u << lsh;
-            const uint32_t near_k = (1u << lsh) + near_c;   // (tn << lsh) + near_c with tn = tm1 + 1
 
-            // ---------------- phase A: recurrence ----------------
-            int32_t tmv[14], rawv[14], qbv[14], obv[14];
+            // results of this lane's best pass so far (round 1 moves unresolved predictors two powers up)
+            uint32_t w0 = 0, w1 = 0, term_bits = 0, trouble_bits = 0, terminal = 0;
+            uint64_t err = 0;
+            int sp = 0;
+            int32_t q1 = p1, q2 = p2;  // newest two reconstructed samples of that pass (biased)
             int32_t xn[14];
             uint32_t key_rest_next = 0;
+            bool resolved = false;     // this lane's predictor already has its chain-ending pass
+
+            // fully unrolled on purpose: in round 0 the next frame's loads/keys must sit in the same straight-line block
+            // as the recurrence to be interleaved with it; the round-1 copy is cold code (about 6 % of the frames)
 #pragma unroll
-            for (int s = 0; s < 14; s++) {
-                const int32_t wt = imad(x[s], 2048, base_m);
-                const int32_t an = imad(p2, nc1, wt);          // p2 terms: one step off the chain
-                const int32_t ah = an - half;
-                const int32_t gn = imad(p2, c1, base_g);
-                const int32_t tm1 = imad(p1, nc0, an);         // diff + half - 1          <- chain
-                const int32_t e1 = imad(p1, nc0, ah);          // diff - 1: negative iff diff <= 0
-                const int32_t wf = imad(p1, c0, gn);           // guess + 1024 - 8*2^shift
-                // round half toward zero: (diff + half - (diff > 0)) >> shift = (tm1 + (diff <= 0)) >> shift
-                const int32_t t2 = tm1 + (int32_t)((uint32_t)e1 >> 31);
-                const int32_t raw = sar(t2, shift);
-                const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);        // clamp4(raw) + 8
-                const int32_t o = imad(qb, mul, wf >> 11);
-                const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);   // clamp16(o) + 32768
-                tmv[s] = tm1; rawv[s] = raw; qbv[s] = qb; obv[s] = ob;
-                p2 = p1;
-                p1 = ob;
-                // independent work for the NEXT frame rides along (software pipelining)
-                if (s == 1) {
+            for (int round = 0; round < 2; round++) {
+                const int sp_raw = sp_first + 2 * round + cand;
+                const int sp_try = min(sp_raw, 12);
+                const uint32_t valid = sp_raw <= 12 ? 1u : 0u;
+                const int shift = sp_try + 11;
+                const int32_t half_q = (int32_t)(1u << (shift - 1));
+                const int32_t mul = (int32_t)(1u << sp_try);                        // 2^(shift-11)
+                // tm1 = diff + half - 1 = x*2048 + base_m - c0*p1 - c1*p2 ;  e1 = tm1 - half (sign bit = diff <= 0)
+                const int32_t base_m = wadd(bias_c, half_q) - 1;
+                // guess + 1024 - 8*2^shift = c0*p1 + c1*p2 + base_g
+                const int32_t base_g = wsub(wsub(1024, (int32_t)(8u << shift)), bias_c);
+                const int lsh = 32 - shift;
+                const uint32_t near_c = 128u << lsh;
+                const uint32_t near_k = (1u << lsh) + near_c;   // (tn << lsh) + near_c with tn = tm1 + 1
+
+                // ---------------- phase A: recurrence ----------------
+                int32_t tmv[14], rawv[14], qbv[14], obv[14];
+                int32_t r1 = p1_in, r2 = p2_in;
 #pragma unroll
-                    for (int j = 0; j < 14; j++) xn[j] = frame_next[j];  // same address in every lane: broadcast
+                for (int s = 0; s < 14; s++) {
+                    const int32_t wt = imad(x[s], 2048, base_m);
+                    const int32_t an = imad(r2, nc1, wt);          // r2 terms: one step off the chain
+                    const int32_t ah = an - half_q;
+                    const int32_t gn = imad(r2, c1, base_g);
+                    const int32_t tm1 = imad(r1, nc0, an);         // diff + half - 1          <- chain
+                    const int32_t e1 = imad(r1, nc0, ah);          // diff - 1: negative iff diff <= 0
+                    const int32_t wf = imad(r1, c0, gn);           // guess + 1024 - 8*2^shift
+                    // round half toward zero: (diff + half - (diff > 0)) >> shift = (tm1 + (diff <= 0)) >> shift
+                    const int32_t t2 = tm1 + (int32_t)((uint32_t)e1 >> 31);
+                    const int32_t raw = sar(t2, shift);
+                    const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);        // clamp4(raw) + 8
+                    const int32_t o = imad(qb, mul, wf >> 11);
+                    const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);   // clamp16(o) + 32768
+                    tmv[s] = tm1; rawv[s] = raw; qbv[s] = qb; obv[s] = ob;
+                    r2 = r1;
+                    r1 = ob;
+                    // independent work for the NEXT frame rides along (software pipelining), first round only
+                    if (round == 0) {
+                        if (s == 1) {
+#pragma unroll
+                            for (int j = 0; j < 14; j++) xn[j] = frame_next[j];  // same address per half: broadcast
+                        }
+                        if (s == 4) key_rest_next = key_rest_partial(frame_next);
+                        if (s == 10) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 1));
+                    }
                 }
-                if (s == 4) key_rest_next = key_rest_partial(frame_next);
-                if (s == 8) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 1));
-                if (s == 12) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 2));
-            }
 
-            // ---------------- phase B ----------------
-            int32_t rmin = 0, rmax = 0;
-            uint32_t nearmin = 0xFFFFFFFFu;
+                // ---------------- phase B ----------------
+                int32_t rmin = 0, rmax = 0;
+                uint32_t nearmin = 0xFFFFFFFFu;
 #pragma unroll
-            for (int s = 0; s < 14; s += 2) {
-                rmin = __vimin3_s32(rmin, rawv[s], rawv[s + 1]);
-                rmax = __vimax3_s32(rmax, rawv[s], rawv[s + 1]);
-            }
+                for (int s = 0; s < 14; s += 2) {
+                    rmin = __vimin3_s32(rmin, rawv[s], rawv[s + 1]);
+                    rmax = __vimax3_s32(rmax, rawv[s], rawv[s + 1]);
+                }
 #pragma unroll
-            for (int s = 0; s < 14; s++) nearmin = __viaddmin_u32((uint32_t)tmv[s] << lsh, near_k, nearmin);
-            // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical path.
-            // maxOverflow (:147-151) is max(rmax - 7, -8 - rmin, 0); only its comparisons are needed.
-            const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
-            const uint32_t big = (uint32_t)(rmax >= big_thr) | (uint32_t)(rmin <= -big_thr);     // some |diff| >= 2^24
-            const uint32_t huge = (uint32_t)(rmax >= huge_thr) | (uint32_t)(rmin <= -huge_thr);  // some |diff| >= 2^29
-            const uint32_t over_ge_240 = (uint32_t)(rmax >= 247) | (uint32_t)(rmin <= -248);
-            const uint32_t over_gt_248 = (uint32_t)(rmax > 255) | (uint32_t)(rmin < -256);
-            const uint32_t over_le_1 = (uint32_t)(rmax <= 8) & (uint32_t)(rmin >= -9);
-            const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | over_ge_240;
-            const uint32_t inexact = valid & (huge | (big & near));
-            const uint32_t terminal = valid & (over_le_1 | (uint32_t)(sp >= 12));  // the while condition (:170) fails
-            const uint32_t bump = valid & (uint32_t)(sp < 12) & over_gt_248;       // the bump loop (:166-168) would run
-            const uint32_t term_bits = __ballot_sync(kFull, terminal != 0u);
-            const uint32_t trouble_bits = __ballot_sync(kFull, (inexact | bump) != 0u);
+                for (int s = 0; s < 14; s++) nearmin = __viaddmin_u32((uint32_t)tmv[s] << lsh, near_k, nearmin);
+                // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical
+                // path.  maxOverflow (:147-151) is max(rmax - 7, -8 - rmin, 0); only its comparisons are needed.
+                const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
+                const uint32_t big = (uint32_t)(rmax >= big_thr) | (uint32_t)(rmin <= -big_thr);     // |diff| >= 2^24
+                const uint32_t huge = (uint32_t)(rmax >= huge_thr) | (uint32_t)(rmin <= -huge_thr);  // |diff| >= 2^29
+                const uint32_t over_ge_240 = (uint32_t)(rmax >= 247) | (uint32_t)(rmin <= -248);
+                const uint32_t over_gt_248 = (uint32_t)(rmax > 255) | (uint32_t)(rmin < -256);
+                const uint32_t over_le_1 = (uint32_t)(rmax <= 8) & (uint32_t)(rmin >= -9);
+                const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | over_ge_240;
+                const bool take = !resolved;  // lanes of resolved predictors keep their round-0 result
+                const uint32_t live_take = valid & (uint32_t)(take && active);
+                const uint32_t inexact = live_take & (huge | (big & near));
+                const uint32_t bump = live_take & (uint32_t)(sp_try < 12) & over_gt_248;  // bump loop (:166-168)
+                // while (:170) fails; an idle half reports "done" so that it never forces a second round
+                const uint32_t term_now = active ? (valid & (over_le_1 | (uint32_t)(sp_try >= 12))) : 1u;
+                terminal = take ? term_now : terminal;
+                term_bits = __ballot_sync(kFull, terminal != 0u);
+                trouble_bits |= __ballot_sync(kFull, (inexact | bump) != 0u);
 
-            // squared error (four partial sums) and nibble packing
-            uint64_t e0 = 0, e1s = 0, e2 = 0, e3 = 0;
-            uint32_t w0 = 0, w1 = 0;
+                // squared error (four partial sums) and nibble packing of this pass: fills the ballot latency;
+                // computed unconditionally and kept with selects (a divergent block would cost more than it saves)
+                uint64_t e0 = 0, e1s = 0, e2 = 0, e3 = 0;
+                uint32_t nw0 = 0, nw1 = 0;
 #pragma unroll
-            for (int s = 0; s < 14; s++) {
-                const int32_t miss = x[s] + 32768 - obv[s];
-                const uint64_t sq = (uint64_t)((int64_t)miss * miss);  // exact; the sum stays below 2^36
-                if ((s & 3) == 0) e0 += sq; else if ((s & 3) == 1) e1s += sq; else if ((s & 3) == 2) e2 += sq; else e3 += sq;
-                const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
-                if (byte < 4) w0 += (uint32_t)qbv[s] << bit; else w1 += (uint32_t)qbv[s] << bit;  // disjoint fields
+                for (int s = 0; s < 14; s++) {
+                    const int32_t miss = x[s] + 32768 - obv[s];
+                    const uint64_t sq = (uint64_t)((int64_t)miss * miss);  // exact; the sum stays below 2^36
+                    if ((s & 3) == 0) e0 += sq; else if ((s & 3) == 1) e1s += sq; else if ((s & 3) == 2) e2 += sq; else e3 += sq;
+                    const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
+                    if (byte < 4) nw0 += (uint32_t)qbv[s] << bit; else nw1 += (uint32_t)qbv[s] << bit;  // disjoint
+                }
+                const uint64_t nerr = (e0 + e1s) + (e2 + e3);
+                err = take ? nerr : err;
+                w0 = take ? (nw0 ^ 0x88888800u) : w0;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8)
+                w1 = take ? (nw1 ^ 0x88888888u) : w1;
+                sp = take ? sp_try : sp;
+                q1 = take ? r1 : q1;
+                q2 = take ? r2 : q2;
+
+                // a predictor (lane pair) none of whose passes ended the chain needs the next two powers
+                const uint32_t pair_done = (term_bits | (term_bits >> 1)) & 0x55555555u;
+                if (pair_done == 0x55555555u) break;       // warp-uniform: every predictor of both channels resolved
+                resolved = (pair_done >> (lane & ~1)) & 1u;
             }
-            const uint64_t err = (e0 + e1s) + (e2 + e3);
-            w0 ^= 0x88888800u;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8); byte 0 is the header
-            w1 ^= 0x88888888u;
 
             // ---------------- tail: replay the scale chain, argmin over predictors ----------------
-            const uint32_t group = (term_bits >> (lane & ~3)) & 0xFu;
-            // a predictor whose four candidates all failed to end the chain leaves the window (all lanes see it)
-            const uint32_t any4 = term_bits | (term_bits >> 1) | (term_bits >> 2) | (term_bits >> 3);
-            const uint32_t pred_winner = terminal & (uint32_t)((group & ((1u << cand) - 1u)) == 0u);  // first that ends
-            // first minimum wins (:66-76): lane = predictor*4 + candidate is monotone in the predictor
+            const uint32_t pair = (term_bits >> (lane & ~1)) & 3u;
+            // a predictor still unresolved after four powers leaves the window: handled as trouble (all lanes see it)
+            const uint32_t pair_done = (term_bits | (term_bits >> 1)) & 0x55555555u;
+            const uint32_t pred_winner = terminal & (uint32_t)(cand == 0 || (pair & 1u) == 0u);  // first that ends
+            // first minimum wins (:66-76): lane16 = predictor*2 + candidate is monotone in the predictor
             const uint32_t e_sat = err < (uint64_t)kErrSat ? (uint32_t)err : kErrSat;
-            const uint32_t key32 = pred_winner ? ((e_sat << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
-            uint32_t best = __reduce_min_sync(kFull, key32);
-            if ((best >> 5) >= kErrSat) {
-                // loud frame (warp-uniform): every candidate error is >= 2^27 - 1, reduce on the full 64-bit value
-                const uint64_t full_key = pred_winner ? ((err << 5) | (uint64_t)lane) : ~0ull;
+            const uint32_t key32 = (pred_winner && active) ? ((e_sat << 4) | (uint32_t)l16) : 0xFFFFFFFFu;
+            uint32_t best0, best1;
+            half_min_u32_both(key32, half, best0, best1);
+            const bool sat0 = (best0 >> 4) >= kErrSat && best0 != 0xFFFFFFFFu;
+            const bool sat1 = (best1 >> 4) >= kErrSat && best1 != 0xFFFFFFFFu;
+            if (sat0 || sat1) {
+                // loud frame (warp-uniform): candidate errors of >= 2^27 - 1, reduce on the full 64-bit value
+                const uint64_t full_key = (pred_winner && active) ? ((err << 4) | (uint64_t)l16) : ~0ull;
                 const uint32_t hi = (uint32_t)(full_key >> 16);
-                const uint32_t min_hi = __reduce_min_sync(kFull, hi);
+                const uint32_t min_hi = half_min_u32(hi, half);
                 const uint32_t lo = hi == min_hi ? (uint32_t)(full_key & 0xFFFFu) : 0xFFFFFFFFu;
-                best = __reduce_min_sync(kFull, lo);  // low 5 bits = winning lane
+                half_min_u32_both(lo, half, best0, best1);  // low 4 bits = winning lane16
             }
-            const int best_lane = (int)(best & 31u);
+            const uint32_t best = half ? best1 : best0;
+            const int best_lane = half * 16 + (int)(best & 15u);
             const uint32_t head = (uint32_t)((pred << 4) | sp);  // CombineNibbles (:83)
-            if (lane == best_lane) *reinterpret_cast<uint2 *>(&out_buf[warp][i * kGcFrameBytes]) = make_uint2(w0 | head, w1);
+            uint8_t *out8 = &out_buf[warp][half][i * kGcFrameBytes];
+            if (lane == best_lane && active) *reinterpret_cast<uint2 *>(out8) = make_uint2(w0 | head, w1);
             // pcmBuffer[0] = pcmBuffer[14]; pcmBuffer[1] = pcmBuffer[15] (:40-41): the winner's two newest samples
-            uint32_t packed = __shfl_sync(kFull, (uint32_t)p1 | ((uint32_t)p2 << 16), best_lane);
-            // anything unusual (warp-uniform, rare): redo the frame with the exact arithmetic and the literal loop
-            if (trouble_bits != 0u || (any4 & 0x11111111u) != 0x11111111u)
-                packed = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane,
-                                       &out_buf[warp][i * kGcFrameBytes]);
-            p1 = (int32_t)(packed & 0xFFFFu);
-            p2 = (int32_t)(packed >> 16);
+            uint32_t packed = __shfl_sync(kFull, (uint32_t)q1 | ((uint32_t)q2 << 16), best_lane);
+            // anything unusual (rare): redo the frame with the exact arithmetic and the literal loop.  Both halves'
+            // status comes from ballots every lane holds, so the branch is warp-uniform without another vote
+            // (an idle half reported every predictor done and raises no trouble flags).
+            const bool trouble0 = (trouble_bits & 0x0000FFFFu) != 0u || (pair_done & 0x00005555u) != 0x00005555u;
+            const bool trouble1 = (trouble_bits & 0xFFFF0000u) != 0u || (pair_done & 0x55550000u) != 0x55550000u;
+            if (trouble0 || trouble1) {
+                const bool mine = (half ? trouble1 : trouble0) && active;
+                const uint32_t redo = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane, mine, out8);
+                if (mine) packed = redo;
+            }
+            if (active) {
+                p1 = (int32_t)(packed & 0xFFFFu);
+                p2 = (int32_t)(packed >> 16);
+            }
 
 #pragma unroll
             for (int j = 0; j < 14; j++) x[j] = xn[j];
@@ -421,15 +515,15 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         __syncwarp();
 
         // write the chunk's bytes; only the channel's last frame can be partial (:38)
-        {
+        if (frames_here > 0) {
             const int64_t byte0 = (int64_t)cf * kGcFrameBytes;
             const int bytes_here = (int)min((int64_t)frames_here * kGcFrameBytes, (int64_t)total_bytes - byte0);
-            if (lane < 8) {
-                const int b = lane * 16;
+            if (l16 < 8) {
+                const int b = l16 * 16;
                 if (b + 16 <= bytes_here) {
-                    *reinterpret_cast<uint4 *>(dst + byte0 + b) = *reinterpret_cast<const uint4 *>(&out_buf[warp][b]);
+                    *reinterpret_cast<uint4 *>(dst + byte0 + b) = *reinterpret_cast<const uint4 *>(&out_buf[warp][half][b]);
                 } else {
-                    for (int j = b; j < bytes_here; j++) dst[byte0 + j] = out_buf[warp][j];
+                    for (int j = b; j < bytes_here; j++) dst[byte0 + j] = out_buf[warp][half][j];
                 }
             }
         }
@@ -437,7 +531,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         buf ^= 1;
     }
 
-    if (lane == 0) {
+    if (l16 == 0 && live) {
         tab.hist[2 * ch] = (int16_t)(p1 - 32768);
         tab.hist[2 * ch + 1] = (int16_t)(p2 - 32768);
     }
@@ -500,7 +594,8 @@ void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16
 {
     if (tab.n_channels <= 0 || max_frames <= 0) return;
     if (frame_begin >= frame_end || frame_begin >= max_frames) return;
-    int blocks = (tab.n_channels + kEncWarps - 1) / kEncWarps;
+    const int per_block = kEncWarps * 2;  // two channels per warp
+    int blocks = (tab.n_channels + per_block - 1) / per_block;
     gc_encode_kernel<<<blocks, kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end);
 }
 
