@@ -269,14 +269,27 @@ __device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blo
         if (COUNT > 1) {
             // ContrastVectors (:335-342); its `val` is r.x and (-rec1*val - rec2) is r.y
             const double ta = 2.0 * r.x, tb = 2.0 * r.y;
-            double least = 1.0e30;
+            // all distances first (independent), then a tournament instead of the reference's sequential scan
+            // (:373-381: `if (tempVal < value)`, value starting at 1.0e30): a later candidate replaces an earlier one
+            // only when strictly smaller, so ties keep the lower index - the same first-minimum rule, depth log2(NB)
+            double d[NB];
+            int idx[NB];
 #pragma unroll
             for (int i = 0; i < NB; i++) {
-                const double d = e0[i] + (ta * e1[i]) + (tb * e2[i]);
-                const bool better = d < least;  // strict: the first minimum wins (:376-380)
-                least = better ? d : least;
-                pick = better ? i : pick;
+                const double di = e0[i] + (ta * e1[i]) + (tb * e2[i]);
+                d[i] = di < 1.0e30 ? di : __longlong_as_double(0x7FF0000000000000ll);  // never wins (also NaN), as in the scan
+                idx[i] = i;
             }
+#pragma unroll
+            for (int step = 1; step < NB; step *= 2) {
+#pragma unroll
+                for (int i = 0; i + step < NB; i += 2 * step) {
+                    const bool right = d[i + step] < d[i];
+                    d[i] = right ? d[i + step] : d[i];
+                    idx[i] = right ? idx[i + step] : idx[i];
+                }
+            }
+            pick = d[0] < 1.0e30 ? idx[0] : 0;  // nothing below the initial 1.0e30: the index stays 0
         }
         uint32_t mine = 0;
 #pragma unroll
@@ -329,7 +342,16 @@ __device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blo
             for (int kk = 0; kk < NB; kk++) mine = my_bucket == kk ? cur_bits[kk] : mine;
             const int n_mine = __popc(mine);
             const double *col = reinterpret_cast<const double *>(queues[b & 1].q[my_bucket & 7]) + my_comp;
-            for (int j = 0; j < n_mine; j++) acc += col[2 * j];
+            // eight queue entries per step: the loads are issued together (entries past the end read as -0.0, the
+            // additive identity), then a pure DADD chain
+            const int n_max = __reduce_max_sync(0xFFFFFFFFu, n_mine);
+            for (int j0 = 0; j0 < n_max; j0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = (j0 + j < n_mine) ? col[2 * (j0 + j)] : -0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc += v[j];
+            }
             hits += n_mine;
 #pragma unroll
             for (int kk = 0; kk < NB; kk++) cur_bits[kk] = next_bits[kk];
