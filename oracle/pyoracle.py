@@ -57,6 +57,18 @@ def lib() -> C.CDLL:
         L.vgo_adx_encode.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp]
         L.vgo_adx_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
         L.vgo_adx_decode.restype = None
+        L.vgo_hca_init.argtypes = [vp, vp]
+        L.vgo_hca_encode.argtypes = [vp, vp, vp, vp]
+        L.vgo_hca_spectra.argtypes = [vp, vp, vp]
+        L.vgo_hca_decode.argtypes = [vp, vp, vp]
+        L.vgo_hca_mdct_run.argtypes = [vp, i32, vp]
+        L.vgo_hca_mdct_run.restype = None
+        L.vgo_hca_imdct_run.argtypes = [vp, i32, vp]
+        L.vgo_hca_imdct_run.restype = None
+        L.vgo_hca_mdct_tables.argtypes = [vp, vp, vp, i32]
+        L.vgo_hca_mdct_tables.restype = None
+        L.vgo_crc16.argtypes = [vp, i32]
+        L.vgo_crc16.restype = C.c_uint16
         _lib = L
     return _lib
 
@@ -162,3 +174,93 @@ def adx_encode_frame(pcm_in_out: np.ndarray, coefs, samples_per_frame=32, type=A
     lib().vgo_adx_encode_frame(pcm_in_out.ctypes.data, out.ctypes.data, coefs.ctypes.data, samples_per_frame, type,
                                version)
     return out
+
+
+# ---- CRI HCA (oracle/crihca.c; tables pinned, frame bytes parity unpinned, non-looping only) -----------------------
+class HcaParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("quality", "bitrate", "limit_bitrate", "channel_count", "sample_rate",
+                                         "sample_count", "looping", "loop_start", "loop_end")]
+
+
+class HcaInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "channel_count", "sample_rate", "sample_count", "frame_count", "inserted_samples", "appended_samples",
+        "header_size", "frame_size", "min_resolution", "max_resolution", "track_count", "channel_config",
+        "total_band_count", "base_band_count", "stereo_band_count", "hfr_band_count", "bands_per_hfr_group",
+        "hfr_group_count", "bitrate")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _chan_table(channels):
+    arrs = [np.ascontiguousarray(c, dtype=np.int16) for c in channels]
+    tab = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return arrs, tab
+
+
+def hca_params(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False) -> HcaParams:
+    return HcaParams(quality, bitrate, int(limit_bitrate), len(channels), sample_rate, len(channels[0]), 0, 0, 0)
+
+
+def hca_init(params: HcaParams) -> HcaInfo:
+    info = HcaInfo()
+    rc = lib().vgo_hca_init(C.byref(params), C.byref(info))
+    if rc:
+        raise ValueError(f"vgo_hca_init failed: {rc}")
+    return info
+
+
+def hca_encode(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False):
+    """CriHcaFormat.EncodeFromPcm16 for one non-looping stream -> (HcaInfo, frames[frame_count, frame_size])."""
+    arrs, tab = _chan_table(channels)
+    p = hca_params(arrs, sample_rate, quality, bitrate, limit_bitrate)
+    info = hca_init(p)
+    frames = np.zeros((info.frame_count, info.frame_size), dtype=np.uint8)
+    rc = lib().vgo_hca_encode(tab, C.byref(p), C.byref(info), frames.ctypes.data)
+    if rc:
+        raise ValueError(f"vgo_hca_encode failed: {rc}")
+    return info, frames
+
+
+def hca_spectra(channels, sample_rate=48000, quality=2, bitrate=0):
+    arrs, tab = _chan_table(channels)
+    p = hca_params(arrs, sample_rate, quality, bitrate)
+    info = hca_init(p)
+    out = np.zeros((info.frame_count, info.channel_count, 8, 128))
+    lib().vgo_hca_spectra(tab, C.byref(p), out.ctypes.data)
+    return out
+
+
+def hca_decode(info: HcaInfo, frames) -> np.ndarray:
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    out = np.zeros((info.channel_count, info.sample_count), dtype=np.int16)
+    tab = (C.c_void_p * info.channel_count)(*[out[c].ctypes.data for c in range(info.channel_count)])
+    lib().vgo_hca_decode(C.byref(info), frames.ctypes.data, tab)
+    return out
+
+
+def hca_mdct(blocks: np.ndarray) -> np.ndarray:
+    blocks = np.ascontiguousarray(blocks, dtype=np.float64).reshape(-1, 128)
+    out = np.zeros_like(blocks)
+    lib().vgo_hca_mdct_run(blocks.ctypes.data, len(blocks), out.ctypes.data)
+    return out
+
+
+def hca_imdct(spectra: np.ndarray) -> np.ndarray:
+    spectra = np.ascontiguousarray(spectra, dtype=np.float64).reshape(-1, 128)
+    out = np.zeros_like(spectra)
+    lib().vgo_hca_imdct_run(spectra.ctypes.data, len(spectra), out.ctypes.data)
+    return out
+
+
+def hca_mdct_tables(bits: int):
+    n = 1 << bits
+    s, c, sh = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+    lib().vgo_hca_mdct_tables(s.ctypes.data, c.ctypes.data, sh.ctypes.data, bits)
+    return s, c, sh
+
+
+def crc16(data: bytes) -> int:
+    buf = np.frombuffer(data, dtype=np.uint8)
+    return int(lib().vgo_crc16(buf.ctypes.data, len(buf)))

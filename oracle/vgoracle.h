@@ -82,6 +82,30 @@ int vgo_adx_encode(const int16_t *pcm, int pcm_length, int sample_rate, int fram
 void vgo_adx_decode(const uint8_t *adpcm, int sample_count, int sample_rate, int highpass_freq, int frame_size,
                     int version, int history, int padding, int type, int16_t *pcm_out);
 
+/* ---- CRI HCA (Codecs/CriHca, Utilities/Mdct.cs) — tables pinned by the reference's test literals, frame bytes
+ * PARITY UNPINNED (the reference never runs its encoder/decoder in a test); non-looping streams only ---- */
+typedef struct vgo_hca_params { /* CriHcaParameters.cs:3-15 (+ CodecParameters.SampleCount) */
+    int32_t quality;       /* CriHcaQuality: 0 NotSet, 1 Highest, 2 High, 3 Middle, 4 Low, 5 Lowest */
+    int32_t bitrate;       /* 0 = derive from quality */
+    int32_t limit_bitrate;
+    int32_t channel_count, sample_rate, sample_count;
+    int32_t looping, loop_start, loop_end;
+} vgo_hca_params;
+typedef struct vgo_hca_info { /* HcaInfo.cs:5-48, the fields the codec uses */
+    int32_t channel_count, sample_rate, sample_count, frame_count, inserted_samples, appended_samples;
+    int32_t header_size, frame_size, min_resolution, max_resolution, track_count, channel_config;
+    int32_t total_band_count, base_band_count, stereo_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
+    int32_t bitrate;
+} vgo_hca_info;
+int vgo_hca_init(const vgo_hca_params *p, vgo_hca_info *info_out);              /* CriHcaEncoder.Initialize :61-114 */
+int vgo_hca_encode(const int16_t *const *pcm, const vgo_hca_params *p, vgo_hca_info *info_out, uint8_t *frames_out);
+int vgo_hca_spectra(const int16_t *const *pcm, const vgo_hca_params *p, double *spectra_out);
+int vgo_hca_decode(const vgo_hca_info *h, const uint8_t *frames, int16_t *const *pcm_out); /* CriHcaDecoder.Decode :11-25 */
+void vgo_hca_mdct_run(const double *blocks, int n, double *spectra_out);         /* Mdct.RunMdct :63-92, state from zero */
+void vgo_hca_imdct_run(const double *spectra, int n, double *blocks_out);        /* Mdct.RunImdct :94-119 */
+void vgo_hca_mdct_tables(double *sin_out, double *cos_out, int *shuffle_out, int bits); /* :183-208 */
+uint16_t vgo_crc16(const uint8_t *data, int size);                               /* Crc16.Compute, poly 0x8005 */
+
 #ifdef __cplusplus
 }
 #endif
