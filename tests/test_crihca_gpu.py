@@ -1,0 +1,77 @@
+"""GPU parity tests for the CRI HCA encoder: CUDA frames (through the C ABI) against the CPU oracle.
+
+north_star asks for <= 1e-5 RMS on HCA's float path; because the kernel keeps fp64 and the reference's operation order
+the frames are expected to be BYTE-IDENTICAL to the oracle, which is what is asserted (the RMS criterion - oracle-decoded
+PCM of GPU frames vs of oracle frames, normalised to full scale - is then trivially 0 and checked as well)."""
+import numpy as np
+import pytest
+
+from vgaudio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _streams(n_streams, nch, n, first=100):
+    return [[synth.channel(first + s * nch + c, n, degenerate=False) for c in range(nch)] for s in range(n_streams)]
+
+
+@pytest.mark.parametrize("nch,quality", [(1, 2), (2, 2), (1, 1), (2, 5), (1, 5), (2, 3), (3, 4), (6, 2), (8, 5)])
+def test_frames_byte_identical_to_oracle(vg, oracle, nch, quality):
+    n = 20000
+    streams = _streams(3, nch, n)
+    cfg = vg.crihca.CriHcaParameters(quality=quality)
+    infos, frames = vg.crihca.encode_batch(streams, 48000, cfg)
+    for s in range(3):
+        o_info, o_frames = oracle.hca_encode(streams[s], 48000, quality)
+        assert infos[s].as_dict() == o_info.as_dict()
+        same = (frames[s] == o_frames).all(axis=1)
+        assert same.all(), f"{int((~same).sum())} of {len(same)} frames differ (first {int(np.argmin(same))})"
+        dec_g = oracle.hca_decode(o_info, frames[s]).astype(np.float64)
+        dec_o = oracle.hca_decode(o_info, o_frames).astype(np.float64)
+        assert np.sqrt(((dec_g - dec_o) ** 2).mean()) / 32768 <= 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1023, 1024, 1025, 2047, 5000])
+def test_edge_lengths(vg, oracle, n):
+    streams = [[synth.channel(40 + i, max(n, 1))[:n]] for i in range(4)]
+    infos, frames = vg.crihca.encode_batch(streams, 44100)
+    for s in range(4):
+        o_info, o_frames = oracle.hca_encode(streams[s], 44100)
+        assert infos[s].as_dict() == o_info.as_dict()
+        assert np.array_equal(frames[s], o_frames), (n, s)
+
+
+def test_ragged_batch_and_degenerate_signals(vg, oracle):
+    lens = [3000, 48000, 1, 10240, 7777]
+    sigs = [np.zeros(lens[0], np.int16), synth.channel(1, lens[1]), synth.channel(5, lens[2]),
+            synth.reference_sine(lens[3], 440, 48000), synth.reference_ramp(0, lens[4])]
+    streams = [[s] for s in sigs]
+    infos, frames = vg.crihca.encode_batch(streams, 48000, vg.crihca.CriHcaParameters(quality=vg.crihca.HIGHEST))
+    for i in range(len(streams)):
+        o_info, o_frames = oracle.hca_encode(streams[i], 48000, 1)
+        assert np.array_equal(frames[i], o_frames), i
+
+
+def test_custom_bitrate_and_limit(vg, oracle):
+    streams = _streams(2, 2, 9000)
+    cfg = vg.crihca.CriHcaParameters(bitrate=64000, limit_bitrate=True)
+    infos, frames = vg.crihca.encode_batch(streams, 48000, cfg)
+    for s in range(2):
+        o_info, o_frames = oracle.hca_encode(streams[s], 48000, 2, 64000, True)
+        assert infos[s].as_dict() == o_info.as_dict()
+        assert np.array_equal(frames[s], o_frames)
+
+
+def test_query_matches_c4_numbers(vg):
+    info = vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=1, sample_rate=48000, sample_count=1440000))
+    assert (info.bitrate, info.frame_size, info.frame_count, info.total_band_count) == (128000, 341, 1407, 128)
+
+
+def test_errors(vg):
+    with pytest.raises(vg.VgbError):   # > 8 channels: ArgumentOutOfRangeException (CriHcaEncoder.cs:63-66)
+        vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=9, sample_rate=48000, sample_count=100))
+    with pytest.raises(vg.VgbError):   # looping not implemented in round 1
+        vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=1, sample_rate=48000, sample_count=100, looping=True))
+    with pytest.raises(vg.VgbError) as e:  # "Bitrate is set too low." (CriHcaEncoder.cs:469-472)
+        vg.crihca.encode([synth.channel(7, 5000)], 48000, vg.crihca.CriHcaParameters(bitrate=900))
+    assert e.value.code == -2

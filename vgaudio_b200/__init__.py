@@ -6,4 +6,4 @@ Host-side mirror of the reference's interface for that path (names follow the re
 All arithmetic runs in libvgaudio_b200.so (CUDA, sm_100a) through the C ABI in include/vgaudio_b200.h.
 """
 from ._native import VgbError, lib  # noqa: F401  (fails loudly when the native library is missing)
-from . import gcadpcm, criadx, formats  # noqa: F401
+from . import gcadpcm, criadx, crihca, formats  # noqa: F401

@@ -29,6 +29,26 @@ class VgbAdxParams(C.Structure):
                 ("filter", C.c_int32)]
 
 
+class VgbHcaParams(C.Structure):
+    """Mirror of CriHcaParameters (Codecs/CriHca/CriHcaParameters.cs:3-15)."""
+
+    _fields_ = [(n, C.c_int32) for n in ("quality", "bitrate", "limit_bitrate", "channel_count", "sample_rate",
+                                         "sample_count", "looping", "loop_start", "loop_end")]
+
+
+class VgbHcaInfo(C.Structure):
+    """The HcaInfo fields the codec uses (Codecs/CriHca/HcaInfo.cs:5-48)."""
+
+    _fields_ = [(n, C.c_int32) for n in (
+        "channel_count", "sample_rate", "sample_count", "frame_count", "inserted_samples", "appended_samples",
+        "header_size", "frame_size", "min_resolution", "max_resolution", "track_count", "channel_config",
+        "total_band_count", "base_band_count", "stereo_band_count", "hfr_band_count", "bands_per_hfr_group",
+        "hfr_group_count", "bitrate")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64)
 
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against include/vgaudio_b200.h
@@ -72,6 +92,8 @@ SIGNATURES = {
     "vgb_adx_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "vgb_adx_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_hca_query": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "vgb_hca_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -992,4 +992,302 @@ int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes
     return VGB_OK;
 }
 
+// ---- CRI HCA --------------------------------------------------------------------------------------------------
+
+}  // extern "C"
+
+namespace {
+
+#include "hca_tables.inc"
+
+// Extensions.DivideByRoundUp for non-negative ints
+inline int hca_div_up(int a, int b) { return (int)std::ceil((double)a / b); }
+inline int hca_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+inline int hca_next_multiple(int v, int m) { if (m <= 0) return v; if (v % m == 0) return v; return v + m - v % m; }
+
+// CriHcaEncoder.Initialize (CriHcaEncoder.cs:61-114, non-looping) = CalculateBitrate :288-324,
+// CalculateBandCounts :326-368, HcaInfo.CalculateHfrValues (HcaInfo.cs:50-56), SetChannelConfiguration :370-381,
+// CalculateHeaderSize :400-418.  Integer/`Math.Round` logic only (half-to-even = nearbyint).
+int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h)
+{
+    if (p.channel_count > 8)
+        return fail(VGB_E_ARG, "HCA channel count must be 8 or below");
+    if (p.channel_count < 1) return fail(VGB_E_ARG, "HCA channel count must be at least 1");
+    if (p.sample_rate <= 0 || p.sample_count < 0) return fail(VGB_E_ARG, "bad sample rate / sample count");
+    if (p.looping) return fail(VGB_E_ARG, "looping HCA streams are not implemented yet (round 1 covers non-looping encode)");
+    std::memset(&h, 0, sizeof h);
+    const int cutoff0 = p.sample_rate / 2;
+    h.channel_count = p.channel_count;
+    h.track_count = 1;
+    h.sample_count = p.sample_count;
+    h.sample_rate = p.sample_rate;
+    h.min_resolution = 1;
+    h.max_resolution = 15;
+    h.inserted_samples = 128;
+
+    const int pcm_bitrate = h.sample_rate * h.channel_count * 16;
+    {
+        const int max_bitrate = pcm_bitrate / 4;
+        int min_bitrate = 0, ratio = 6;
+        switch (p.quality) {
+        case 1: ratio = 4; break;
+        case 2: ratio = 6; break;
+        case 3: ratio = 8; break;
+        case 4: ratio = h.channel_count == 1 ? 10 : 12; break;
+        case 5: ratio = h.channel_count == 1 ? 12 : 16; break;
+        default: break;
+        }
+        int bitrate = p.bitrate != 0 ? p.bitrate : pcm_bitrate / ratio;
+        if (p.limit_bitrate) min_bitrate = std::min(h.channel_count == 1 ? 42666 : 32000 * h.channel_count, pcm_bitrate / 6);
+        h.bitrate = hca_clampi(bitrate, min_bitrate, max_bitrate);
+    }
+    if (h.bitrate <= 0) return fail(VGB_E_ARG, "bitrate must be positive");
+    {
+        const int bitrate = h.bitrate;
+        int cutoff = cutoff0;
+        h.frame_size = (int)((int64_t)bitrate * 1024 / h.sample_rate / 8);
+        int hfr_ratio, cutoff_ratio;
+        if (h.channel_count <= 1 || pcm_bitrate / bitrate <= 6) { hfr_ratio = 6; cutoff_ratio = 12; }
+        else { hfr_ratio = 8; cutoff_ratio = 16; }
+        if (bitrate < pcm_bitrate / cutoff_ratio) cutoff = std::min(cutoff, cutoff_ratio * bitrate / (32 * h.channel_count));
+        const int total = (int)std::nearbyint(cutoff * 256.0 / h.sample_rate);
+        const double hs = std::nearbyint((hfr_ratio * (double)bitrate * 128.0) / pcm_bitrate);
+        const int hfr_start = (int)std::min((double)total, hs);
+        const int stereo_start = hfr_ratio == 6 ? hfr_start : (hfr_start + 1) / 2;
+        const int hfr_bands = total - hfr_start;
+        const int per_group = hca_div_up(hfr_bands, 8);
+        int groups = 0;
+        if (per_group > 0) groups = hca_div_up(hfr_bands, per_group);
+        h.total_band_count = total;
+        h.base_band_count = stereo_start;
+        h.stereo_band_count = hfr_start - stereo_start;
+        h.hfr_group_count = groups;
+        h.bands_per_hfr_group = per_group;
+    }
+    if (h.frame_size < 8) return fail(VGB_E_DATA, "Bitrate is set too low.");
+    if (h.bands_per_hfr_group > 0) {
+        h.hfr_band_count = h.total_band_count - h.base_band_count - h.stereo_band_count;
+        h.hfr_group_count = hca_div_up(h.hfr_band_count, h.bands_per_hfr_group);
+    }
+    {
+        const int per_track = h.channel_count / h.track_count;
+        const int config = kHcaDefaultChannelMapping[per_track];
+        if (kHcaValidChannelMappings[per_track - 1][config] != 1) return fail(VGB_E_ARG, "Channel mapping is not valid.");
+        h.channel_config = config;
+    }
+    h.header_size = hca_next_multiple(96, 32);
+    const int total_samples = h.sample_count + h.inserted_samples;
+    h.frame_count = hca_div_up(total_samples, 1024);
+    h.appended_samples = h.frame_count * 1024 - h.inserted_samples - h.sample_count;
+    return VGB_OK;
+}
+
+// CriHcaFrame.GetChannelTypes (CriHcaFrame.cs:34-52)
+void hca_channel_types(const vgb_hca_info &h, int32_t types[8])
+{
+    static const int t2[] = {1, 2}, t3[] = {1, 2, 0}, t4a[] = {1, 2, 0, 0}, t4b[] = {1, 2, 1, 2}, t5a[] = {1, 2, 0, 0, 0},
+                     t5b[] = {1, 2, 0, 1, 2}, t6[] = {1, 2, 0, 0, 1, 2}, t7[] = {1, 2, 0, 0, 1, 2, 0},
+                     t8[] = {1, 2, 0, 0, 1, 2, 1, 2};
+    for (int i = 0; i < 8; i++) types[i] = 0;
+    const int per_track = h.channel_count / h.track_count;
+    if (h.stereo_band_count == 0 || per_track == 1) return;
+    const int *src = nullptr;
+    switch (per_track) {
+    case 2: src = t2; break;
+    case 3: src = t3; break;
+    case 4: src = h.channel_config != 0 ? t4a : t4b; break;
+    case 5: src = h.channel_config > 2 ? t5a : t5b; break;
+    case 6: src = t6; break;
+    case 7: src = t7; break;
+    case 8: src = t8; break;
+    default: return;
+    }
+    for (int i = 0; i < per_track; i++) types[i] = src[i];
+}
+
+// One-time upload of the codec tables (per process/device).  Trig tables: Mdct.GenerateTrigTables (Mdct.cs:183-195)
+// with the host libm, exactly as the oracle builds them; dead zones: CriHcaTables.QuantizerDeadZoneFunction (:68-78).
+struct HcaTableStore {
+    bool ready = false;
+    void *blob = nullptr;
+    HcaTables view{};
+} g_hca_tables;
+
+int32_t hca_tables_ready_locked()
+{
+    if (g_hca_tables.ready) return VGB_OK;
+    std::vector<unsigned char> host;
+    auto put = [&](const void *src, size_t bytes) { size_t at = align_up(host.size(), 16); host.resize(at + bytes); std::memcpy(host.data() + at, src, bytes); return at; };
+    const size_t o_window = put(kHcaMdctWindow, sizeof kHcaMdctWindow);
+    size_t o_sin[8], o_cos[8];
+    for (int bits = 0; bits <= 7; bits++) {
+        const int size = 1 << bits;
+        std::vector<double> sn(size), cs(size);
+        for (int i = 0; i < size; i++) {
+            const double value = 3.14159265358979323846 * (4 * i + 1) / (4 * size);
+            sn[i] = std::sin(value);
+            cs[i] = std::cos(value);
+        }
+        o_sin[bits] = put(sn.data(), size * sizeof(double));
+        o_cos[bits] = put(cs.data(), size * sizeof(double));
+    }
+    int32_t shuffle[128];
+    for (int i = 0; i < 128; i++) {
+        unsigned v = (unsigned)(i ^ (i / 2));
+        v = ((v & 0xaaaaaaaau) >> 1) | ((v & 0x55555555u) << 1);
+        v = ((v & 0xccccccccu) >> 2) | ((v & 0x33333333u) << 2);
+        v = ((v & 0xf0f0f0f0u) >> 4) | ((v & 0x0f0f0f0fu) << 4);
+        v = ((v & 0xff00ff00u) >> 8) | ((v & 0x00ff00ffu) << 8);
+        v = (v >> 16) | (v << 16);
+        shuffle[i] = (int32_t)(v >> (32 - 7));
+    }
+    const size_t o_shuffle = put(shuffle, sizeof shuffle);
+    const size_t o_deq = put(kHcaDequantizerScaling, sizeof kHcaDequantizerScaling);
+    const size_t o_qs = put(kHcaQuantizerScaling, sizeof kHcaQuantizerScaling);
+    const size_t o_inv = put(kHcaQuantizerInverseStepSize, sizeof kHcaQuantizerInverseStepSize);
+    double dead[16];
+    for (int i = 0; i < 16; i++) {
+        const int steps = (i < 8 ? i : (1 << (i - 4)) - 1) + 1;
+        double boundary = kHcaQuantizerStepSize[i] / 2;
+        int64_t bits;
+        std::memcpy(&bits, &boundary, 8);
+        bits -= steps;
+        std::memcpy(&dead[i], &bits, 8);
+    }
+    const size_t o_dead = put(dead, sizeof dead);
+    const size_t o_bounds = put(kHcaIntensityRatioBounds, sizeof kHcaIntensityRatioBounds);
+    const size_t o_s2r = put(kHcaScaleToResolutionCurve, sizeof kHcaScaleToResolutionCurve);
+    const size_t o_maxbits = put(kHcaQuantizedSpectrumMaxBits, sizeof kHcaQuantizedSpectrumMaxBits);
+    const size_t o_qbits = put(kHcaQuantizeSpectrumBits, sizeof kHcaQuantizeSpectrumBits);
+    const size_t o_qval = put(kHcaQuantizeSpectrumValue, sizeof kHcaQuantizeSpectrumValue);
+    uint16_t crc[256];
+    for (int i = 0; i < 256; i++) {
+        uint16_t cur = (uint16_t)(i << 8);
+        for (int j = 0; j < 8; j++) {
+            const bool x = (cur & 0x8000) != 0;
+            cur = (uint16_t)(cur << 1);
+            if (x) cur ^= 0x8005;
+        }
+        crc[i] = cur;
+    }
+    const size_t o_crc = put(crc, sizeof crc);
+
+    CUDA_TRY(cudaMalloc(&g_hca_tables.blob, host.size()));
+    CUDA_TRY(cudaMemcpy(g_hca_tables.blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+    const char *b = static_cast<const char *>(g_hca_tables.blob);
+    HcaTables &T = g_hca_tables.view;
+    T.window = reinterpret_cast<const double *>(b + o_window);
+    for (int bits = 0; bits <= 7; bits++) {
+        T.sin_tab[bits] = reinterpret_cast<const double *>(b + o_sin[bits]);
+        T.cos_tab[bits] = reinterpret_cast<const double *>(b + o_cos[bits]);
+    }
+    T.shuffle = reinterpret_cast<const int32_t *>(b + o_shuffle);
+    T.mdct_scale = std::sqrt(2.0 / 128);
+    T.sqrt2 = std::sqrt(2.0);
+    T.dequantizer_scaling = reinterpret_cast<const double *>(b + o_deq);
+    T.quantizer_scaling = reinterpret_cast<const double *>(b + o_qs);
+    T.inv_step = reinterpret_cast<const double *>(b + o_inv);
+    T.dead_zone = reinterpret_cast<const double *>(b + o_dead);
+    T.intensity_bounds = reinterpret_cast<const double *>(b + o_bounds);
+    T.scale_to_resolution = reinterpret_cast<const uint8_t *>(b + o_s2r);
+    T.quantized_max_bits = reinterpret_cast<const uint8_t *>(b + o_maxbits);
+    T.quantize_bits = reinterpret_cast<const uint8_t(*)[16]>(b + o_qbits);
+    T.quantize_value = reinterpret_cast<const uint8_t(*)[16]>(b + o_qval);
+    T.crc_table = reinterpret_cast<const uint16_t *>(b + o_crc);
+    g_hca_tables.ready = true;
+    return VGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vgb_hca_query(const vgb_hca_params *params, vgb_hca_info *info_out)
+{
+    if (!params || !info_out) return fail(VGB_E_ARG, "NULL argument");
+    return hca_initialize(*params, *info_out);
+}
+
+int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
+                             vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user)
+{
+    if (n_streams < 0) return fail(VGB_E_ARG, "n_streams is negative");
+    if (n_streams == 0) return VGB_OK;
+    if (!pcm || !params || !frames_out) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<vgb_hca_info> infos(n_streams);
+    for (int s = 0; s < n_streams; s++) {
+        VGB_TRY(hca_initialize(params[s], infos[s]));
+        const vgb_hca_params &a = params[0], &b = params[s];
+        if (a.channel_count != b.channel_count || a.sample_rate != b.sample_rate || a.quality != b.quality ||
+            a.bitrate != b.bitrate || a.limit_bitrate != b.limit_bitrate)
+            return fail(VGB_E_ARG, "stream %d: all streams of one call must share channel count, sample rate, quality and bitrate", s);
+    }
+    const vgb_hca_info &h0 = infos[0];
+    const int nch = h0.channel_count;
+    HcaConfig cfg{};
+    cfg.channel_count = nch;
+    cfg.frame_size = h0.frame_size;
+    cfg.base_band_count = h0.base_band_count;
+    cfg.stereo_band_count = h0.stereo_band_count;
+    cfg.total_band_count = h0.total_band_count;
+    cfg.hfr_band_count = h0.hfr_band_count;
+    cfg.bands_per_hfr_group = h0.bands_per_hfr_group;
+    cfg.hfr_group_count = h0.hfr_group_count;
+    hca_channel_types(h0, cfg.channel_type);
+
+    std::vector<HcaStream> streams(n_streams);
+    std::vector<int64_t> in_off((size_t)n_streams * nch), in_len((size_t)n_streams * nch), out_off(n_streams), out_len(n_streams);
+    int64_t ps = 0, fb = 0, frames_total = 0;
+    int max_frames = 0;
+    for (int s = 0; s < n_streams; s++) {
+        const int64_t stride = (int64_t)align_up((size_t)infos[s].sample_count, 8);
+        streams[s].pcm_off = ps;
+        streams[s].channel_stride = stride;
+        streams[s].frames_off = fb;
+        streams[s].sample_count = infos[s].sample_count;
+        streams[s].frame_count = infos[s].frame_count;
+        for (int c = 0; c < nch; c++) {
+            if (!pcm[(size_t)s * nch + c] && infos[s].sample_count > 0) return fail(VGB_E_ARG, "pcm[%d][%d] is NULL", s, c);
+            in_off[(size_t)s * nch + c] = (ps + c * stride) * 2;
+            in_len[(size_t)s * nch + c] = (int64_t)infos[s].sample_count * 2;
+        }
+        ps += stride * nch;
+        out_off[s] = fb;
+        out_len[s] = (int64_t)infos[s].frame_count * infos[s].frame_size;
+        if (!frames_out[s] && out_len[s] > 0) return fail(VGB_E_ARG, "frames_out[%d] is NULL", s);
+        fb += (int64_t)align_up((size_t)out_len[s], 16);
+        max_frames = std::max(max_frames, infos[s].frame_count);
+        frames_total += infos[s].frame_count;
+    }
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(hca_tables_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
+    VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)fb + 16));
+    VGB_TRY(g_ctx.misc.reserve(o_status + (size_t)n_streams * 4));
+    char *misc = static_cast<char *>(g_ctx.misc.p);
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
+    CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
+    CUDA_TRY(launch_hca_encode(static_cast<const int16_t *>(g_ctx.pcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
+                               max_frames, cfg, g_hca_tables.view, static_cast<uint8_t *>(g_ctx.adpcm.p),
+                               reinterpret_cast<int32_t *>(misc + o_status), st));
+    g_ctx.launches += 1;
+    std::vector<int32_t> status(n_streams, 0);
+    CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
+    VGB_TRY(copy_channels_out(frames_out, static_cast<const char *>(g_ctx.adpcm.p), out_off, out_len, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_streams; s++) {
+        if (status[s] == VGB_HCA_BITRATE_TOO_LOW) return fail(VGB_E_DATA, "stream %d: Bitrate is set too low.", s);
+        if (status[s] == VGB_HCA_NOT_IMPLEMENTED) return fail(VGB_E_STATE, "stream %d: evaluation boundary search failed (NotImplementedException in the reference)", s);
+        if (status[s] == VGB_HCA_BIT_OVERFLOW) return fail(VGB_E_STATE, "stream %d: Not enough bits left in output buffer", s);
+    }
+    if (info_out) for (int s = 0; s < n_streams; s++) info_out[s] = infos[s];
+    if (cb) cb(user, frames_total);
+    return VGB_OK;
+}
+
 }  // extern "C"

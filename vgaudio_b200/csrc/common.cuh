@@ -65,4 +65,42 @@ struct AdxChannel {
     int16_t coef0, coef1;  // fixed-table pair or CalculateCoefficients (host, once per distinct sample rate)
 };
 
+// ---- CRI HCA ------------------------------------------------------------------------------------------------
+// per-stream status codes the encoder kernel can raise (mapped to the reference's exceptions by the C ABI)
+constexpr int32_t VGB_HCA_BITRATE_TOO_LOW = 1;   // InvalidDataException("Bitrate is set too low.") CriHcaEncoder.cs:469-472
+constexpr int32_t VGB_HCA_NOT_IMPLEMENTED = 2;   // NotImplementedException, CriHcaEncoder.cs:499
+constexpr int32_t VGB_HCA_BIT_OVERFLOW = 3;      // InvalidOperationException, BitWriter.cs:30-33
+
+// Stream-independent encoder configuration = the HcaInfo fields EncodeFrame reads (HcaInfo.cs:5-48) + channel types
+// (CriHcaFrame.GetChannelTypes :34-52).
+struct HcaConfig {
+    int32_t channel_count, frame_size;
+    int32_t base_band_count, stereo_band_count, total_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
+    int32_t channel_type[8];  // 0 Discrete, 1 StereoPrimary, 2 StereoSecondary
+};
+
+struct HcaStream {
+    int64_t pcm_off;         // sample offset of channel 0 of the stream in the PCM slab
+    int64_t channel_stride;  // samples between consecutive channels of the stream
+    int64_t frames_off;      // byte offset of the stream's first frame in the output slab
+    int32_t sample_count, frame_count;
+};
+
+// Read-only codec tables, resident in HBM (uploaded once per device).  Values: the reference's test literals
+// (hca_tables.inc) + host-computed trig/CRC/dead-zone tables (same formulas and libm as the oracle).
+struct HcaTables {
+    const double *window;                 // [128] MdctWindow (float32 data widened, CriHcaTables.cs:18)
+    const double *sin_tab[8], *cos_tab[8];  // Mdct trig tables by size bits 0..7 (Mdct.cs:183-195)
+    const int32_t *shuffle;               // [128] (Mdct.cs:197-208)
+    double mdct_scale, sqrt2;
+    const double *dequantizer_scaling, *quantizer_scaling;  // [64]
+    const double *inv_step, *dead_zone;   // [16] QuantizerInverseStepSize, QuantizerDeadZone
+    const double *intensity_bounds;       // [14]
+    const uint8_t *scale_to_resolution;   // [59]
+    const uint8_t *quantized_max_bits;    // [16]
+    const uint8_t (*quantize_bits)[16];   // [8][16] QuantizeSpectrumBits
+    const uint8_t (*quantize_value)[16];  // [8][16] QuantizeSpectrumValue
+    const uint16_t *crc_table;            // [256] Crc16 (poly 0x8005)
+};
+
 }  // namespace vgb

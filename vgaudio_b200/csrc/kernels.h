@@ -29,4 +29,10 @@ void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels
                        cudaStream_t stream);
 void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream);
 
+// hca.cu — CriHcaEncoder.EncodeFrame + CriHcaPacking.PackFrame (Codecs/CriHca/CriHcaEncoder.cs:271-286)
+size_t hca_encode_smem_bytes(const HcaConfig &cfg);
+cudaError_t launch_hca_encode(const int16_t *pcm, const HcaStream *streams, int n_streams, int max_frames,
+                              const HcaConfig &cfg, const HcaTables &tables, uint8_t *frames_out, int32_t *status_out,
+                              cudaStream_t stream);
+
 }  // namespace vgb
