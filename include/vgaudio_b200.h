@@ -213,6 +213,18 @@ int32_t vgb_hca_query(const vgb_hca_params *params, vgb_hca_info *info_out);
 int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
                              vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user);
 
+/* CRI HCA decode: replaces CriHcaDecoder.Decode (Codecs/CriHca/CriHcaDecoder.cs:11-25) for a batch of streams.
+ * info[s] is what the caller's container reader parsed (HcaReader -> HcaInfo); the codec reads channel_count,
+ * frame_size, the band layout, track_count / channel_config (channel types), sample_count, frame_count and
+ * inserted_samples.  All streams of a call share everything but the last three.  frames[s] = frame_count(s) *
+ * frame_size bytes (the reference's byte[][] AudioData, concatenated); pcm_out is a flat table
+ * [n_streams * channel_count] (stream-major) of buffers of sample_count(s) samples.  Frames are not CRC-checked
+ * (CriHcaPacking.UnpackFrame does not check either).  Errors: VGB_E_DATA ("Invalid frame header" - sync word is not
+ * 0xffff, CriHcaPacking.cs:73-77; or a scale-factor delta out of range, where the reference silently keeps decoding
+ * with the previous frame's state). */
+int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
+                             int16_t *const *pcm_out);
+
 #ifdef __cplusplus
 }
 #endif

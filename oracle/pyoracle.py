@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.vgo_hca_encode.argtypes = [vp, vp, vp, vp]
         L.vgo_hca_spectra.argtypes = [vp, vp, vp]
         L.vgo_hca_decode.argtypes = [vp, vp, vp]
+        L.vgo_hca_unpack_ok.argtypes = [vp, vp]
+        L.vgo_hca_unpack_ok.restype = C.c_int
         L.vgo_hca_mdct_run.argtypes = [vp, i32, vp]
         L.vgo_hca_mdct_run.restype = None
         L.vgo_hca_imdct_run.argtypes = [vp, i32, vp]
@@ -238,6 +240,11 @@ def hca_decode(info: HcaInfo, frames) -> np.ndarray:
     tab = (C.c_void_p * info.channel_count)(*[out[c].ctypes.data for c in range(info.channel_count)])
     lib().vgo_hca_decode(C.byref(info), frames.ctypes.data, tab)
     return out
+
+
+def hca_unpack_ok(info, frames) -> bool:
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    return bool(lib().vgo_hca_unpack_ok(C.byref(info), frames.ctypes.data))
 
 
 def hca_mdct(blocks: np.ndarray) -> np.ndarray:

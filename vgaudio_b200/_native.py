@@ -94,6 +94,7 @@ SIGNATURES = {
     "vgb_adx_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_hca_query": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "vgb_hca_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgb_hca_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -4,6 +4,7 @@ Reference interface (paths under /root/reference/src/VGAudio/):
   CriHcaParameters / CriHcaQuality                    Codecs/CriHca/CriHcaParameters.cs:3-15, CriHcaQuality.cs:3-10
   CriHcaEncoder.InitializeNew(config) -> .Hca (HcaInfo)  Codecs/CriHca/CriHcaEncoder.cs:49-114
   CriHcaFormat.EncodeFromPcm16(pcm16, config)          Formats/CriHca/CriHcaFormat.cs:34-84  (-> byte[FrameCount][FrameSize])
+  CriHcaDecoder.Decode(hca, audio, config) -> short[][] Codecs/CriHca/CriHcaDecoder.cs:11-25
 Round 1: non-looping streams.
 """
 from __future__ import annotations
@@ -82,3 +83,32 @@ def encode(channels: Sequence[np.ndarray], sample_rate: int, config: Optional[Cr
     config = config or CriHcaParameters()
     infos, outs = encode_batch([channels], sample_rate, config, config.progress)
     return infos[0], outs[0]
+
+
+def decode_batch(infos: Sequence[N.VgbHcaInfo], frames: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
+    """CriHcaDecoder.Decode for a batch of streams that share the band layout: frames[s] is uint8[frame_count,
+    frame_size] (the reference's byte[][] audio); returns per stream a list of int16[sample_count] channels."""
+    n = len(infos)
+    if n == 0:
+        return []
+    if len(frames) != n:
+        raise ValueError("one frame array per stream")
+    nch = infos[0].channel_count
+    info_arr = (N.VgbHcaInfo * n)(*infos)
+    ins = []
+    for s in range(n):
+        f = np.ascontiguousarray(frames[s], dtype=np.uint8).reshape(-1)
+        if f.size < infos[s].frame_count * infos[s].frame_size:
+            raise ValueError(f"stream {s}: {f.size} bytes of frames, HcaInfo needs {infos[s].frame_count * infos[s].frame_size}")
+        ins.append(f)
+    outs = [[np.zeros(max(infos[s].sample_count, 0), dtype=np.int16) for _ in range(nch)] for s in range(n)]
+    ftab = (C.c_void_p * n)(*[a.ctypes.data for a in ins])
+    flat = [a for st in outs for a in st]
+    otab = (C.c_void_p * max(len(flat), 1))(*[a.ctypes.data for a in flat])
+    N.check(N.lib.vgb_hca_decode_batch(ftab, C.cast(info_arr, C.c_void_p), n, otab))
+    return outs
+
+
+def decode(info: N.VgbHcaInfo, frames: np.ndarray) -> List[np.ndarray]:
+    """One stream: list of int16[sample_count] channels."""
+    return decode_batch([info], [frames])[0]

@@ -1171,6 +1171,11 @@ int32_t hca_tables_ready_locked()
         crc[i] = cur;
     }
     const size_t o_crc = put(crc, sizeof crc);
+    const size_t o_step = put(kHcaQuantizerStepSize, sizeof kHcaQuantizerStepSize);
+    const size_t o_ratio = put(kHcaIntensityRatio, sizeof kHcaIntensityRatio);
+    const size_t o_conv = put(kHcaScaleConversion, sizeof kHcaScaleConversion);
+    const size_t o_dbits = put(kHcaQuantizedSpectrumBits, sizeof kHcaQuantizedSpectrumBits);
+    const size_t o_dval = put(kHcaQuantizedSpectrumValue, sizeof kHcaQuantizedSpectrumValue);
 
     CUDA_TRY(cudaMalloc(&g_hca_tables.blob, host.size()));
     CUDA_TRY(cudaMemcpy(g_hca_tables.blob, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -1194,6 +1199,11 @@ int32_t hca_tables_ready_locked()
     T.quantize_bits = reinterpret_cast<const uint8_t(*)[16]>(b + o_qbits);
     T.quantize_value = reinterpret_cast<const uint8_t(*)[16]>(b + o_qval);
     T.crc_table = reinterpret_cast<const uint16_t *>(b + o_crc);
+    T.step_size = reinterpret_cast<const double *>(b + o_step);
+    T.intensity_ratio = reinterpret_cast<const double *>(b + o_ratio);
+    T.scale_conversion = reinterpret_cast<const double *>(b + o_conv);
+    T.dequantize_bits = reinterpret_cast<const uint8_t(*)[16]>(b + o_dbits);
+    T.dequantize_value = reinterpret_cast<const int8_t(*)[16]>(b + o_dval);
     g_hca_tables.ready = true;
     return VGB_OK;
 }
@@ -1287,6 +1297,103 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     }
     if (info_out) for (int s = 0; s < n_streams; s++) info_out[s] = infos[s];
     if (cb) cb(user, frames_total);
+    return VGB_OK;
+}
+
+int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
+                             int16_t *const *pcm_out)
+{
+    if (n_streams < 0) return fail(VGB_E_ARG, "n_streams is negative");
+    if (n_streams == 0) return VGB_OK;
+    if (!frames || !info || !pcm_out) return fail(VGB_E_ARG, "NULL argument");
+    const vgb_hca_info &h0 = info[0];
+    const int nch = h0.channel_count;
+    if (nch < 1 || nch > 8) return fail(VGB_E_ARG, "channel_count must be 1..8");
+    for (int s = 0; s < n_streams; s++) {
+        const vgb_hca_info &b = info[s];
+        if (b.channel_count != nch || b.frame_size != h0.frame_size || b.base_band_count != h0.base_band_count ||
+            b.stereo_band_count != h0.stereo_band_count || b.total_band_count != h0.total_band_count ||
+            b.hfr_band_count != h0.hfr_band_count || b.bands_per_hfr_group != h0.bands_per_hfr_group ||
+            b.hfr_group_count != h0.hfr_group_count || b.track_count != h0.track_count || b.channel_config != h0.channel_config)
+            return fail(VGB_E_ARG, "stream %d: all streams of one call must share the band layout and frame size", s);
+        if (b.sample_count < 0 || b.frame_count < 0 || b.inserted_samples < 0) return fail(VGB_E_ARG, "stream %d: negative count", s);
+    }
+    if (h0.frame_size < 8 || h0.frame_size > 0xffff) return fail(VGB_E_ARG, "frame_size out of range");
+    if (h0.base_band_count < 0 || h0.stereo_band_count < 0 || h0.base_band_count + h0.stereo_band_count > 128 ||
+        h0.total_band_count > 128 || h0.hfr_group_count < 0 || h0.hfr_group_count > 8 ||
+        (h0.hfr_group_count > 0 && h0.bands_per_hfr_group <= 0))
+        return fail(VGB_E_ARG, "band layout out of range");
+    if (h0.hfr_group_count > 0) {  // ReconstructHighFrequency mirrors bands around base+stereo: keep both sides in 0..127
+        const int start = h0.base_band_count + h0.stereo_band_count;
+        const int hfr_bands = std::min(h0.hfr_band_count, std::min(h0.total_band_count, 127) - h0.hfr_band_count);
+        if (hfr_bands > start || start + hfr_bands > 128) return fail(VGB_E_ARG, "high-frequency band layout out of range");
+    }
+    HcaConfig cfg{};
+    cfg.channel_count = nch;
+    cfg.frame_size = h0.frame_size;
+    cfg.base_band_count = h0.base_band_count;
+    cfg.stereo_band_count = h0.stereo_band_count;
+    cfg.total_band_count = h0.total_band_count;
+    cfg.hfr_band_count = h0.hfr_band_count;
+    cfg.bands_per_hfr_group = h0.bands_per_hfr_group;
+    cfg.hfr_group_count = h0.hfr_group_count;
+    hca_channel_types(h0, cfg.channel_type);
+
+    std::vector<HcaStream> streams(n_streams);
+    std::vector<int64_t> in_off(n_streams), in_len(n_streams), out_off((size_t)n_streams * nch), out_len((size_t)n_streams * nch);
+    int64_t ps = 0, fb = 0, frames_total = 0;
+    int max_frames = 0;
+    for (int s = 0; s < n_streams; s++) {
+        const int64_t stride = (int64_t)align_up((size_t)info[s].sample_count, 8);
+        streams[s].pcm_off = ps;
+        streams[s].channel_stride = stride;
+        streams[s].frames_off = fb;
+        streams[s].dct_off = frames_total;
+        streams[s].sample_count = info[s].sample_count;
+        streams[s].frame_count = info[s].frame_count;
+        streams[s].inserted_samples = info[s].inserted_samples;
+        for (int c = 0; c < nch; c++) {
+            if (!pcm_out[(size_t)s * nch + c] && info[s].sample_count > 0) return fail(VGB_E_ARG, "pcm_out[%d][%d] is NULL", s, c);
+            out_off[(size_t)s * nch + c] = (ps + c * stride) * 2;
+            out_len[(size_t)s * nch + c] = (int64_t)info[s].sample_count * 2;
+        }
+        ps += stride * nch;
+        in_off[s] = fb;
+        in_len[s] = (int64_t)info[s].frame_count * info[s].frame_size;
+        if (!frames[s] && in_len[s] > 0) return fail(VGB_E_ARG, "frames[%d] is NULL", s);
+        fb += (int64_t)align_up((size_t)in_len[s], 16);
+        max_frames = std::max(max_frames, info[s].frame_count);
+        frames_total += info[s].frame_count;
+    }
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(hca_tables_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
+    const size_t o_edge = align_up(o_status + (size_t)n_streams * 4, 256);
+    VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)fb + 16));
+    VGB_TRY(g_ctx.misc.reserve(o_edge + (size_t)frames_total * nch * 2 * 128 * sizeof(double)));
+    char *misc = static_cast<char *>(g_ctx.misc.p);
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, frames, in_len, st));
+    CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
+    // samples past the last frame (sample_count > frame_count * 1024 - inserted) stay zero, like a fresh short[]
+    CUDA_TRY(cudaMemsetAsync(g_ctx.pcm.p, 0, (size_t)ps * 2, st));
+    CUDA_TRY(launch_hca_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
+                               max_frames, cfg, g_hca_tables.view, reinterpret_cast<double *>(misc + o_edge),
+                               static_cast<int16_t *>(g_ctx.pcm.p), reinterpret_cast<int32_t *>(misc + o_status), st));
+    g_ctx.launches += 2;
+    std::vector<int32_t> status(n_streams, 0);
+    CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
+    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_streams; s++) {
+        if (status[s] == VGB_HCA_BAD_SYNC) return fail(VGB_E_DATA, "stream %d: Invalid frame header", s);
+        if (status[s] == VGB_HCA_BAD_DELTA) return fail(VGB_E_DATA, "stream %d: scale factor delta out of range", s);
+        if (status[s] == VGB_HCA_BAD_INDEX) return fail(VGB_E_DATA, "stream %d: intensity index out of range", s);
+    }
     return VGB_OK;
 }
 

@@ -70,6 +70,9 @@ struct AdxChannel {
 constexpr int32_t VGB_HCA_BITRATE_TOO_LOW = 1;   // InvalidDataException("Bitrate is set too low.") CriHcaEncoder.cs:469-472
 constexpr int32_t VGB_HCA_NOT_IMPLEMENTED = 2;   // NotImplementedException, CriHcaEncoder.cs:499
 constexpr int32_t VGB_HCA_BIT_OVERFLOW = 3;      // InvalidOperationException, BitWriter.cs:30-33
+constexpr int32_t VGB_HCA_BAD_SYNC = 4;          // InvalidDataException("Invalid frame header"), CriHcaPacking.cs:73-77
+constexpr int32_t VGB_HCA_BAD_INDEX = 6;         // intensity index 15: IndexOutOfRangeException in ApplyIntensityStereo
+constexpr int32_t VGB_HCA_BAD_DELTA = 5;         // UnpackFrame returns false (scale-factor delta out of range)
 
 // Stream-independent encoder configuration = the HcaInfo fields EncodeFrame reads (HcaInfo.cs:5-48) + channel types
 // (CriHcaFrame.GetChannelTypes :34-52).
@@ -83,7 +86,9 @@ struct HcaStream {
     int64_t pcm_off;         // sample offset of channel 0 of the stream in the PCM slab
     int64_t channel_stride;  // samples between consecutive channels of the stream
     int64_t frames_off;      // byte offset of the stream's first frame in the output slab
+    int64_t dct_off;         // decoder: index of the stream's first frame in the seam scratch (frames)
     int32_t sample_count, frame_count;
+    int32_t inserted_samples, reserved;  // decoder: HcaInfo.InsertedSamples (CopyPcmToOutput, CriHcaDecoder.cs:26-37)
 };
 
 // Read-only codec tables, resident in HBM (uploaded once per device).  Values: the reference's test literals
@@ -101,6 +106,12 @@ struct HcaTables {
     const uint8_t (*quantize_bits)[16];   // [8][16] QuantizeSpectrumBits
     const uint8_t (*quantize_value)[16];  // [8][16] QuantizeSpectrumValue
     const uint16_t *crc_table;            // [256] Crc16 (poly 0x8005)
+    // decoder side
+    const double *step_size;              // [16] QuantizerStepSize
+    const double *intensity_ratio;        // [15]
+    const double *scale_conversion;       // [128]
+    const uint8_t (*dequantize_bits)[16]; // [8][16] QuantizedSpectrumBits
+    const int8_t (*dequantize_value)[16]; // [8][16] QuantizedSpectrumValue
 };
 
 }  // namespace vgb

@@ -460,6 +460,300 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
     for (int b = tid; b < cfg.frame_size; b += blockDim.x) dst[b] = frame_buf[b];
 }
 
+// ==========================================================================================================
+// Decoder: CriHcaPacking.UnpackFrame (CriHcaPacking.cs:10-229) + CriHcaDecoder.DecodeFrame (CriHcaDecoder.cs:62-192)
+// ==========================================================================================================
+// The only state the reference carries between frames is the IMDCT overlap buffer (Mdct.cs:114-117), and that is a
+// pure function of the previous subframe's DCT-IV output.  So decoding splits into two embarrassingly parallel
+// kernels: (A) one CTA per (stream, frame): parse the bitstream (one thread - prefix codes are serial), dequantise,
+// rebuild the high band and intensity-stereo band, run the eight DCT-IV, window + overlap-add subframes 1..7, convert
+// to int16 and write the samples the container asks for (CopyPcmToOutput, CriHcaDecoder.cs:26-37); the two addends of
+// subframe 0 (2 KB per channel-frame) are parked in HBM; (B) one CTA per (stream, frame, channel) adds frame k's head
+// to frame k-1's tail.
+// Malformed input: a wrong sync word raises VGB_HCA_BAD_SYNC (InvalidDataException in the reference); a failed
+// scale-factor delta decode raises VGB_HCA_BAD_DELTA (the reference ignores UnpackFrame's `false` and keeps decoding
+// with whatever the previous frame left in its buffers - state we deliberately do not carry).
+
+namespace {
+
+struct BitPeeker {  // BitReader.PeekInt / Position (Utilities/BitReader.cs:51-99): bits past the end read as zero
+    const uint8_t *buf;
+    int pos, length_bits;
+    __device__ int peek(int count) const
+    {
+        int v = 0;
+        for (int i = 0; i < count; i++) {
+            const int p = pos + i;
+            const int bit = p < length_bits ? (buf[p >> 3] >> (7 - (p & 7))) & 1 : 0;
+            v = (v << 1) | bit;
+        }
+        return v;
+    }
+    __device__ int read(int count) { const int v = peek(count); pos += count; return v; }
+};
+
+// PcmFloatToShort (CriHcaDecoder.cs:168-181)
+__device__ __forceinline__ int16_t hca_pcm_float_to_short(double x)
+{
+    const double v = x * 32768.0;
+    const int sample = (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : INT32_MIN;  // x64 cvttsd2si (A.8)
+    return (int16_t)clamp16(sample);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__restrict__ streams, HcaConfig cfg,
+                         HcaTables T, double *__restrict__ edge, int16_t *__restrict__ pcm,
+                         int32_t *__restrict__ status_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nch = cfg.channel_count;
+    double *spectra = reinterpret_cast<double *>(smem_raw);                   // [nch][8][128]
+    double *work = spectra + (size_t)nch * kSub * kBins;                      // [2][128]
+    int *quantized = reinterpret_cast<int *>(work + 2 * kBins);               // [nch][8][128]
+    HcaChannelState *chs = reinterpret_cast<HcaChannelState *>(quantized + (size_t)nch * kSub * kBins);
+    uint8_t *frame_buf = reinterpret_cast<uint8_t *>(chs + nch);
+
+    const int tid = threadIdx.x;
+    const int s = blockIdx.y, k = blockIdx.x;
+    const HcaStream st = streams[s];
+    if (k >= st.frame_count) return;
+
+    const uint8_t *src = frames + st.frames_off + (int64_t)k * cfg.frame_size;
+    for (int b = tid; b < cfg.frame_size; b += blockDim.x) frame_buf[b] = src[b];
+    if (tid < nch) {
+        chs[tid].type = cfg.channel_type[tid];
+        chs[tid].coded_count = cfg.channel_type[tid] == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
+    }
+    __syncthreads();
+
+    // ---- UnpackFrame: serial bit parsing by one thread
+    if (tid == 0) {
+        BitPeeker r{frame_buf, 0, cfg.frame_size * 8};
+        int status = 0;
+        if (r.read(16) != 0xffff) status = VGB_HCA_BAD_SYNC;
+        const int noise_level = r.read(9);
+        const int eval_boundary = r.read(7);
+        for (int c = 0; c < nch && !status; c++) {
+            HcaChannelState &ch = chs[c];
+            ch.delta_bits = r.read(3);  // ReadScaleFactors (:108-126)
+            if (ch.delta_bits == 0) {
+                for (int b = 0; b < kBins; b++) ch.scale_factors[b] = 0;
+            } else if (ch.delta_bits >= 6) {
+                for (int b = 0; b < ch.coded_count; b++) ch.scale_factors[b] = r.read(6);
+                for (int b = ch.coded_count; b < kBins; b++) ch.scale_factors[b] = 0;
+            } else {  // DeltaDecode (:183-208)
+                ch.scale_factors[0] = r.read(6);
+                const int max_delta = 1 << (ch.delta_bits - 1);
+                for (int b = 1; b < ch.coded_count; b++) {
+                    const int delta = r.read(ch.delta_bits) - (max_delta - 1);  // ReadOffsetBinary, OffsetBias.Positive
+                    if (delta < max_delta) {
+                        const int value = ch.scale_factors[b - 1] + delta;
+                        if (value < 0 || value > 63) { status = VGB_HCA_BAD_DELTA; break; }
+                        ch.scale_factors[b] = value;
+                    } else {
+                        ch.scale_factors[b] = r.read(6);
+                    }
+                }
+                for (int b = ch.coded_count; b < kBins; b++) ch.scale_factors[b] = 0;
+            }
+            if (status) break;
+            for (int b = 0; b < kBins; b++) {
+                int res = 0;
+                if (b < ch.coded_count)
+                    res = hca_resolution(T, ch.scale_factors[b], b < eval_boundary ? noise_level - 1 : noise_level);  // ATH curve unused
+                ch.resolution[b] = res;
+            }
+            if (ch.type == 2) {
+                for (int i = 0; i < kSub; i++) {
+                    ch.intensity[i] = r.read(4);
+                    if (ch.intensity[i] > 14) { status = VGB_HCA_BAD_INDEX; ch.intensity[i] = 14; }
+                }
+            } else if (cfg.hfr_group_count > 0) {
+                for (int i = 0; i < cfg.hfr_group_count; i++) ch.hfr_scales[i] = r.read(6);
+            }
+        }
+        if (!status) {
+            for (int sf = 0; sf < kSub; sf++)  // ReadSpectralCoefficients (:144-181)
+                for (int c = 0; c < nch; c++) {
+                    const HcaChannelState &ch = chs[c];
+                    int *q = quantized + ((size_t)c * kSub + sf) * kBins;
+                    for (int b = 0; b < ch.coded_count; b++) {
+                        const int resolution = ch.resolution[b];
+                        int bits = T.quantized_max_bits[resolution];
+                        const int code = r.peek(bits);
+                        if (resolution < 8) {
+                            bits = T.dequantize_bits[resolution][code];
+                            q[b] = T.dequantize_value[resolution][code];
+                        } else {
+                            const int v = code / 2 * (1 - (code % 2 * 2));
+                            if (v == 0) bits--;
+                            q[b] = v;
+                        }
+                        r.pos += bits;
+                    }
+                }
+        } else {
+            atomicCAS(status_out + s, 0, status);
+            for (int e = 0; e < nch * kSub * kBins; e++) quantized[e] = 0;
+            for (int c = 0; c < nch; c++)
+                for (int b = 0; b < kBins; b++) { chs[c].scale_factors[b] = 0; chs[c].resolution[b] = 0; }
+        }
+    }
+    __syncthreads();
+
+    // ---- DequantizeFrame (CriHcaDecoder.cs:72-105): thread = band
+    for (int c = 0; c < nch; c++) {
+        const int b = tid;
+        const double gain = b < chs[c].coded_count ? T.dequantizer_scaling[chs[c].scale_factors[b]] * T.step_size[chs[c].resolution[b]] : 0.0;
+#pragma unroll
+        for (int sf = 0; sf < kSub; sf++)
+            spectra[((size_t)c * kSub + sf) * kBins + b] = b < chs[c].coded_count ? quantized[((size_t)c * kSub + sf) * kBins + b] * gain : 0.0;
+    }
+    __syncthreads();
+    // ---- ReconstructHighFrequency (:106-134): every high band is a scaled copy of a low band
+    if (cfg.hfr_group_count != 0) {
+        const int total = min(cfg.total_band_count, 127);
+        const int start = cfg.base_band_count + cfg.stereo_band_count;
+        const int hfr_bands = min(cfg.hfr_band_count, total - cfg.hfr_band_count);
+        for (int c = 0; c < nch; c++) {
+            if (chs[c].type == 2) continue;
+            const int band = tid;
+            if (band < hfr_bands && band / cfg.bands_per_hfr_group < cfg.hfr_group_count) {
+                const int group = band / cfg.bands_per_hfr_group;
+                const int high = start + band, low = start - band - 1;
+                const int index = chs[c].hfr_scales[group] - chs[c].scale_factors[low] + 64;
+                const double conv = T.scale_conversion[index];
+#pragma unroll
+                for (int sf = 0; sf < kSub; sf++)
+                    spectra[((size_t)c * kSub + sf) * kBins + high] = conv * spectra[((size_t)c * kSub + sf) * kBins + low];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- ApplyIntensityStereo (:135-157)
+    if (cfg.stereo_band_count > 0) {
+        for (int c = 0; c < nch; c++) {
+            if (chs[c].type != 1) continue;
+            const int b = tid;
+            if (b >= cfg.base_band_count && b < cfg.total_band_count) {
+#pragma unroll
+                for (int sf = 0; sf < kSub; sf++) {
+                    const double rl = T.intensity_ratio[chs[c + 1].intensity[sf]];
+                    const double rr = rl - 2.0;
+                    double &l = spectra[((size_t)c * kSub + sf) * kBins + b];
+                    spectra[((size_t)(c + 1) * kSub + sf) * kBins + b] = l * rr;
+                    l *= rl;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- the DCT-IV of RunImdct (Mdct.cs:107): two subframes at a time, each output replaces its input in `spectra`
+    const int grp = tid >> 6, i = tid & 63;
+    double *t = work + grp * kBins;
+    for (int c = 0; c < nch; c++) {
+        for (int sf2 = 0; sf2 < kSub; sf2 += 2) {
+            const int sf = sf2 + grp;
+            double *io = spectra + ((size_t)c * kSub + sf) * kBins;
+            {
+                const int i2 = i * 2;
+                const double a = io[i2], b = io[kBins - 1 - i2];
+                const double sn = T.sin_tab[7][i], cs = T.cos_tab[7][i];
+                t[i2] = a * cs + b * sn;
+                t[i2 + 1] = a * sn - b * cs;
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int stage = 0; stage < 6; stage++) {
+                const int block_bits = 6 - stage, half_bits = block_bits - 1;
+                const int block_size = 1 << block_bits, block_half = 1 << half_bits;
+                const int block = i >> half_bits, j = i & (block_half - 1);
+                const int front = (block * block_size + j) * 2, back = front + block_size;
+                const double a = t[front] - t[back];
+                const double b = t[front + 1] - t[back + 1];
+                const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
+                const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
+                t[front] = f0;
+                t[front + 1] = f1;
+                t[back] = a * cs + b * sn;
+                t[back + 1] = a * sn - b * cs;
+                __syncthreads();
+            }
+            io[i] = t[T.shuffle[i]] * T.mdct_scale;
+            io[64 + i] = t[T.shuffle[64 + i]] * T.mdct_scale;
+            __syncthreads();
+        }
+    }
+
+    // ---- window + overlap-add (Mdct.cs:108-117).  The overlap buffer a subframe sees is a pure function of the
+    // previous subframe's DCT output, so subframes 1..7 finish here; subframe 0 needs the previous FRAME's tail, so its
+    // two addends go to HBM (head = this frame's products, tail = the overlap terms subframe 7 leaves behind) and
+    // hca_decode_seam_kernel adds them.  thread = (h, i): h = 0 -> output[i], h = 1 -> output[i + 64].
+    const int h = grp;
+    for (int c = 0; c < nch; c++) {
+        int16_t *dst = pcm + st.pcm_off + (int64_t)c * st.channel_stride;
+        const double *d = spectra + (size_t)c * kSub * kBins;
+        double *e = edge + (((size_t)st.dct_off + k) * nch + c) * 2 * kBins;
+        auto product = [&](const double *cur) {  // this subframe's own term
+            return h == 0 ? T.window[i] * cur[i + 64] : T.window[i + 64] * -cur[kBins - 1 - i];
+        };
+        auto overlap = [&](const double *prev) {  // what the previous subframe left in the overlap buffer
+            return h == 0 ? T.window[kBins - 1 - i] * -prev[64 - i - 1] : T.window[64 - i - 1] * prev[i];
+        };
+        e[tid] = product(d);
+        e[kBins + tid] = overlap(d + 7 * kBins);
+#pragma unroll 1
+        for (int sf = 1; sf < kSub; sf++) {
+            const double a = product(d + sf * kBins), p = overlap(d + (sf - 1) * kBins);
+            const int64_t pos = (int64_t)k * kFrame + sf * kBins + tid - st.inserted_samples;
+            if (pos >= 0 && pos < st.sample_count) dst[pos] = hca_pcm_float_to_short(h == 0 ? a + p : a - p);
+        }
+    }
+}
+
+// First subframe of every frame: head(k) +/- tail(k-1).  grid: x = frame, y = channel, z = stream; 128 threads.
+__global__ void __launch_bounds__(128)
+hca_decode_seam_kernel(const double *__restrict__ edge, const HcaStream *__restrict__ streams, HcaConfig cfg,
+                       int16_t *__restrict__ pcm)
+{
+    const int k = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    const HcaStream st = streams[s];
+    if (k >= st.frame_count) return;
+    const int nch = cfg.channel_count, tid = threadIdx.x;
+    const double a = edge[((((size_t)st.dct_off + k) * nch + c) * 2) * kBins + tid];
+    const double p = k > 0 ? edge[((((size_t)st.dct_off + k - 1) * nch + c) * 2 + 1) * kBins + tid] : 0.0;
+    const int64_t pos = (int64_t)k * kFrame + tid - st.inserted_samples;
+    if (pos >= 0 && pos < st.sample_count)
+        pcm[st.pcm_off + (int64_t)c * st.channel_stride + pos] = hca_pcm_float_to_short(tid < 64 ? a + p : a - p);
+}
+
+size_t hca_decode_smem_bytes(const HcaConfig &cfg)
+{
+    const size_t nch = (size_t)cfg.channel_count;
+    return nch * kSub * kBins * sizeof(double) + 2 * kBins * sizeof(double) + nch * kSub * kBins * sizeof(int) +
+           nch * sizeof(HcaChannelState) + (size_t)((cfg.frame_size + 15) & ~15) + 16;
+}
+
+cudaError_t launch_hca_decode(const uint8_t *frames, const HcaStream *streams, int n_streams, int max_frames,
+                              const HcaConfig &cfg, const HcaTables &tables, double *edge_scratch, int16_t *pcm,
+                              int32_t *status_out, cudaStream_t stream)
+{
+    if (n_streams <= 0 || max_frames <= 0) return cudaSuccess;
+    const size_t smem = hca_decode_smem_bytes(cfg);
+    cudaError_t e = cudaFuncSetAttribute(hca_decode_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid_a((unsigned)max_frames, (unsigned)n_streams);
+    hca_decode_unpack_kernel<<<grid_a, 128, smem, stream>>>(frames, streams, cfg, tables, edge_scratch, pcm, status_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 grid_b((unsigned)max_frames, (unsigned)cfg.channel_count, (unsigned)n_streams);
+    hca_decode_seam_kernel<<<grid_b, 128, 0, stream>>>(edge_scratch, streams, cfg, pcm);
+    return cudaGetLastError();
+}
+
 size_t hca_encode_smem_bytes(const HcaConfig &cfg)
 {
     const size_t nch = (size_t)cfg.channel_count;

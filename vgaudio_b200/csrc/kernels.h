@@ -35,4 +35,10 @@ cudaError_t launch_hca_encode(const int16_t *pcm, const HcaStream *streams, int 
                               const HcaConfig &cfg, const HcaTables &tables, uint8_t *frames_out, int32_t *status_out,
                               cudaStream_t stream);
 
+// CriHcaPacking.UnpackFrame + CriHcaDecoder.DecodeFrame (Codecs/CriHca/CriHcaDecoder.cs:62-192)
+size_t hca_decode_smem_bytes(const HcaConfig &cfg);
+cudaError_t launch_hca_decode(const uint8_t *frames, const HcaStream *streams, int n_streams, int max_frames,
+                              const HcaConfig &cfg, const HcaTables &tables, double *edge_scratch, int16_t *pcm,
+                              int32_t *status_out, cudaStream_t stream);  // edge_scratch: 2*128 doubles per channel-frame
+
 }  // namespace vgb
