@@ -133,8 +133,9 @@ int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offs
                                void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
 
 /* Per-kernel device time (ms, CUDA events on the launching stream) of the most recent *_dev or host call on this
- * thread's workspace: [0] coefficient phase 1, [1] coefficient refinement, [2] encode, [3] decode.  Only filled
- * when vgb_set_kernel_timing(1) was called; bench.py uses it for the roofline object. */
+ * thread's workspace: [0] GC coefficient phase 1, [1] GC coefficient refinement, [2] GC encode, [3] GC decode,
+ * [4] ADX encode, [5] ADX decode, [6] HCA encode, [7] HCA decode (both kernels).  Only filled when
+ * vgb_set_kernel_timing(1) was called; bench.py / tools/secondary_bench.py use it for the roofline objects. */
 int32_t vgb_set_kernel_timing(int32_t enabled);
 int32_t vgb_last_kernel_ms(float *ms_out, int32_t n);
 

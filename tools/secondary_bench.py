@@ -1,8 +1,16 @@
 #!/usr/bin/env python
-"""tools/secondary_bench.py — wall-clock throughput of the non-headline paths through the host C ABI (pageable numpy
-buffers, so H2D/D2H are part of every number): GC-ADPCM decode (config C3 shape, scaled), CRI ADX encode/decode and
-CRI HCA encode (config C4 shape, scaled).  Usage: python tools/secondary_bench.py [--scale 0.25]"""
+"""tools/secondary_bench.py — the non-headline paths of SURVEY.md §8 measured on one GPU.
+
+For each of GC-ADPCM decode (BASELINE config C3 shape), CRI ADX encode/decode and CRI HCA encode/decode (C4 shape) it
+reports, through the host C ABI (pageable numpy buffers):
+  wall_ms / Msamples_per_s   the synchronous call, H2D and D2H included
+  kernel_ms                  CUDA events around the kernel(s) on the library's stream (vgb_set_kernel_timing)
+  roofline                   algorithmic bytes of the kernel / kernel_ms against MEASURED_PEAKS.json's HBM copy peak
+Shapes are scaled by --scale (default 0.25 of C3/C4) to keep pageable host buffers and run time moderate.
+Usage: python tools/secondary_bench.py [--scale 0.25] [--only gcdec,adx,hca]
+"""
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -10,57 +18,95 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import vgaudio_b200 as vg  # noqa: E402
+from vgaudio_b200 import _native as N  # noqa: E402
 from vgaudio_b200 import synth  # noqa: E402
 
+SLOT = {"gc_decode": 3, "adx_encode": 4, "adx_decode": 5, "hca_encode": 6, "hca_decode": 7}
 
-def timed(fn, reps=3):
+
+def peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 7700.0, "fallback (B200_PROFILING.md nominal)"
+
+
+def timed(fn, slot, reps=3):
     fn()
-    t = []
+    best, kms = None, None
+    buf = (C.c_float * 8)()
     for _ in range(reps):
         t0 = time.perf_counter()
         fn()
-        t.append(time.perf_counter() - t0)
-    return min(t)
+        dt = time.perf_counter() - t0
+        N.check(vg.lib.vgb_last_kernel_ms(buf, 8))
+        if best is None or dt < best:
+            best, kms = dt, float(buf[slot])
+    return best, kms
+
+
+def entry(samples, dt, kms, alg_bytes, extra):
+    peak, src = peak_gbs()
+    out = dict(extra)
+    out.update({"Msamples_per_s": round(samples / dt / 1e6, 1), "wall_ms": round(dt * 1e3, 1), "kernel_ms": round(kms, 3),
+                "kernel_Msamples_per_s": round(samples / kms / 1e3, 1) if kms > 0 else None,
+                "roofline": {"bound": "hbm", "achieved": round(alg_bytes / kms / 1e6, 1) if kms > 0 else None, "peak": peak,
+                             "unit": "GB/s", "frac": round(alg_bytes / kms / 1e6 / peak, 4) if kms > 0 else None,
+                             "algorithmic_bytes": int(alg_bytes), "peak_source": src}})
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=0.25)
+    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--only", default="gcdec,adx,hca")
     a = ap.parse_args()
+    only = set(a.only.split(","))
+    N.check(vg.lib.vgb_set_kernel_timing(1))
     out = {}
-    rng = np.random.default_rng(0)
-    base = synth.batch(16, 48000 * 30, degenerate=False, first_index=10)
+    n = int(48000 * a.seconds)
+    base = synth.batch(16, n, degenerate=False, first_index=10)
 
-    # GC-ADPCM decode, C3 shape: 8192 channels x 30 s (scaled)
-    n_ch = max(64, int(8192 * a.scale))
-    pcm = base[np.arange(n_ch) % 16]
-    coefs, adpcm = vg.gcadpcm.encode_batch(pcm)
-    ad = np.stack(adpcm)
-    cfgs = [vg.gcadpcm.GcAdpcmParameters(pcm.shape[1])] * n_ch
-    dt = timed(lambda: vg.gcadpcm.decode_batch(ad, coefs, cfgs))
-    out["gcadpcm_decode"] = {"channels": n_ch, "Msamples_per_s": round(pcm.size / dt / 1e6, 1), "ms": round(dt * 1e3, 1)}
+    if "gcdec" in only:  # GC-ADPCM decode, C3 shape: 8192 channels x 30 s (scaled)
+        n_ch = max(64, int(8192 * a.scale))
+        coefs16, adpcm16 = vg.gcadpcm.encode_batch(base)
+        idx = np.arange(n_ch) % 16
+        ad = np.stack(adpcm16)[idx]
+        coefs = np.asarray(coefs16)[idx]
+        cfgs = [vg.gcadpcm.GcAdpcmParameters(n)] * n_ch
+        dt, kms = timed(lambda: vg.gcadpcm.decode_batch(ad, coefs, cfgs), SLOT["gc_decode"])
+        out["gcadpcm_decode"] = entry(n_ch * n, dt, kms, n_ch * (n * 2 + ad.shape[1]), {"channels": n_ch})
 
-    # CRI ADX encode / decode
-    n_ch = max(64, int(4096 * a.scale))
-    pcm = base[np.arange(n_ch) % 16]
-    cfg = vg.criadx.CriAdxParameters()
-    dt = timed(lambda: vg.criadx.encode_batch(pcm, cfg))
-    out["adx_encode"] = {"channels": n_ch, "Msamples_per_s": round(pcm.size / dt / 1e6, 1), "ms": round(dt * 1e3, 1)}
-    adx, hist = vg.criadx.encode_batch(pcm, cfg)
-    dcfg = [vg.criadx.CriAdxParameters(history=int(h)) for h in hist]
-    dt = timed(lambda: vg.criadx.decode_batch(np.stack(adx), pcm.shape[1], dcfg))
-    out["adx_decode"] = {"channels": n_ch, "Msamples_per_s": round(pcm.size / dt / 1e6, 1), "ms": round(dt * 1e3, 1)}
+    if "adx" in only:  # CRI ADX encode / decode
+        n_ch = max(64, int(4096 * a.scale))
+        pcm = base[np.arange(n_ch) % 16]
+        cfg = vg.criadx.CriAdxParameters()
+        dt, kms = timed(lambda: vg.criadx.encode_batch(pcm, cfg), SLOT["adx_encode"])
+        adx, hist = vg.criadx.encode_batch(pcm, cfg)
+        adx = np.stack(adx)
+        out["adx_encode"] = entry(pcm.size, dt, kms, pcm.size * 2 + adx.size, {"channels": n_ch})
+        dcfg = [vg.criadx.CriAdxParameters(history=int(h)) for h in hist]
+        dt, kms = timed(lambda: vg.criadx.decode_batch(adx, n, dcfg), SLOT["adx_decode"])
+        out["adx_decode"] = entry(pcm.size, dt, kms, pcm.size * 2 + adx.size, {"channels": n_ch})
 
-    # CRI HCA encode, C4 shape: 512 mono streams x 30 s, Quality=High (scaled)
-    n_st = max(16, int(512 * a.scale))
-    streams = [[base[s % 16]] for s in range(n_st)]
-    dt = timed(lambda: vg.crihca.encode_batch(streams, 48000))
-    out["hca_encode_mono_high"] = {"streams": n_st, "Msamples_per_s": round(n_st * base.shape[1] / dt / 1e6, 1), "ms": round(dt * 1e3, 1)}
-    streams2 = [[base[s % 16], base[(s + 1) % 16]] for s in range(n_st // 2)]
-    dt = timed(lambda: vg.crihca.encode_batch(streams2, 48000))
-    out["hca_encode_stereo_high"] = {"streams": n_st // 2, "Msample_channels_per_s": round(n_st // 2 * 2 * base.shape[1] / dt / 1e6, 1), "ms": round(dt * 1e3, 1)}
+    if "hca" in only:  # CRI HCA, C4 shape: 512 mono streams x 30 s, Quality=High (scaled)
+        n_st = max(16, int(512 * a.scale))
+        streams = [[base[s % 16]] for s in range(n_st)]
+        dt, kms = timed(lambda: vg.crihca.encode_batch(streams, 48000), SLOT["hca_encode"])
+        infos, frames = vg.crihca.encode_batch(streams, 48000)
+        fbytes = sum(f.size for f in frames)
+        out["hca_encode_mono_high"] = entry(n_st * n, dt, kms, n_st * n * 2 + fbytes, {"streams": n_st})
+        dt, kms = timed(lambda: vg.crihca.decode_batch(infos, frames), SLOT["hca_decode"])
+        out["hca_decode_mono_high"] = entry(n_st * n, dt, kms, n_st * n * 2 + fbytes, {"streams": n_st})
+        streams2 = [[base[s % 16], base[(s + 1) % 16]] for s in range(n_st // 2)]
+        dt, kms = timed(lambda: vg.crihca.encode_batch(streams2, 48000), SLOT["hca_encode"])
+        infos2, frames2 = vg.crihca.encode_batch(streams2, 48000)
+        fbytes2 = sum(f.size for f in frames2)
+        out["hca_encode_stereo_high"] = entry(n_st // 2 * 2 * n, dt, kms, n_st // 2 * 2 * n * 2 + fbytes2, {"streams": n_st // 2})
     print(json.dumps(out))
 
 

@@ -7,6 +7,10 @@
 // reconstruct recurrence with its one fp64 multiply + truncation per sample (:126).
 // Latency bound (one fp64 multiply, two conversions and ~10 integer ops per sample on the dependent chain);
 // algorithmic traffic 2 B/sample in + frame_size/samples_per_frame B/sample out (2.5625 B/sample at 18-byte frames).
+// The standard layout (18-byte frames, no padding) streams privately per thread: cp.async copies a frame's 32 samples
+// (encoder, four 16-byte chunks) or 8 frames' 144 bytes (decoder, nine chunks) into the thread's own shared-memory ring
+// two steps ahead, results leave as halfword / 16-byte stores straight from registers (partial sectors merge in L2), so
+// DRAM latency never reaches the recurrence.  Other frame sizes / padded streams / a partial last frame take the general loop.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,10 +29,21 @@ __device__ __forceinline__ int32_t adx_short_to_nibble(int32_t s)
     return clamp4((s + 2340 * sgn) / 4681);
 }
 
-__global__ void __launch_bounds__(64)
+constexpr int kAdxThreads = 32;   // one warp per CTA: spreads a few thousand channels over all SMs
+constexpr int kAdxStages = 3;     // cp.async ring depth (kAdxStages - 1 frames / frame groups in flight)
+constexpr int kAdxDecGroup = 8;   // decoder: 8 frames = 144 B = nine 16-byte chunks per thread and step
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(kAdxThreads)
 adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict__ tab, int n_channels,
                   uint8_t *__restrict__ adpcm, int16_t *__restrict__ history_out)
 {
+    __shared__ __align__(16) uint4 enc_ring[kAdxStages][4][kAdxThreads];  // [stage][16-byte chunk of the frame][thread]
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_channels) return;
     const AdxChannel c = tab[ch];
@@ -49,8 +64,82 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
     }
     if (history_out) history_out[ch] = hist_cfg;
 
+    int f_first = 0;
+    if (c.frame_size == 18 && c.padding == 0) {
+        // ---- standard layout: whole frames of 32 samples straight from registers
+        const int whole = c.n_samples / 32;
+        const uint4 *vin = reinterpret_cast<const uint4 *>(src);  // pcm_off is a multiple of 8 samples
+        auto issue = [&](int f) {  // frame f -> ring stage f % kAdxStages (cp.async: no register scoreboard to wait on)
+            if (f < whole) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) cp_async16(&enc_ring[f % kAdxStages][j][threadIdx.x], vin + (int64_t)f * 4 + j);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int a = 0; a < kAdxStages - 1; a++) issue(a);
+        for (int f = 0; f < whole; f++) {
+            issue(f + kAdxStages - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kAdxStages - 1) : "memory");
+            int32_t x[32];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = enc_ring[f % kAdxStages][j][threadIdx.x];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    x[8 * j + 2 * k] = (int32_t)(int16_t)(w[k] & 0xFFFFu);
+                    x[8 * j + 2 * k + 1] = (int32_t)w[k] >> 16;
+                }
+            }
+            int32_t max_distance = 0;  // pass 1 (:112-118)
+            {
+                int32_t p0 = h2, p1 = h1;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const int32_t predicted = (wmul(p1, c0) >> 12) + (wmul(p0, c1) >> 12);
+                    max_distance = max(max_distance, abs(clamp16(x[i] - predicted)));
+                    p0 = p1;
+                    p1 = x[i];
+                }
+            }
+            int32_t scale = (max_distance - 1) / 7 + 1;  // CalculateScale (:149-165)
+            if (scale > 0x1000) scale = 0x1000;
+            int32_t scale_out = scale - 1;
+            if (exponential) {
+                const int power = scale_out == 0 ? 0 : (31 - __clz(scale_out)) + 1;
+                scale = 1 << power;
+                scale_out = 12 - power;
+                max_distance = 8 * scale - 1;
+            }
+            const double gain = max_distance == 0 ? 0.0 : __ddiv_rn(32767.0, (double)max_distance);
+            uint16_t *out16 = reinterpret_cast<uint16_t *>(dst + (int64_t)f * 18);  // adpcm_off is even
+            const uint32_t hdr0 = ((uint32_t)(scale_out >> 8) & 0x1fu) | (c.type == 2 ? (uint32_t)(c.filter << 5) : 0u);
+            out16[0] = (uint16_t)((hdr0 & 0xFFu) | (((uint32_t)scale_out & 0xFFu) << 8));  // :140-141
+            uint32_t hw = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {  // pass 2 (:122-138)
+                int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
+                const int32_t raw = x[i] - predicted;
+                const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
+                const int32_t q = adx_short_to_nibble(scaled);
+                const int32_t decoded_distance = clamp16(wmul(scale, q));
+                if (v4) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
+                const int32_t recon = clamp16(decoded_distance + predicted);
+                h2 = h1;
+                h1 = recon;
+                // byte = (q_even << 4) | q_odd; halfword = byte0 | byte1 << 8
+                const int sh = ((i & 1) ? 0 : 4) + ((i & 2) ? 8 : 0);
+                hw |= ((uint32_t)q & 0xFu) << sh;
+                if ((i & 3) == 3) { out16[1 + (i >> 2)] = (uint16_t)hw; hw = 0; }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        f_first = whole;
+    }
+
     int padding_remaining = c.padding;
-    for (int f = 0; f < frame_count; f++) {
+    for (int f = f_first; f < frame_count; f++) {
         int to_copy = min(sample_count - f * spf, spf);  // :78
         int lead = 0;                                    // zero samples in front (pcmBufferStart - 2)
         if (padding_remaining != 0) {                    // :80-89
@@ -116,10 +205,11 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
     }
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kAdxThreads)
 adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restrict__ tab, int n_channels,
                   int16_t *__restrict__ pcm)
 {
+    __shared__ __align__(16) uint4 dec_ring[kAdxStages][9][kAdxThreads];  // [stage][16-byte chunk of the group][thread]
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_channels) return;
     const AdxChannel c = tab[ch];
@@ -134,7 +224,67 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
     int start_sample = c.padding > 0 ? c.padding % spf : 0;       // :21
     int64_t in = (int64_t)(c.padding / spf) * c.frame_size;      // :22
 
-    for (int f = 0; f < frame_count; f++) {
+    int f_first = 0;
+    if (c.frame_size == 18 && c.padding == 0) {
+        // ---- standard layout: groups of 8 whole frames (144 B = nine 16-byte chunks) through a cp.async ring
+        const int groups = sample_count / (32 * kAdxDecGroup);
+        const uint4 *vin = reinterpret_cast<const uint4 *>(src);  // adpcm_off is a multiple of 16
+        auto issue = [&](int g) {
+            if (g < groups) {
+#pragma unroll
+                for (int j = 0; j < 9; j++) cp_async16(&dec_ring[g % kAdxStages][j][threadIdx.x], vin + (int64_t)g * 9 + j);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int a = 0; a < kAdxStages - 1; a++) issue(a);
+        for (int g = 0; g < groups; g++) {
+            issue(g + kAdxStages - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kAdxStages - 1) : "memory");
+            uint32_t w[36];  // the group's 144 bytes
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const uint4 v = dec_ring[g % kAdxStages][j][threadIdx.x];
+                w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            }
+#pragma unroll
+            for (int fr = 0; fr < kAdxDecGroup; fr++) {
+                const int base = 18 * fr;  // byte offset of the frame inside the group (even)
+                auto byte_at = [&](int k) -> uint32_t { return (w[(base + k) >> 2] >> (((base + k) & 3) * 8)) & 0xFFu; };
+                const uint32_t b0 = byte_at(0), b1 = byte_at(1);
+                int32_t c0 = c.coef0, c1 = c.coef1;
+                if (c.type == 2) {
+                    const int k = ((int)((b0 >> 4) & 0xF) >> 1) & 3;
+                    c0 = k == 0 ? 0 : (k == 1 ? 0x0F00 : (k == 2 ? 0x1CC0 : 0x1880));
+                    c1 = k == 0 ? 0 : (k == 1 ? 0 : (k == 2 ? (int16_t)0xF300 : (int16_t)0xF240));
+                }
+                int32_t scale = (int16_t)(((b0 << 8) | b1) & 0x1FFF);
+                scale = (int16_t)(c.type == 4 ? (1 << ((12 - scale) & 31)) : scale + 1);
+                uint32_t o[16];
+#pragma unroll
+                for (int s2 = 0; s2 < 32; s2++) {
+                    const int byte = base + 2 + (s2 >> 1);
+                    const int lo_bit = (byte & 3) * 8 + ((s2 & 1) ? 0 : 4);
+                    int32_t sample = (int32_t)(w[byte >> 2] << (28 - lo_bit)) >> 28;
+                    if (v4) sample = wadd(wmul(scale, sample), wadd(wmul(hist1, c0), wmul(hist2, c1)) >> 12);
+                    else sample = wadd(wadd(wmul(scale, sample), wmul(hist1, c0) >> 12), wmul(hist2, c1) >> 12);
+                    const int32_t out = clamp16(sample);
+                    hist2 = hist1;
+                    hist1 = out;
+                    if (s2 & 1) o[s2 >> 1] |= (uint32_t)out << 16; else o[s2 >> 1] = (uint32_t)out & 0xFFFFu;
+                }
+                uint4 *vout = reinterpret_cast<uint4 *>(dst + ((int64_t)g * kAdxDecGroup + fr) * 32);  // pcm_off % 8 == 0
+#pragma unroll
+                for (int j = 0; j < 4; j++) vout[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        f_first = groups * kAdxDecGroup;
+        current = f_first * 32;
+        in = (int64_t)f_first * 18;
+    }
+
+    for (int f = f_first; f < frame_count; f++) {
         const uint32_t b0 = src[in], b1 = src[in + 1];
         const int filter_num = (int)((b0 >> 4) & 0xF) >> 1;  // :26
         int32_t c0 = c.coef0, c1 = c.coef1;
@@ -168,13 +318,13 @@ void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels
                        cudaStream_t stream)
 {
     if (n_channels <= 0) return;
-    adx_encode_kernel<<<(n_channels + 63) / 64, 64, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out);
+    adx_encode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out);
 }
 
 void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream)
 {
     if (n_channels <= 0) return;
-    adx_decode_kernel<<<(n_channels + 63) / 64, 64, 0, stream>>>(adpcm, tab, n_channels, pcm);
+    adx_decode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(adpcm, tab, n_channels, pcm);
 }
 
 }  // namespace vgb

@@ -84,7 +84,7 @@ struct DevBuf {
     }
 };
 
-constexpr int kTimers = 4;  // 0 coef phase 1, 1 coef refine, 2 encode, 3 decode
+constexpr int kTimers = 8;  // 0 coef phase 1, 1 coef refine, 2 gc encode, 3 gc decode, 4 adx encode, 5 adx decode, 6 hca encode, 7 hca decode
 constexpr int kMaxGroups = 4;  // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
 
 struct Context {
@@ -933,8 +933,10 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
     VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 2));
     VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
     CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
+    tick(4, true, st);
     launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
                       static_cast<uint8_t *>(g_ctx.adpcm.p), static_cast<int16_t *>(g_ctx.coefs.p), st);
+    tick(4, false, st);
     g_ctx.launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (history_out) CUDA_TRY(cudaMemcpyAsync(history_out, g_ctx.coefs.p, (size_t)n_channels * 2, cudaMemcpyDeviceToHost, st));
@@ -983,8 +985,10 @@ int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes
     VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
     VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, adpcm, in_len, st));
     CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
+    tick(5, true, st);
     launch_adx_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
                       static_cast<int16_t *>(g_ctx.pcm.p), st);
+    tick(5, false, st);
     g_ctx.launches += 1;
     CUDA_TRY(cudaGetLastError());
     VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
@@ -1282,9 +1286,11 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
     CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
+    tick(6, true, st);
     CUDA_TRY(launch_hca_encode(static_cast<const int16_t *>(g_ctx.pcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
                                max_frames, cfg, g_hca_tables.view, static_cast<uint8_t *>(g_ctx.adpcm.p),
                                reinterpret_cast<int32_t *>(misc + o_status), st));
+    tick(6, false, st);
     g_ctx.launches += 1;
     std::vector<int32_t> status(n_streams, 0);
     CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
@@ -1381,9 +1387,11 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
     CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
     // samples past the last frame (sample_count > frame_count * 1024 - inserted) stay zero, like a fresh short[]
     CUDA_TRY(cudaMemsetAsync(g_ctx.pcm.p, 0, (size_t)ps * 2, st));
+    tick(7, true, st);
     CUDA_TRY(launch_hca_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
                                max_frames, cfg, g_hca_tables.view, reinterpret_cast<double *>(misc + o_edge),
                                static_cast<int16_t *>(g_ctx.pcm.p), reinterpret_cast<int32_t *>(misc + o_status), st));
+    tick(7, false, st);
     g_ctx.launches += 2;
     std::vector<int32_t> status(n_streams, 0);
     CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));

@@ -3,120 +3,142 @@
 // Replaces GcAdpcmDecoder.Decode (Codecs/GcAdpcm/GcAdpcmDecoder.cs:10-54).  The recurrence
 //     s[t] = Clamp16((c1*s[t-1] + c2*s[t-2] + scale*nibble + 1024) >> 11)
 // is non-linear (the clamp), so a channel is strictly serial; parallelism is across channels: one THREAD owns one
-// channel.  To keep HBM traffic coalesced although every thread walks its own stream, a warp moves data through
-// shared memory in tiles of 16 frames per channel: 32 x 128 B of ADPCM in (one fully coalesced 128-byte row per
-// channel), 32 x 448 B of PCM out (28 coalesced 16-byte vectors per channel).
+// channel and streams it privately — no shared-memory transpose:
+//   in    groups of 4 frames = 32 B = two 16-byte cp.async copies per thread into the thread's own shared-memory ring,
+//         issued three groups (~3500 cycles of decode work) ahead so DRAM latency never reaches the recurrence; the
+//         32-byte sector a thread touches is its own, so HBM moves every ADPCM byte exactly once;
+//   out   4 frames = 56 samples = 112 B = seven 16-byte stores per thread straight from registers (fire and forget;
+//         the two halves of a 32-byte sector are merged in L2 before they reach DRAM).
+// Per sample the dependent chain is IMAD -> SHF -> VIADDMNMX.RELU (~13.5 cycles): history is kept with a +32768 bias so
+// that Clamp16 is one instruction, the bias and the rounding constant are folded into a per-frame constant, and the
+// older-sample product, nibble extraction and scale multiply sit off the chain.  All sums are wrapping int32 like the
+// reference (A.7); folding constants is exact in the ring.
+// Bound: chain latency at <= 1 warp per SM sub-partition (8192 channels = 256 warps), HBM (2.57 B/sample) above that.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vgb {
 
-constexpr int kDecWarps = 2;               // warps per CTA (64 channels)
-constexpr int kDecTileFrames = 16;         // frames per channel per tile: 128 B in, 448 B out
-constexpr int kDecInWords = kDecTileFrames * kGcFrameBytes / 4;          // 32 words per channel
-constexpr int kDecOutWords = kDecTileFrames * kGcFrameSamples * 2 / 4;   // 112 words per channel
-constexpr int kDecInPitch = kDecInWords + 1;     // 33: lane-per-channel reads hit distinct banks
-constexpr int kDecOutPitch = kDecOutWords + 1;   // 113 (odd): lane-per-channel writes hit distinct banks
+constexpr int kDecThreads = 32;      // one warp per CTA: 8192 channels -> 256 CTAs spread over all SMs
+constexpr int kDecGroupFrames = 4;   // 32 B in, 112 B out per thread
+constexpr int kDecAhead = 4;         // ring stages (kDecAhead - 1 groups in flight)
 
-__device__ __forceinline__ int32_t nibble_signed(uint32_t v) { return (int32_t)(v << 28) >> 28; }  // Helpers.cs:50-56
+namespace {
 
-__global__ void __launch_bounds__(kDecWarps * 32)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+struct DecState {
+    int32_t hb1, hb2;  // biased history (+32768): newest, older
+};
+
+// 14 samples of one frame (8 bytes in w0,w1; byte 0 = header).  out[0..6] = the 14 samples, two per word.
+__device__ __forceinline__ void gc_decode_frame(uint32_t w0, uint32_t w1, const uint32_t *coef_pairs, DecState &st, uint32_t *out)
+{
+    const uint32_t head = w0 & 0xFFu;
+    const int sp = (int)(head & 0xFu);
+    const int32_t scale = (int32_t)((1u << sp) * 2048u);
+    // a hostile header may select pairs 8..15: the reference would throw; we wrap to stay in bounds
+    const uint32_t pair = coef_pairs[(head >> 4) & 7u];
+    const int32_t c1 = (int32_t)(int16_t)(pair & 0xFFFFu), c2 = (int32_t)pair >> 16;
+    const int32_t k = wsub(1024, wmul(32768, wadd(c1, c2)));  // rounding constant minus the bias of both histories
+    int32_t hb1 = st.hb1, hb2 = st.hb2;
+#pragma unroll
+    for (int s = 0; s < 14; s++) {
+        const int byte = 1 + s / 2;
+        const uint32_t word = byte < 4 ? w0 : w1;
+        const int lo_bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);                 // position of the nibble's lowest bit
+        const int32_t q = (int32_t)(word << (28 - lo_bit)) >> 28;              // Helpers.GetHighNibbleSigned/Low (:50-56)
+        const int32_t t = wadd(wmul(c2, hb2), wadd(wmul(scale, q), k));        // off the chain
+        const int32_t v = wadd(wmul(c1, hb1), t);                              // chain: IMAD
+        const int32_t ob = __viaddmin_s32_relu(v >> 11, 32768, 65535);         // chain: SHF, VIADDMNMX.RELU
+        hb2 = hb1;
+        hb1 = ob;
+        if (s & 1) out[s / 2] |= (uint32_t)ob << 16; else out[s / 2] = (uint32_t)ob;
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) out[j] ^= 0x80008000u;  // remove the bias from both halves
+    st.hb1 = hb1;
+    st.hb2 = hb2;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kDecThreads)
 gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
                  int16_t *__restrict__ pcm, int frame_begin, int frame_end)
 {
-    extern __shared__ uint32_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *in_tile = smem + warp * (32 * kDecInPitch + 32 * kDecOutPitch);
-    uint32_t *out_tile = in_tile + 32 * kDecInPitch;
+    __shared__ uint32_t coef_smem[kDecThreads][9];  // 8 (c1 | c2 << 16) pairs per channel, odd pitch: conflict free
+    __shared__ __align__(16) uint4 ring_smem[kDecAhead][2][kDecThreads];  // [stage][half of the 32 bytes][thread]
+    const int ch = blockIdx.x * kDecThreads + threadIdx.x;
+    if (ch >= tab.n_channels) return;
 
-    const int ch0 = (blockIdx.x * kDecWarps + warp) * 32;  // first channel of this warp
-    if (ch0 >= tab.n_channels) return;
-    const int ch = ch0 + lane;
-    const bool live = ch < tab.n_channels;
-
-    const int n = live ? tab.n_samples[ch] : 0;
+    const int n = tab.n_samples[ch];
     const int n_frames = div_round_up(n, kGcFrameSamples);
-    int32_t h1 = live ? tab.hist[2 * ch] : 0, h2 = live ? tab.hist[2 * ch + 1] : 0;
-    const int16_t *my_coefs = coefs + (int64_t)(live ? ch : 0) * 16;
-
-    // frames the warp as a whole still has to visit
-    int warp_frames = n_frames;
+    const int f_hi = min(frame_end, n_frames);
+    if (frame_begin >= f_hi) return;
+    const uint8_t *src = adpcm + tab.adpcm_off[ch];
+    int16_t *dst = pcm + tab.pcm_off[ch];
+    uint32_t *pairs = coef_smem[threadIdx.x];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_frames = max(warp_frames, __shfl_xor_sync(0xFFFFFFFFu, warp_frames, o));
-    const int f_hi_warp = min(frame_end, warp_frames);
+    for (int p = 0; p < 8; p++) {
+        const uint32_t c1 = (uint16_t)coefs[(int64_t)ch * 16 + 2 * p], c2 = (uint16_t)coefs[(int64_t)ch * 16 + 2 * p + 1];
+        pairs[p] = c1 | (c2 << 16);
+    }
+    DecState st{tab.hist[2 * ch] + 32768, tab.hist[2 * ch + 1] + 32768};
 
-    for (int tf = frame_begin; tf < f_hi_warp; tf += kDecTileFrames) {
-        // ---- stage in: channel c's 128-byte row, one 4-byte word per lane
-        for (int c = 0; c < 32; c++) {
-            const int cc = ch0 + c;
-            if (cc >= tab.n_channels) break;
-            const int cn = tab.n_samples[cc];
-            const int64_t cbytes = gc_sample_count_to_byte_count(cn);
-            const int64_t b = (int64_t)tf * kGcFrameBytes + lane * 4;
-            uint32_t v = 0;
-            if (b < cbytes) v = __ldg(reinterpret_cast<const uint32_t *>(adpcm + tab.adpcm_off[cc] + b));
-            in_tile[c * kDecInPitch + lane] = v;
+    // groups of 4 whole frames whose 56 samples all exist go through the vector path
+    const int full_frames = min(f_hi, n / kGcFrameSamples);  // frames with all 14 samples
+    const int g_lo = frame_begin / kDecGroupFrames;          // frame_begin is a multiple of 16
+    const int g_hi = max(full_frames / kDecGroupFrames, g_lo);
+    const uint4 *vin = reinterpret_cast<const uint4 *>(src);
+
+    // Ring of kDecAhead groups per thread in shared memory, filled by cp.async (LDGSTS): asynchronous copies have no
+    // register scoreboard, so neither a register rotation nor the compiler's habit of sinking loads next to their
+    // first use can shorten the prefetch distance.  A thread only ever reads what it copied itself: no barrier.
+    auto issue = [&](int g) {
+        if (g < g_hi) {
+            const uint4 *p = vin + (int64_t)g * 2;
+            uint4 *slot = &ring_smem[g % kDecAhead][0][threadIdx.x];
+            cp_async16(slot, p);
+            cp_async16(slot + kDecThreads, p + 1);
         }
-        __syncwarp();
-
-        // ---- decode my channel's frames of this tile
-        const uint32_t *mine = in_tile + lane * kDecInPitch;
-        uint32_t *mine_out = out_tile + lane * kDecOutPitch;
-        const int f_hi = min(min(frame_end, n_frames), tf + kDecTileFrames);
-        for (int f = tf; f < f_hi; f++) {
-            const int i = f - tf;
-            const uint32_t w0 = mine[2 * i], w1 = mine[2 * i + 1];
-            const uint32_t head = w0 & 0xFFu;
-            const int32_t scale = (int32_t)((1u << (head & 0xFu)) * 2048u);
-            const int p = (head >> 4) & 0xF;  // a hostile header may select pairs 8..15: the reference would throw;
-            const int32_t c1 = my_coefs[(p & 7) * 2], c2 = my_coefs[(p & 7) * 2 + 1];  // we wrap to stay in bounds
-            uint32_t packed = 0;
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one (possibly empty) group per step keeps the count exact
+    };
 #pragma unroll
-            for (int s = 0; s < 14; s++) {
-                const int byte = 1 + s / 2;
-                const uint32_t word = byte < 4 ? w0 : w1;
-                const uint32_t nib = (word >> ((byte & 3) * 8 + ((s & 1) ? 0 : 4))) & 0xFu;
-                const int32_t q = nibble_signed(nib);
-                const int32_t guess = wadd(wmul(c1, h1), wmul(c2, h2));
-                const int32_t out = clamp16(wadd(wadd(guess, wmul(scale, q)), 1024) >> 11);
-                h2 = h1;
-                h1 = out;
-                if (s & 1) {
-                    packed |= (uint32_t)(out & 0xFFFF) << 16;
-                    mine_out[i * 7 + s / 2] = packed;
-                } else {
-                    packed = (uint32_t)(out & 0xFFFF);
-                }
-            }
-        }
-        __syncwarp();
+    for (int a = 0; a < kDecAhead - 1; a++) issue(g_lo + a);
+    for (int g = g_lo; g < g_hi; g++) {
+        issue(g + kDecAhead - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDecAhead - 1) : "memory");  // group g has landed
+        const uint4 a = ring_smem[g % kDecAhead][0][threadIdx.x], b = ring_smem[g % kDecAhead][1][threadIdx.x];
+        uint32_t o[28];
+        gc_decode_frame(a.x, a.y, pairs, st, o);
+        gc_decode_frame(a.z, a.w, pairs, st, o + 7);
+        gc_decode_frame(b.x, b.y, pairs, st, o + 14);
+        gc_decode_frame(b.z, b.w, pairs, st, o + 21);
+        uint4 *vout = reinterpret_cast<uint4 *>(dst + (int64_t)g * kDecGroupFrames * kGcFrameSamples);
+#pragma unroll
+        for (int j = 0; j < 7; j++) vout[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-        // ---- stage out: channel c's PCM, 4 bytes per lane per step, only the samples that exist
-        for (int c = 0; c < 32; c++) {
-            const int cc = ch0 + c;
-            if (cc >= tab.n_channels) break;
-            const int cn = tab.n_samples[cc];
-            const int64_t s0 = (int64_t)tf * kGcFrameSamples;  // first sample of the tile
-            int64_t avail = min((int64_t)cn, (int64_t)min(frame_end, tf + kDecTileFrames) * kGcFrameSamples) - s0;
-            if (avail <= 0) continue;
-            int16_t *dst = pcm + tab.pcm_off[cc] + s0;
-            const uint32_t *srcw = out_tile + c * kDecOutPitch;
-            for (int wi = lane; wi < kDecOutWords; wi += 32) {
-                const int64_t s = (int64_t)wi * 2;
-                if (s + 1 < avail) {
-                    *reinterpret_cast<uint32_t *>(dst + s) = srcw[wi];
-                } else if (s < avail) {
-                    dst[s] = (int16_t)(srcw[wi] & 0xFFFFu);
-                }
-            }
-        }
-        __syncwarp();
+    // the rest (< 4 whole frames, and the channel's partial last frame): byte loads, only the samples that exist
+    for (int f = max(g_hi * kDecGroupFrames, frame_begin); f < f_hi; f++) {
+        const int take = min(kGcFrameSamples, n - f * kGcFrameSamples);
+        const int bytes = 1 + (take + 1) / 2;  // header + nibble bytes present (SampleCountToByteCount)
+        uint32_t w[2] = {0, 0};  // bytes the stream does not hold decode as zero nibbles; those samples are not written
+        for (int j = 0; j < bytes; j++) w[j >> 2] |= (uint32_t)src[(int64_t)f * kGcFrameBytes + j] << ((j & 3) * 8);
+        uint32_t o[7];
+        gc_decode_frame(w[0], w[1], pairs, st, o);
+        int16_t *d = dst + (int64_t)f * kGcFrameSamples;
+        for (int s = 0; s < take; s++) d[s] = (int16_t)((o[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu);
     }
 
-    if (live) {  // carried into the next time slice of the same call
-        tab.hist[2 * ch] = (int16_t)h1;
-        tab.hist[2 * ch + 1] = (int16_t)h2;
-    }
+    tab.hist[2 * ch] = (int16_t)(st.hb1 - 32768);  // carried into the next time slice of the same call
+    tab.hist[2 * ch + 1] = (int16_t)(st.hb2 - 32768);
 }
 
 void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, int16_t *pcm,
@@ -124,10 +146,8 @@ void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int
 {
     if (tab.n_channels <= 0 || max_frames <= 0) return;
     if (frame_begin >= frame_end || frame_begin >= max_frames) return;
-    const int ch_per_block = kDecWarps * 32;
-    int blocks = (tab.n_channels + ch_per_block - 1) / ch_per_block;
-    size_t smem = (size_t)kDecWarps * (32 * kDecInPitch + 32 * kDecOutPitch) * sizeof(uint32_t);
-    gc_decode_kernel<<<blocks, kDecWarps * 32, smem, stream>>>(adpcm, tab, coefs, pcm, frame_begin, frame_end);
+    const int blocks = (tab.n_channels + kDecThreads - 1) / kDecThreads;
+    gc_decode_kernel<<<blocks, kDecThreads, 0, stream>>>(adpcm, tab, coefs, pcm, frame_begin, frame_end);
 }
 
 }  // namespace vgb
