@@ -13,7 +13,8 @@
 //   allocation  CalculateUsedBits is an integer sum -> block reduction; the two binary searches (noise level,
 //               evaluation boundary) run ~16 probes of it
 //   order-sensitive fp64 sums (intensity stereo energies, HFR group averages) stay sequential inside one thread each
-//   pack        one thread appends the bits (MSB first) and computes the CRC; the frame leaves with coalesced stores
+//   pack        thread = band sizes and places its own codes (two warp-scan passes over the stream's sections, bits
+//               ORed into big-endian words), the CRC is folded by one warp using its linearity
 // fp64 throughout like the reference (A.14); with identical tables and operation order the frames are byte-identical
 // to the oracle.  ALU/latency bound: ~135 ops per sample, algorithmic traffic 2 B/sample in +
 // frame_size/1024 B/sample out.
@@ -25,6 +26,7 @@ namespace vgb {
 namespace {
 
 constexpr int kSub = 8, kBins = 128, kFrame = 1024;
+constexpr int kMaxSections = 8 + kSub * 8;  // packer: one header per channel + one code row per (subframe, channel)
 
 __device__ __forceinline__ double dclamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -73,20 +75,6 @@ struct BlockSum {  // integer sum over the 128 threads of the CTA, result in eve
         if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
         __syncthreads();
         return scratch[0] + scratch[1] + scratch[2] + scratch[3];
-    }
-};
-
-struct BitAppender {  // BitWriter.Write on a zeroed buffer: MSB-first append (BitWriter.cs:26-70)
-    uint8_t *buf;
-    int pos, length_bits;
-    bool overflow;
-    __device__ void write(int value, int count)
-    {
-        if (count > length_bits - pos) { overflow = true; return; }
-        for (int i = count - 1; i >= 0; i--) {
-            if ((value >> i) & 1) buf[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
-            pos++;
-        }
     }
 };
 
@@ -398,66 +386,164 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
 #pragma unroll
         for (int sf = 0; sf < kSub; sf++) quantized[((size_t)c * kSub + sf) * kBins + b] = q[sf];
     }
-    for (int b = tid; b < cfg.frame_size; b += blockDim.x) frame_buf[b] = 0;
-    __syncthreads();
+    // ---- PackFrame (CriHcaPacking.cs:17-58), in parallel.  The bitstream is a sequence of SECTIONS - one header per
+    // channel (WriteScaleFactors :262-295 + intensity / HFR scales), then one row of spectral codes per (subframe,
+    // channel) (WriteSpectra :238-260) - and inside a section thread = band owns one element (0..3 short codes).
+    // Pass A sizes every element (warp scans -> per-warp totals), thread 0 turns the totals into section offsets,
+    // pass B recomputes the codes and ORs them into the frame at their bit positions.  The frame is held as big-endian
+    // 32-bit words in shared memory (bit p of the stream = bit 31 - p%32 of word p/32), converted on the way out.
+    uint32_t *words = reinterpret_cast<uint32_t *>(frame_buf);
+    const int n_words = (cfg.frame_size + 3) >> 2;
+    int *warp_tot = reinterpret_cast<int *>(scaled);      // [sections][4]   (`scaled` is dead after quantisation)
+    int *sec_base = warp_tot + kMaxSections * 4;          // [sections]
+    int *pack_flag = sec_base + kMaxSections;             // [1] overflow
+    __syncthreads();                                      // all reads of `scaled` are done
+    for (int w = tid; w < ((cfg.frame_size + 15) & ~15) / 4; w += blockDim.x) words[w] = 0;
+    if (tid == 0) *pack_flag = 0;
+    const int n_sections = nch + kSub * nch;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int capacity = cfg.frame_size * 8;              // BitWriter over the whole frame buffer (BitWriter.cs:26-33)
 
-    // ---- PackFrame (CriHcaPacking.cs:17-58): one thread appends the bits, then the CRC (Crc16.cs)
-    if (tid == 0) {
-        BitAppender w{frame_buf, 0, cfg.frame_size * 8, false};
-        w.write(0xffff, 16);
-        w.write(noise_level, 9);
-        w.write(eval_boundary, 7);
-        for (int c = 0; c < nch; c++) {
-            const HcaChannelState &ch = chs[c];
-            const int delta_bits = ch.delta_bits;  // WriteScaleFactors (:262-295)
-            w.write(delta_bits, 3);
-            if (delta_bits == 6) {
-                for (int b = 0; b < ch.coded_count; b++) w.write(ch.scale_factors[b], 6);
-            } else if (delta_bits != 0) {
-                w.write(ch.scale_factors[0], 6);
-                const int max_delta = (1 << (delta_bits - 1)) - 1;
-                const int escape = (1 << delta_bits) - 1;
-                for (int b = 1; b < ch.coded_count; b++) {
-                    const int delta = ch.scale_factors[b] - ch.scale_factors[b - 1];
-                    if (abs(delta) > max_delta) {
-                        w.write(escape, delta_bits);
-                        w.write(ch.scale_factors[b], 6);
+    // the codes thread `tid` contributes to section `sec`, in stream order, through emit(value, bit count)
+    auto element = [&](int sec, auto &&emit) {
+        if (sec < nch) {
+            const HcaChannelState &ch = chs[sec];
+            const int db = ch.delta_bits, b = tid;
+            if (b == 0) emit((uint32_t)db, 3);
+            if (b < ch.coded_count) {
+                if (db == 6) {
+                    emit((uint32_t)ch.scale_factors[b], 6);
+                } else if (db != 0) {
+                    if (b == 0) {
+                        emit((uint32_t)ch.scale_factors[0], 6);
                     } else {
-                        w.write(max_delta + delta, delta_bits);
+                        const int max_delta = (1 << (db - 1)) - 1, escape = (1 << db) - 1;
+                        const int delta = ch.scale_factors[b] - ch.scale_factors[b - 1];
+                        if (abs(delta) > max_delta) {
+                            emit((uint32_t)escape, db);
+                            emit((uint32_t)ch.scale_factors[b], 6);
+                        } else {
+                            emit((uint32_t)(max_delta + delta), db);
+                        }
                     }
                 }
             }
-            if (ch.type == 2) {
-                for (int sf = 0; sf < kSub; sf++) w.write(ch.intensity[sf], 4);
-            } else if (cfg.hfr_group_count > 0) {
-                for (int g = 0; g < cfg.hfr_group_count; g++) w.write(ch.hfr_scales[g], 6);
+            if (b == max(ch.coded_count - 1, 0)) {  // the channel's trailer rides behind its last scale factor
+                if (ch.type == 2) {
+                    for (int sf = 0; sf < kSub; sf++) emit((uint32_t)ch.intensity[sf], 4);
+                } else if (cfg.hfr_group_count > 0) {
+                    for (int g = 0; g < cfg.hfr_group_count; g++) emit((uint32_t)ch.hfr_scales[g], 6);
+                }
+            }
+        } else {
+            const int row = sec - nch, sf = row / nch, c = row - sf * nch, b = tid;
+            const HcaChannelState &ch = chs[c];
+            if (b < ch.coded_count) {
+                const int resolution = ch.resolution[b];
+                const int q = quantized[((size_t)c * kSub + sf) * kBins + b];
+                if (resolution != 0) {
+                    if (resolution < 8) {
+                        emit((uint32_t)T.quantize_value[resolution][q + 8], (int)T.quantize_bits[resolution][q + 8]);
+                    } else {
+                        emit((uint32_t)abs(q), (int)T.quantized_max_bits[resolution] - 1);
+                        if (q != 0) emit(q > 0 ? 0u : 1u, 1);
+                    }
+                }
             }
         }
-        for (int sf = 0; sf < kSub; sf++)  // WriteSpectra (:238-260)
-            for (int c = 0; c < nch; c++) {
-                const HcaChannelState &ch = chs[c];
-                for (int b = 0; b < ch.coded_count; b++) {
-                    const int resolution = ch.resolution[b];
-                    const int q = quantized[((size_t)c * kSub + sf) * kBins + b];
-                    if (resolution == 0) continue;
-                    if (resolution < 8) {
-                        w.write(T.quantize_value[resolution][q + 8], T.quantize_bits[resolution][q + 8]);
-                    } else {
-                        w.write(abs(q), T.quantized_max_bits[resolution] - 1);
-                        if (q != 0) w.write(q > 0 ? 0 : 1, 1);
-                    }
+    };
+    auto warp_inclusive = [&](int v) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += up;
+        }
+        return v;
+    };
+
+    for (int sec = 0; sec < n_sections; sec++) {  // pass A
+        int len = 0;
+        element(sec, [&](uint32_t, int n) { len += n; });
+        const int incl = warp_inclusive(len);
+        if (lane == 31) warp_tot[sec * 4 + warp] = incl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int running = 32;  // sync word, noise level, evaluation boundary
+        for (int sec = 0; sec < n_sections; sec++) {
+            sec_base[sec] = running;
+            running += warp_tot[sec * 4] + warp_tot[sec * 4 + 1] + warp_tot[sec * 4 + 2] + warp_tot[sec * 4 + 3];
+        }
+        if (running > capacity) *pack_flag = 1;  // InvalidOperationException (BitWriter.cs:30-33)
+        words[0] = 0xffff0000u | ((uint32_t)noise_level << 7) | (uint32_t)eval_boundary;  // 16 + 9 + 7 bits
+    }
+    __syncthreads();
+    for (int sec = 0; sec < n_sections; sec++) {  // pass B
+        int len = 0;
+        element(sec, [&](uint32_t, int n) { len += n; });
+        int pos = sec_base[sec] + warp_inclusive(len) - len;
+        for (int w = 0; w < warp; w++) pos += warp_tot[sec * 4 + w];
+        element(sec, [&](uint32_t value, int n) {
+            if (n > 0 && pos + n <= capacity) {
+                const int w = pos >> 5, sh = 32 - (pos & 31) - n;
+                if (sh >= 0) {
+                    atomicOr(&words[w], value << sh);
+                } else {
+                    atomicOr(&words[w], value >> -sh);
+                    atomicOr(&words[w + 1], value << (32 + sh));
                 }
             }
-        if (w.overflow && !status) status = VGB_HCA_BIT_OVERFLOW;  // InvalidOperationException (BitWriter.cs:30-33)
-        uint16_t crc = 0;  // WriteChecksum (:231-236)
-        for (int b = 0; b < cfg.frame_size - 2; b++) crc = (uint16_t)((crc << 8) ^ T.crc_table[(crc >> 8) ^ frame_buf[b]]);
-        frame_buf[cfg.frame_size - 2] = (uint8_t)(crc >> 8);
-        frame_buf[cfg.frame_size - 1] = (uint8_t)crc;
-        if (status) atomicCAS(status_out + s, 0, status);
+            pos += n;
+        });
+    }
+    __syncthreads();
+    if (*pack_flag && !status) status = VGB_HCA_BIT_OVERFLOW;
+
+    // ---- WriteChecksum (:231-236, Crc16.cs): CRC-16 (poly 0x8005, init 0) is linear and ignores leading zero bytes,
+    // so the message is right-aligned into 32 equal segments, one per lane of warp 0, and the partial CRCs are folded
+    // pairwise: crc(A || B) = crc(A) * x^(8 |B|) + crc(B) in GF(2)[x] / P.
+    if (warp == 0) {
+        const int n_msg = cfg.frame_size - 2;
+        const int seg = (n_msg + 31) / 32, pad = seg * 32 - n_msg;
+        auto byte_at = [&](int i) -> uint32_t { return (words[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu; };
+        auto mulmod = [](uint32_t a, uint32_t bb) {  // a * bb mod x^16 + x^15 + x^2 + 1
+            uint32_t r = 0;
+#pragma unroll
+            for (int i = 15; i >= 0; i--) {
+                r <<= 1;
+                if (r & 0x10000u) r ^= 0x18005u;
+                if ((bb >> i) & 1u) r ^= a;
+            }
+            return r;
+        };
+        uint32_t crc = 0;
+        for (int j = 0; j < seg; j++) {
+            const int i = lane * seg + j - pad;
+            const uint32_t byte = i >= 0 ? byte_at(i) : 0u;
+            crc = ((crc << 8) & 0xFFFFu) ^ T.crc_table[(crc >> 8) ^ byte];
+        }
+        uint32_t shift = 1;  // x^(8 * seg): multiplier for a right neighbour of one segment
+        for (int j = 0; j < 8 * seg; j++) {
+            shift <<= 1;
+            if (shift & 0x10000u) shift ^= 0x18005u;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, crc, o);
+            if ((lane & (2 * o - 1)) == 0) crc = mulmod(crc, shift) ^ right;
+            shift = mulmod(shift, shift);
+        }
+        if (lane == 0) {  // big-endian CRC in the last two bytes
+            const int i0 = cfg.frame_size - 2, i1 = cfg.frame_size - 1;
+            atomicOr(&words[i0 >> 2], ((crc >> 8) & 0xFFu) << (24 - 8 * (i0 & 3)));
+            atomicOr(&words[i1 >> 2], (crc & 0xFFu) << (24 - 8 * (i1 & 3)));
+            if (status) atomicCAS(status_out + s, 0, status);
+        }
     }
     __syncthreads();
     uint8_t *dst = frames_out + st.frames_off + (int64_t)k * cfg.frame_size;
-    for (int b = tid; b < cfg.frame_size; b += blockDim.x) dst[b] = frame_buf[b];
+    for (int b = tid; b < cfg.frame_size; b += blockDim.x) dst[b] = (uint8_t)(words[b >> 2] >> (24 - 8 * (b & 3)));
+    (void)n_words;
 }
 
 // ==========================================================================================================
@@ -476,20 +562,29 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
 
 namespace {
 
-struct BitPeeker {  // BitReader.PeekInt / Position (Utilities/BitReader.cs:51-99): bits past the end read as zero
-    const uint8_t *buf;
-    int pos, length_bits;
-    __device__ int peek(int count) const
+// BitReader.ReadInt / PeekInt (Utilities/BitReader.cs:51-99) over a frame held as big-endian 32-bit words: a 64-bit
+// window keeps the next bits left-aligned, so a read is a shift and a refill happens once per 32 consumed bits.
+// Bits past the end of the frame read as zero, like the reference.
+struct BitWindow {
+    const uint32_t *words;
+    int n_words, next;
+    uint64_t win;
+    int avail;
+    __device__ uint32_t word(int i) const { return i < n_words ? words[i] : 0u; }
+    __device__ void open(const uint32_t *w, int n)
     {
-        int v = 0;
-        for (int i = 0; i < count; i++) {
-            const int p = pos + i;
-            const int bit = p < length_bits ? (buf[p >> 3] >> (7 - (p & 7))) & 1 : 0;
-            v = (v << 1) | bit;
-        }
-        return v;
+        words = w; n_words = n;
+        win = ((uint64_t)word(0) << 32) | word(1);
+        avail = 64; next = 2;
     }
-    __device__ int read(int count) { const int v = peek(count); pos += count; return v; }
+    __device__ uint32_t peek(int count) const { return (uint32_t)((win >> 1) >> (63 - count)); }  // count 0..32
+    __device__ void skip(int count)
+    {
+        win <<= count;
+        avail -= count;
+        if (avail <= 32) { win |= (uint64_t)word(next++) << (32 - avail); avail += 32; }
+    }
+    __device__ int read(int count) { const uint32_t v = peek(count); skip(count); return (int)v; }
 };
 
 // PcmFloatToShort (CriHcaDecoder.cs:168-181)
@@ -508,6 +603,8 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
                          int32_t *__restrict__ status_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint8_t s_dbits[8][16], s_maxbits[16];
+    __shared__ int8_t s_dval[8][16];
     const int nch = cfg.channel_count;
     double *spectra = reinterpret_cast<double *>(smem_raw);                   // [nch][8][128]
     double *work = spectra + (size_t)nch * kSub * kBins;                      // [2][128]
@@ -521,7 +618,20 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
     if (k >= st.frame_count) return;
 
     const uint8_t *src = frames + st.frames_off + (int64_t)k * cfg.frame_size;
-    for (int b = tid; b < cfg.frame_size; b += blockDim.x) frame_buf[b] = src[b];
+    uint32_t *words = reinterpret_cast<uint32_t *>(frame_buf);  // big-endian words, zero beyond the frame
+    const int n_words = (cfg.frame_size + 3) >> 2;
+    for (int w = tid; w < n_words; w += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (4 * w + j < cfg.frame_size) v |= (uint32_t)src[4 * w + j] << (24 - 8 * j);
+        words[w] = v;
+    }
+    if (tid < 128) {  // the small code tables move next to the parser
+        s_dbits[tid >> 4][tid & 15] = T.dequantize_bits[tid >> 4][tid & 15];
+        s_dval[tid >> 4][tid & 15] = T.dequantize_value[tid >> 4][tid & 15];
+        if (tid < 16) s_maxbits[tid] = T.quantized_max_bits[tid];
+    }
     if (tid < nch) {
         chs[tid].type = cfg.channel_type[tid];
         chs[tid].coded_count = cfg.channel_type[tid] == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
@@ -530,7 +640,8 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
 
     // ---- UnpackFrame: serial bit parsing by one thread
     if (tid == 0) {
-        BitPeeker r{frame_buf, 0, cfg.frame_size * 8};
+        BitWindow r;
+        r.open(words, n_words);
         int status = 0;
         if (r.read(16) != 0xffff) status = VGB_HCA_BAD_SYNC;
         const int noise_level = r.read(9);
@@ -581,17 +692,18 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
                     int *q = quantized + ((size_t)c * kSub + sf) * kBins;
                     for (int b = 0; b < ch.coded_count; b++) {
                         const int resolution = ch.resolution[b];
-                        int bits = T.quantized_max_bits[resolution];
-                        const int code = r.peek(bits);
+                        int bits = s_maxbits[resolution];
+                        const int code = (int)r.peek(bits);
+                        int v;
                         if (resolution < 8) {
-                            bits = T.dequantize_bits[resolution][code];
-                            q[b] = T.dequantize_value[resolution][code];
+                            bits = s_dbits[resolution][code];
+                            v = s_dval[resolution][code];
                         } else {
-                            const int v = code / 2 * (1 - (code % 2 * 2));
+                            v = code / 2 * (1 - (code % 2 * 2));
                             if (v == 0) bits--;
-                            q[b] = v;
                         }
-                        r.pos += bits;
+                        q[b] = v;
+                        r.skip(bits);
                     }
                 }
         } else {
