@@ -27,6 +27,7 @@ namespace VGAudio.Native
         public int HeaderSize, FrameSize, MinResolution, MaxResolution, TrackCount, ChannelConfig;
         public int TotalBandCount, BaseBandCount, StereoBandCount, HfrBandCount, BandsPerHfrGroup, HfrGroupCount;
         public int Bitrate;
+        public int Looping, LoopStartFrame, LoopEndFrame, PreLoopSamples, PostLoopSamples;  // HcaInfo.cs:29-33
     }
 
     internal static unsafe class VgAudioB200Cri
@@ -104,8 +105,8 @@ namespace VGAudio.Formats.CriHca
 {
     public partial class CriHcaFormat
     {
-        // replaces the frame loop of CriHcaFormat.EncodeFromPcm16 (Formats/CriHca/CriHcaFormat.cs:43-81) for a
-        // non-looping stream: returns byte[FrameCount][FrameSize] and the HcaInfo CriHcaEncoder.Initialize computes.
+        // replaces the frame loop of CriHcaFormat.EncodeFromPcm16 (Formats/CriHca/CriHcaFormat.cs:43-81), looping
+        // streams included: returns byte[FrameCount][FrameSize] and the HcaInfo CriHcaEncoder.Initialize computes.
         private static unsafe byte[][] EncodeFramesB200(Pcm16Format pcm16, CriHcaParameters config, out Native.VgbHcaInfo info)
         {
             int nch = pcm16.ChannelCount;

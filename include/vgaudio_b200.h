@@ -183,7 +183,6 @@ int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes
 /* ---------------------------------------------------------------------------------------------------------
  * CRI HCA encode (Codecs/CriHca/CriHcaEncoder.cs), host buffers.  One call replaces CriHcaFormat.EncodeFromPcm16
  * (Formats/CriHca/CriHcaFormat.cs:34-84, single-threaded in the reference) for a batch of streams.
- * Round-1 restriction: non-looping streams (params.looping must be 0).
  * ------------------------------------------------------------------------------------------------------- */
 
 /* Mirror of CriHcaParameters : CodecParameters (Codecs/CriHca/CriHcaParameters.cs:3-15).
@@ -200,6 +199,7 @@ typedef struct vgb_hca_info {
     int32_t header_size, frame_size, min_resolution, max_resolution, track_count, channel_config;
     int32_t total_band_count, base_band_count, stereo_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
     int32_t bitrate;
+    int32_t looping, loop_start_frame, loop_end_frame, pre_loop_samples, post_loop_samples; /* HcaInfo.cs:29-33 */
 } vgb_hca_info;
 
 /* CriHcaEncoder.Initialize (CriHcaEncoder.cs:61-114): stream parameters for one configuration, so the caller can
@@ -207,9 +207,11 @@ typedef struct vgb_hca_info {
 int32_t vgb_hca_query(const vgb_hca_params *params, vgb_hca_info *info_out);
 
 /* Encode n_streams streams.  All streams of a call share channel_count / sample_rate / quality / bitrate /
- * limit_bitrate (one band layout); sample_count may differ.  pcm is a flat table [n_streams * channel_count]
+ * limit_bitrate (one band layout); sample_count and the loop points may differ.  For a looping stream
+ * params.sample_count is the PCM length the caller holds, info.sample_count becomes min(loop_end, sample_count)
+ * (CriHcaEncoder.cs:89-99).  pcm is a flat table [n_streams * channel_count]
  * (stream-major) of channel pointers, frames_out[s] receives frame_count(s) * frame_size bytes, info_out is
- * [n_streams].  Errors: VGB_E_ARG (> 8 channels, mismatched streams, looping), VGB_E_DATA ("Bitrate is set too
+ * [n_streams].  Errors: VGB_E_ARG (> 8 channels, mismatched streams, loop points outside 0 <= start < end, start < sample_count), VGB_E_DATA ("Bitrate is set too
  * low.", CriHcaEncoder.cs:469-472), VGB_E_STATE (bit writer overflow). */
 int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
                              vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user);

@@ -189,7 +189,8 @@ class HcaInfo(C.Structure):
         "channel_count", "sample_rate", "sample_count", "frame_count", "inserted_samples", "appended_samples",
         "header_size", "frame_size", "min_resolution", "max_resolution", "track_count", "channel_config",
         "total_band_count", "base_band_count", "stereo_band_count", "hfr_band_count", "bands_per_hfr_group",
-        "hfr_group_count", "bitrate")]
+        "hfr_group_count", "bitrate", "looping", "loop_start_frame", "loop_end_frame", "pre_loop_samples",
+        "post_loop_samples")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -201,8 +202,10 @@ def _chan_table(channels):
     return arrs, tab
 
 
-def hca_params(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False) -> HcaParams:
-    return HcaParams(quality, bitrate, int(limit_bitrate), len(channels), sample_rate, len(channels[0]), 0, 0, 0)
+def hca_params(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None) -> HcaParams:
+    """loop = (loop_start, loop_end) in samples or None (Pcm16Format.Looping / LoopStart / LoopEnd)."""
+    looping, ls, le = (1, int(loop[0]), int(loop[1])) if loop else (0, 0, 0)
+    return HcaParams(quality, bitrate, int(limit_bitrate), len(channels), sample_rate, len(channels[0]), looping, ls, le)
 
 
 def hca_init(params: HcaParams) -> HcaInfo:
@@ -213,10 +216,10 @@ def hca_init(params: HcaParams) -> HcaInfo:
     return info
 
 
-def hca_encode(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False):
-    """CriHcaFormat.EncodeFromPcm16 for one non-looping stream -> (HcaInfo, frames[frame_count, frame_size])."""
+def hca_encode(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None):
+    """CriHcaFormat.EncodeFromPcm16 for one stream -> (HcaInfo, frames[frame_count, frame_size])."""
     arrs, tab = _chan_table(channels)
-    p = hca_params(arrs, sample_rate, quality, bitrate, limit_bitrate)
+    p = hca_params(arrs, sample_rate, quality, bitrate, limit_bitrate, loop)
     info = hca_init(p)
     frames = np.zeros((info.frame_count, info.frame_size), dtype=np.uint8)
     rc = lib().vgo_hca_encode(tab, C.byref(p), C.byref(info), frames.ctypes.data)

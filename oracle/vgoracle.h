@@ -83,7 +83,7 @@ void vgo_adx_decode(const uint8_t *adpcm, int sample_count, int sample_rate, int
                     int version, int history, int padding, int type, int16_t *pcm_out);
 
 /* ---- CRI HCA (Codecs/CriHca, Utilities/Mdct.cs) — tables pinned by the reference's test literals, frame bytes
- * PARITY UNPINNED (the reference never runs its encoder/decoder in a test); non-looping streams only ---- */
+ * PARITY UNPINNED (the reference never runs its encoder/decoder in a test) ---- */
 typedef struct vgo_hca_params { /* CriHcaParameters.cs:3-15 (+ CodecParameters.SampleCount) */
     int32_t quality;       /* CriHcaQuality: 0 NotSet, 1 Highest, 2 High, 3 Middle, 4 Low, 5 Lowest */
     int32_t bitrate;       /* 0 = derive from quality */
@@ -96,6 +96,7 @@ typedef struct vgo_hca_info { /* HcaInfo.cs:5-48, the fields the codec uses */
     int32_t header_size, frame_size, min_resolution, max_resolution, track_count, channel_config;
     int32_t total_band_count, base_band_count, stereo_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
     int32_t bitrate;
+    int32_t looping, loop_start_frame, loop_end_frame, pre_loop_samples, post_loop_samples; /* HcaInfo.cs:29-33 */
 } vgo_hca_info;
 int vgo_hca_init(const vgo_hca_params *p, vgo_hca_info *info_out);              /* CriHcaEncoder.Initialize :61-114 */
 int vgo_hca_encode(const int16_t *const *pcm, const vgo_hca_params *p, vgo_hca_info *info_out, uint8_t *frames_out);

@@ -70,8 +70,9 @@ def test_query_matches_c4_numbers(vg):
 def test_errors(vg):
     with pytest.raises(vg.VgbError):   # > 8 channels: ArgumentOutOfRangeException (CriHcaEncoder.cs:63-66)
         vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=9, sample_rate=48000, sample_count=100))
-    with pytest.raises(vg.VgbError):   # looping not implemented in round 1
-        vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=1, sample_rate=48000, sample_count=100, looping=True))
+    with pytest.raises(vg.VgbError):   # loop points the streaming front end has no defined behaviour for
+        vg.crihca.query(vg.crihca.CriHcaParameters(channel_count=1, sample_rate=48000, sample_count=100, looping=True,
+                                                   loop_start=50, loop_end=50))
     with pytest.raises(vg.VgbError) as e:  # "Bitrate is set too low." (CriHcaEncoder.cs:469-472)
         vg.crihca.encode([synth.channel(7, 5000)], 48000, vg.crihca.CriHcaParameters(bitrate=900))
     assert e.value.code == -2
@@ -138,3 +139,47 @@ def test_decode_bad_sync_word(vg):
     with pytest.raises(vg.VgbError) as e:  # InvalidDataException("Invalid frame header")
         vg.crihca.decode(info, frames)
     assert e.value.code == -2
+
+
+# ---- looping streams: the kernel's virtual input stream against the oracle's literal restatement of the streaming
+# front end (CriHcaEncoder.Encode :126-272 driven chunk by chunk like CriHcaFormat.EncodeFromPcm16 :53-81)
+
+LOOPS = [(5000, 25000), (0, 30000), (1024, 20000), (29000, 30000), (29900, 30000), (100, 500), (2048, 2049),
+         (12345, 23456), (1, 2), (29999, 31000), (28000, 40000), (3000, 3072), (1023, 1025)]
+
+
+@pytest.mark.parametrize("loop", LOOPS)
+def test_looping_frames_byte_identical_to_oracle(vg, oracle, loop):
+    n = 30000
+    for nch, quality in [(1, 2), (2, 5)]:
+        chans = [synth.channel(500 + c, n, degenerate=False) for c in range(nch)]
+        cfg = vg.crihca.CriHcaParameters(quality=quality, looping=True, loop_start=loop[0], loop_end=loop[1])
+        info, frames = vg.crihca.encode(chans, 48000, cfg)
+        o_info, o_frames = oracle.hca_encode(chans, 48000, quality, loop=loop)
+        assert info.as_dict() == o_info.as_dict()
+        same = (frames == o_frames).all(axis=1)
+        assert same.all(), f"{loop} {nch}ch: frames {np.flatnonzero(~same)[:8]} differ"
+        pcm = np.stack(vg.crihca.decode(info, frames))
+        assert np.array_equal(pcm, oracle.hca_decode(o_info, o_frames))
+
+
+def test_looping_batch_with_different_loop_points(vg, oracle):
+    lens = [9000, 30000, 4096, 20000]
+    loops = [(100, 9000), (5000, 25000), (0, 4096), (1024, 3000)]
+    streams = [[synth.channel(600 + i, lens[i], degenerate=False)] for i in range(4)]
+    params = (vg._native.VgbHcaParams * 4)()
+    import ctypes as C
+    for i in range(4):
+        params[i] = vg._native.VgbHcaParams(2, 0, 0, 1, 48000, lens[i], 1, loops[i][0], loops[i][1])
+    infos = (vg._native.VgbHcaInfo * 4)()
+    for i in range(4):
+        vg._native.check(vg.lib.vgb_hca_query(C.byref(params[i]), C.byref(infos[i])))
+    outs = [np.zeros((infos[i].frame_count, infos[i].frame_size), np.uint8) for i in range(4)]
+    arrs = [np.ascontiguousarray(s[0]) for s in streams]
+    ptab = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+    otab = (C.c_void_p * 4)(*[o.ctypes.data for o in outs])
+    vg._native.check(vg.lib.vgb_hca_encode_batch(ptab, C.cast(params, C.c_void_p), 4, C.cast(infos, C.c_void_p), otab, None, None))
+    for i in range(4):
+        o_info, o_frames = oracle.hca_encode(streams[i], 48000, 2, loop=loops[i])
+        assert infos[i].as_dict() == o_info.as_dict()
+        assert np.array_equal(outs[i], o_frames), i

@@ -108,3 +108,50 @@ def test_silence_and_short_inputs(oracle):
         assert frames.shape[0] == (n + 128 + 1023) // 1024
         dec = oracle.hca_decode(info, frames)
         assert not dec.any()
+
+
+# ---- looping (CriHcaEncoder.Initialize :89-99, CalculateLoopInfo :383-398, CalculateHeaderSize :400-418 and the
+# streaming front end :126-272).  The reference has no test for it: the restatement is held to the format's invariants.
+
+@pytest.mark.parametrize("loop", [(5000, 25000), (0, 30000), (1024, 20000), (29000, 30000), (29900, 30000), (100, 500),
+                                  (2048, 2049), (12345, 23456)])
+def test_looping_stream_invariants(oracle, loop):
+    n = 30000
+    x = synth.reference_sine(n, 440, 48000)
+    info, frames = oracle.hca_encode([x], 48000, 2, loop=loop)
+    d = info.as_dict()
+    assert d["looping"] == 1 and d["sample_count"] == min(loop[1], n)
+    # HcaInfo.LoopStartSample / LoopEndSample (HcaInfo.cs:35-36) give the requested loop points back
+    assert d["loop_start_frame"] * 1024 + d["pre_loop_samples"] - d["inserted_samples"] == loop[0]
+    assert (d["loop_end_frame"] + 1) * 1024 - d["post_loop_samples"] - d["inserted_samples"] == loop[1]
+    # the loop start lands one subframe (the codec delay) into a frame, and that frame on a 2048-byte file boundary
+    assert d["pre_loop_samples"] == 128
+    assert (d["header_size"] + d["frame_size"] * d["loop_start_frame"]) % 2048 == 0
+    assert d["frame_count"] * 1024 == d["inserted_samples"] + d["appended_samples"] + min(-(-d["sample_count"] // 128) * 128, n) + 256
+    # the stream decodes to the input up to the loop end ...
+    y = oracle.hca_decode(info, frames)[0].astype(np.float64)
+    sc = d["sample_count"]
+    assert np.sqrt(((y[:sc] - x[:sc]) ** 2).mean()) < 150
+    # ... and what follows the loop end inside the last frames is the audio of the loop start (seamless wrap-around):
+    # decode with a sample count that exposes the appended audio
+    import copy
+    wide = copy.copy(info)
+    extra = min(128, d["frame_count"] * 1024 - d["inserted_samples"] - sc)
+    wide.sample_count = sc + extra
+    z = oracle.hca_decode(wide, frames)[0].astype(np.float64)
+    if extra >= 64 and loop[0] + extra <= n:
+        wrap = np.sqrt(((z[sc:sc + extra] - x[loop[0]:loop[0] + extra]) ** 2).mean())
+        assert wrap < 2000  # the phase jump at the loop end costs some coding noise
+        if sc + extra <= n and abs((loop[1] - loop[0]) % 109 - 54) < 40:  # 440 Hz at 48 kHz: period ~109 samples
+            assert wrap < 0.5 * np.sqrt(((z[sc:sc + extra] - x[sc:sc + extra]) ** 2).mean())
+
+
+def test_non_looping_streaming_front_end_equals_plain_windows(oracle):
+    """For a non-looping stream the streaming front end reduces to: frame k = k-th 1024-sample window, then zeros.
+    The MDCT tap (plain windows) followed by the rest of the frame pipeline is what the golden frames were made from
+    before the front end was restated; the frames must not have moved."""
+    x = synth.channel(3, 5000)
+    info, frames = oracle.hca_encode([x], 48000, 2)
+    assert info.frame_count == (5000 + 128 + 1023) // 1024 and info.inserted_samples == 128
+    y = oracle.hca_decode(info, frames)[0].astype(np.float64)
+    assert np.sqrt(((y - x) ** 2).mean()) < 0.25 * np.sqrt((x.astype(np.float64) ** 2).mean())

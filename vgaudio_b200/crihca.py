@@ -5,7 +5,8 @@ Reference interface (paths under /root/reference/src/VGAudio/):
   CriHcaEncoder.InitializeNew(config) -> .Hca (HcaInfo)  Codecs/CriHca/CriHcaEncoder.cs:49-114
   CriHcaFormat.EncodeFromPcm16(pcm16, config)          Formats/CriHca/CriHcaFormat.cs:34-84  (-> byte[FrameCount][FrameSize])
   CriHcaDecoder.Decode(hca, audio, config) -> short[][] Codecs/CriHca/CriHcaDecoder.cs:11-25
-Round 1: non-looping streams.
+Looping streams (Pcm16Format.Looping / LoopStart / LoopEnd -> CriHcaParameters) are encoded like the reference's
+streaming front end does (pre-roll, loop-start audio appended after the loop end, loop frame aligned to 2048 bytes).
 """
 from __future__ import annotations
 

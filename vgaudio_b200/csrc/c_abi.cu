@@ -1012,13 +1012,26 @@ inline int hca_next_multiple(int v, int m) { if (m <= 0) return v; if (v % m == 
 // CriHcaEncoder.Initialize (CriHcaEncoder.cs:61-114, non-looping) = CalculateBitrate :288-324,
 // CalculateBandCounts :326-368, HcaInfo.CalculateHfrValues (HcaInfo.cs:50-56), SetChannelConfiguration :370-381,
 // CalculateHeaderSize :400-418.  Integer/`Math.Round` logic only (half-to-even = nearbyint).
-int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h)
+// The encoder's input as ONE virtual sample stream (CriHcaEncoder.Encode :126-272 + the chunk loop of
+// CriHcaFormat.EncodeFromPcm16 :53-81): frame k encodes virtual samples [1024 k, 1024 k + 1024).
+struct HcaVirtual {
+    int32_t pre_zero = 0;    // whole silent frames EncodePreAudio emits while BufferPreSamples > 1024 (:177-182)
+    int32_t pre_fill = 0;    // then copies of the stream's first sample (:184-190)
+    int32_t main_count = 0;  // Hca.SampleCount source samples
+    int32_t post_count = 0;  // PostSamples taken from the loop start (SaveLoopAudio / EncodePostAudio); 0 when not looping
+    int32_t loop_start = 0;  // source position of post sample 0
+    int32_t src_count = 0;   // PCM length
+    int32_t last_chunk = 0;  // index of the last 1024-sample chunk the format layer hands to Encode
+};
+
+int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h, HcaVirtual *virt = nullptr)
 {
     if (p.channel_count > 8)
         return fail(VGB_E_ARG, "HCA channel count must be 8 or below");
     if (p.channel_count < 1) return fail(VGB_E_ARG, "HCA channel count must be at least 1");
     if (p.sample_rate <= 0 || p.sample_count < 0) return fail(VGB_E_ARG, "bad sample rate / sample count");
-    if (p.looping) return fail(VGB_E_ARG, "looping HCA streams are not implemented yet (round 1 covers non-looping encode)");
+    if (p.looping && (p.loop_start < 0 || p.loop_end <= p.loop_start || p.loop_start >= p.sample_count))
+        return fail(VGB_E_ARG, "loop points must satisfy 0 <= loop_start < loop_end and loop_start < sample_count");
     std::memset(&h, 0, sizeof h);
     const int cutoff0 = p.sample_rate / 2;
     h.channel_count = p.channel_count;
@@ -1079,10 +1092,46 @@ int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h)
         if (kHcaValidChannelMappings[per_track - 1][config] != 1) return fail(VGB_E_ARG, "Channel mapping is not valid.");
         h.channel_config = config;
     }
-    h.header_size = hca_next_multiple(96, 32);
-    const int total_samples = h.sample_count + h.inserted_samples;
+    int input_samples = h.sample_count, post_samples = 128;
+    if (p.looping) {  // :89-99
+        h.looping = 1;
+        h.sample_count = std::min(p.loop_end, p.sample_count);
+        h.inserted_samples += hca_next_multiple(p.loop_start, 1024) - p.loop_start;
+        {  // CalculateLoopInfo (:383-398)
+            const int ls = p.loop_start + h.inserted_samples, le = p.loop_end + h.inserted_samples;
+            h.loop_start_frame = ls / 1024;
+            h.pre_loop_samples = ls % 1024;
+            h.loop_end_frame = le / 1024;
+            h.post_loop_samples = 1024 - le % 1024;
+            if (h.post_loop_samples == 1024) { h.loop_end_frame--; h.post_loop_samples = 0; }
+        }
+        input_samples = std::min(hca_next_multiple(h.sample_count, 128), p.sample_count) + 256;
+        post_samples = input_samples - h.sample_count;
+    }
+    h.header_size = hca_next_multiple(96, 32);  // CalculateHeaderSize (:400-418), no comment
+    if (h.looping) {  // whole padding frames so that the loop start frame lands on a 2048-byte boundary of the file
+        const int loop_frame_offset = h.header_size + h.frame_size * h.loop_start_frame;
+        const int padding_bytes = hca_next_multiple(loop_frame_offset, 2048) - loop_frame_offset;
+        const int padding_frames = padding_bytes / h.frame_size;
+        h.inserted_samples += padding_frames * 1024;
+        h.loop_start_frame += padding_frames;
+        h.loop_end_frame += padding_frames;
+        h.header_size += padding_bytes % h.frame_size;
+    }
+    const int total_samples = input_samples + h.inserted_samples;
     h.frame_count = hca_div_up(total_samples, 1024);
-    h.appended_samples = h.frame_count * 1024 - h.inserted_samples - h.sample_count;
+    h.appended_samples = h.frame_count * 1024 - h.inserted_samples - input_samples;
+    if (virt) {
+        const int pre = h.inserted_samples - 128;  // BufferPreSamples (:113)
+        const int zero_frames = pre > 1024 ? hca_div_up(pre, 1024) - 1 : 0;
+        virt->pre_zero = zero_frames * 1024;
+        virt->pre_fill = pre - virt->pre_zero;
+        virt->main_count = h.sample_count;
+        virt->post_count = h.looping ? post_samples : 0;  // a non-looping encoder's PostAudio is all zero
+        virt->loop_start = p.loop_start;
+        virt->src_count = p.sample_count;
+        virt->last_chunk = h.sample_count > 0 ? (h.sample_count - 1) / 1024 : 0;
+    }
     return VGB_OK;
 }
 
@@ -1229,8 +1278,9 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     if (n_streams == 0) return VGB_OK;
     if (!pcm || !params || !frames_out) return fail(VGB_E_ARG, "NULL argument");
     std::vector<vgb_hca_info> infos(n_streams);
+    std::vector<HcaVirtual> virt(n_streams);
     for (int s = 0; s < n_streams; s++) {
-        VGB_TRY(hca_initialize(params[s], infos[s]));
+        VGB_TRY(hca_initialize(params[s], infos[s], &virt[s]));
         const vgb_hca_params &a = params[0], &b = params[s];
         if (a.channel_count != b.channel_count || a.sample_rate != b.sample_rate || a.quality != b.quality ||
             a.bitrate != b.bitrate || a.limit_bitrate != b.limit_bitrate)
@@ -1254,16 +1304,23 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     int64_t ps = 0, fb = 0, frames_total = 0;
     int max_frames = 0;
     for (int s = 0; s < n_streams; s++) {
-        const int64_t stride = (int64_t)align_up((size_t)infos[s].sample_count, 8);
+        const int32_t n_src = params[s].sample_count;  // the PCM the caller holds (>= Hca.SampleCount when looping)
+        const int64_t stride = (int64_t)align_up((size_t)n_src, 8);
         streams[s].pcm_off = ps;
         streams[s].channel_stride = stride;
         streams[s].frames_off = fb;
         streams[s].sample_count = infos[s].sample_count;
         streams[s].frame_count = infos[s].frame_count;
+        streams[s].pre_zero = virt[s].pre_zero;
+        streams[s].pre_fill = virt[s].pre_fill;
+        streams[s].post_count = virt[s].post_count;
+        streams[s].loop_start = virt[s].loop_start;
+        streams[s].src_count = virt[s].src_count;
+        streams[s].last_chunk = virt[s].last_chunk;
         for (int c = 0; c < nch; c++) {
-            if (!pcm[(size_t)s * nch + c] && infos[s].sample_count > 0) return fail(VGB_E_ARG, "pcm[%d][%d] is NULL", s, c);
+            if (!pcm[(size_t)s * nch + c] && n_src > 0) return fail(VGB_E_ARG, "pcm[%d][%d] is NULL", s, c);
             in_off[(size_t)s * nch + c] = (ps + c * stride) * 2;
-            in_len[(size_t)s * nch + c] = (int64_t)infos[s].sample_count * 2;
+            in_len[(size_t)s * nch + c] = (int64_t)n_src * 2;
         }
         ps += stride * nch;
         out_off[s] = fb;

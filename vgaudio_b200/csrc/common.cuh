@@ -89,6 +89,9 @@ struct HcaStream {
     int64_t dct_off;         // decoder: index of the stream's first frame in the seam scratch (frames)
     int32_t sample_count, frame_count;
     int32_t inserted_samples, reserved;  // decoder: HcaInfo.InsertedSamples (CopyPcmToOutput, CriHcaDecoder.cs:26-37)
+    // encoder: the input as one virtual stream (CriHcaEncoder.Encode :126-272): pre_zero zeros, pre_fill copies of the
+    // first sample, sample_count source samples, post_count samples from loop_start on, zeros
+    int32_t pre_zero, pre_fill, post_count, loop_start, src_count, last_chunk;
 };
 
 // Read-only codec tables, resident in HBM (uploaded once per device).  Values: the reference's test literals

@@ -2,10 +2,11 @@
 //
 // Replaces CriHcaEncoder.EncodeFrame and its 12 stages (Codecs/CriHca/CriHcaEncoder.cs:271-286, :420-858),
 // CriHcaPacking.PackFrame (CriHcaPacking.cs:17-58, BitWriter.cs:26-98, Crc16.cs) and Mdct.RunMdct/Dct4
-// (Utilities/Mdct.cs:63-181) for NON-LOOPING streams (frame k of a stream is the k-th 1024-sample window of its PCM
-// followed by zeros, CriHcaFormat.cs:53-81 + CriHcaEncoder.cs:192-242).
+// (Utilities/Mdct.cs:63-181).  The reference's streaming front end (CriHcaEncoder.Encode :126-272 driven by
+// CriHcaFormat.cs:53-81) is folded into one VIRTUAL input stream per channel - pre-roll, source samples, for a looping
+// stream the loop-start audio repeated behind the loop end, zeros - and frame k encodes its k-th 1024-sample window.
 //
-// Frames are independent given the raw PCM (the MDCT overlap is the previous 128 raw samples), so ONE CTA OF 128
+// Frames are independent given that stream (the MDCT overlap is its previous 128 samples), so ONE CTA OF 128
 // THREADS OWNS ONE (stream, frame): massive parallelism across frames, stages inside the CTA separated by barriers.
 //   mdct        2 x 64 threads run two 128-point DCT-IV at a time (6 radix-2 stages in shared memory), fp64, same
 //               operation order as the reference (a*cos + b*sin as mul, mul, add - no FMA)
@@ -80,6 +81,30 @@ struct BlockSum {  // integer sum over the 128 threads of the CTA, result in eve
 
 }  // namespace
 
+// Sample `v` of the encoder's virtual input stream (see HcaStream): what CriHcaEncoder.Encode's buffer management
+// (EncodePreAudio :175-194, EncodeMainAudio :196-211, SaveLoopAudio :247-257, EncodePostAudio :213-245) feeds to
+// EncodeFrame at position v, given the 1024-sample chunks CriHcaFormat.EncodeFromPcm16 (:53-81) hands it.
+__device__ __forceinline__ int16_t hca_virtual_sample(const int16_t *src, const HcaStream &st, int64_t v)
+{
+    if (v < st.pre_zero) return 0;  // before the stream, and the whole silent frames in front of a padded loop
+    v -= st.pre_zero;
+    if (v < st.pre_fill) return st.src_count > 0 ? src[0] : (int16_t)0;  // pcm[i][0] of the first chunk
+    v -= st.pre_fill;
+    if (v < st.sample_count) return src[v];
+    v -= st.sample_count;
+    if (v < st.post_count) {
+        // PostAudio[v] = what the format layer's reused 1024-sample chunk buffer held at source position a when the
+        // chunk went by: the sample itself; past the end of the PCM the previous chunk's sample at the same offset
+        // (the buffer is not cleared, CriHcaFormat.cs:57-61); zero if that chunk was never handed over.
+        const int64_t a = (int64_t)st.loop_start + v;
+        const int64_t chunk = a >> 10;
+        if (chunk > st.last_chunk) return 0;
+        if (a < st.src_count) return src[a];
+        return chunk >= 1 ? src[a - 1024] : (int16_t)0;
+    }
+    return 0;
+}
+
 // Dynamic shared memory layout per CTA (nch = channel count):
 //   double spectra[nch][8][128]; double scaled[nch][128][8]; then the small per-channel state below.
 struct HcaChannelState {
@@ -127,10 +152,7 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
         for (int sf2 = 0; sf2 < kSub; sf2 += 2) {
             const int sf = sf2 + grp;
             const int64_t base = (int64_t)k * kFrame + sf * kBins;  // first sample of this subframe
-            auto sample = [&](int64_t idx) -> double {
-                const int16_t v = (idx >= 0 && idx < st.sample_count) ? src[idx] : (int16_t)0;
-                return (double)v * (1.0 / 32768.0);
-            };
+            auto sample = [&](int64_t idx) -> double { return (double)hca_virtual_sample(src, st, idx) * (1.0 / 32768.0); };
             {   // window + fold into the DCT input (Mdct.cs:77-85); `previous` = the 128 samples before this subframe
                 const double a = T.window[64 - i - 1] * -sample(base + 64 + i);
                 const double b = T.window[64 + i] * sample(base + 64 - i - 1);
