@@ -12,12 +12,12 @@
 //                           (it equals ContrastVectors' `val` terms bit for bit - see DESIGN.md §gc_coef_refine).
 //                           HBM-bound by design: 2 B/sample in, 16 B + 1 bit per frame out.
 //
-//   gc_coef_refine_kernel   phase 2 (:63-108): one WARP per channel.  Nearest-centroid search is parallel over
-//                           32 records; the fp64 accumulations are applied strictly in record order
-//                            by 16 accumulator lanes (8 buckets x 2 components), because any
-//                           tree reduction would change the roundings and can flip a 16-bit coefficient.  Records
-//                           are compacted per bucket (ballot + popc) so each lane's DADD chain only contains its
-//                           own bucket's records.
+//   gc_coef_refine_kernel   phase 2 (:63-108): one CTA per channel, producer warps + one consumer warp.  The
+//                           nearest-centroid search is parallel over 32 records; the fp64 accumulations are applied
+//                           strictly in record order by 16 accumulator lanes (8 buckets x 2
+//                           components), because any tree reduction would change the roundings and can flip a 16-bit
+//                           coefficient.  Records are compacted per bucket (ballot + popc) so each lane's DADD chain
+//                           only contains its own bucket's records.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -230,40 +230,94 @@ __device__ __forceinline__ int16_t gc_quantise_coef(double v)
     return (int16_t)__double2int_rn(d);
 }
 
-constexpr int kRefineWarps = 4;
+// ---- phase 2 as a producer/consumer CTA: one CTA of kRefineWarps warps per channel -----------------------------
+// The ordered fp64 sums are a serial chain (8.3 cycles per add), everything else - loading the records, the nearest
+// centroid search, sorting a block of 32 records into per-bucket queues - is parallel work.  At 1024 channels one
+// warp per channel leaves most of the machine idle and each channel pays for both in sequence, so the work is split
+// and software-pipelined over CHUNKS of kRefineProducers blocks with one CTA barrier per chunk (no polling):
+//   warps 1..P (producers) classify one block of 32 records each and append every record to ITS bucket's queue in
+//              the chunk's shared-memory buffer (rank = number of earlier records of the block in the same bucket,
+//              from a ballot: record order is preserved inside a bucket);
+//   warp 0     (consumer) meanwhile walks the PREVIOUS chunk's blocks in order and lane (bucket, component) adds ONLY
+//              its bucket's records, in record order - exactly the reference's sequence of additions.
+constexpr int kRefineWarps = 4;                    // 1 consumer + 3 producers
+constexpr int kRefineProducers = kRefineWarps - 1;
 
-// Per-bucket queues of one block of 32 records: record lanes append their direct-form pair to the queue of the
-// bucket they were assigned to (rank = number of earlier records of the block in the same bucket, from a ballot),
-// so an accumulator lane walks ONLY its bucket's records, still in record order.
-struct __align__(16) RefineQueues {
-    double2 q[8][32];
+struct __align__(16) RefineSlot {
+    double2 q[8][33];     // per-bucket queues of one block of 32 records; 33: the 16 accumulator lanes (bucket, comp)
+                          // read entry j of all buckets at once, 528-byte rows put them in 16 distinct bank pairs
+    int32_t count[8];     // records per bucket (buckets the pass does not use stay 0)
+    int32_t n_max, pad[3];  // largest count
 };
 
+struct RefineShared {
+    RefineSlot slot[2][kRefineProducers];  // double-buffered chunks
+    double cent[8][3];                      // centroids (1, c1, c2)
+    double econst[8][3];                    // per-centroid constants of ContrastVectors (:338-340), refreshed every pass
+};
+
+// all kRefineWarps warps, once per chunk; PTX named barrier so that the two code paths may use different instructions
+__device__ __forceinline__ void refine_chunk_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kRefineWarps * 32) : "memory"); }
+
+// consumer side of one pass: ordered accumulation (:382-386 / :67-72).  Lane (bucket*2 + comp) walks its bucket's queue
+// of every block in block order - a pure DADD chain over exactly the bucket's records, in record order.
+struct RefineSum { double acc; int hits; };
+__device__ __forceinline__ RefineSum gc_refine_consume(int lane, int n_blocks, int n_chunks, RefineShared &sh)
+{
+    constexpr int P = kRefineProducers;
+    const int my_bucket = (lane >> 1) & 7, my_comp = lane & 1;
+    double a = 0.0;
+    int h = 0;
+    refine_chunk_barrier();  // chunk 0 classified
+    for (int c = 1; c <= n_chunks; c++) {
+        const int first = (c - 1) * P;
+        for (int j = 0; j < P && first + j < n_blocks; j++) {
+            const RefineSlot &slot = sh.slot[(c - 1) & 1][j];
+            const int n_mine = lane < 16 ? slot.count[my_bucket] : 0;
+            const double *col = reinterpret_cast<const double *>(slot.q[my_bucket]) + my_comp;
+            // four queue entries per step (the producers pad every queue to a multiple of four with -0.0, the additive
+            // identity): loads issued together, then the bare DADD chain.  The trip count differs per lane; lanes whose
+            // bucket is done simply drop out (no selects on the chain, 11 instructions per four records).
+            const int n_pad = (n_mine + 3) & ~3;
+            for (int j0 = 0; j0 < n_pad; j0 += 4) {
+                double v[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = col[2 * (j0 + i)];
+#pragma unroll
+                for (int i = 0; i < 4; i++) a += v[i];
+            }
+            h += n_mine;
+        }
+        refine_chunk_barrier();
+    }
+    return RefineSum{a, h};
+}
+
 // One pass over all records of a channel with COUNT centroids (COUNT == 0: the plain ordered mean of :63-76, every
-// record goes to bucket 0).  On return lane (bucket*2 + comp), bucket < max(COUNT,1), holds the ordered sum of that
-// component over the bucket's records in `acc` and the record count in `hits`.
+// record goes to bucket 0), executed by the whole CTA.  On return, in warp 0, lane (bucket*2 + comp) with
+// bucket < max(COUNT,1) holds the ordered sum of that component over the bucket's records in `acc` and the record
+// count in `hits`.
 template <int COUNT>
-__device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blocks, const double2 *__restrict__ rec,
-                                               const uint32_t *__restrict__ mask, RefineQueues *queues,
-                                               const double (*best)[3], double &acc, int &hits)
+__device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames, int n_blocks, const double2 *__restrict__ rec,
+                                               const uint32_t *__restrict__ mask, RefineShared &sh, double &acc, int &hits)
 {
     constexpr int NB = COUNT > 0 ? COUNT : 1;
-    const int my_bucket = lane >> 1, my_comp = lane & 1;
+    constexpr int P = kRefineProducers;
     const uint32_t lanes_below = (1u << lane) - 1u;
+    const int p = warp - 1;                              // producer index (warp 0: unused)
+    const int n_chunks = (n_blocks + P - 1) / P;
 
-    // per-centroid constants of ContrastVectors (:338-340)
-    double e0[NB], e1[NB], e2[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const double a0 = best[i][0], a1 = best[i][1], a2 = best[i][2];
-        e0[i] = (a0 * a0) + (a1 * a1) + (a2 * a2);
-        e1[i] = (a0 * a1) + (a1 * a2);
-        e2[i] = a0 * a2;
-    }
-
-    // classify block b (nearest centroid, parallel over its 32 records) and append to the bucket queues of slot b&1;
-    // bits[k] = which lanes went to bucket k
-    auto stage = [&](int b, double2 r, uint32_t okbits, uint32_t (&bits)[NB]) {
+    auto fetch = [&](int b, double2 &r, uint32_t &okbits) {
+        r = make_double2(0.0, 0.0);
+        okbits = 0;
+        if (warp > 0 && b < n_blocks) {
+            okbits = mask[b];
+            const int f = b * 32 + lane;
+            if (f < n_frames) r = rec[f];
+        }
+    };
+    // producer: classify block b (nearest centroid, parallel over its 32 records) into `slot`
+    auto stage = [&](int b, double2 r, uint32_t okbits, RefineSlot &slot) {
         const bool ok = ((okbits >> lane) & 1u) && (b * 32 + lane < n_frames);
         int pick = 0;
         if (COUNT > 1) {
@@ -276,7 +330,7 @@ __device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blo
             int idx[NB];
 #pragma unroll
             for (int i = 0; i < NB; i++) {
-                const double di = e0[i] + (ta * e1[i]) + (tb * e2[i]);
+                const double di = sh.econst[i][0] + (ta * sh.econst[i][1]) + (tb * sh.econst[i][2]);  // smem broadcast
                 d[i] = di < 1.0e30 ? di : __longlong_as_double(0x7FF0000000000000ll);  // never wins (also NaN), as in the scan
                 idx[i] = i;
             }
@@ -292,93 +346,75 @@ __device__ __forceinline__ void gc_refine_pass(int lane, int n_frames, int n_blo
             pick = d[0] < 1.0e30 ? idx[0] : 0;  // nothing below the initial 1.0e30: the index stays 0
         }
         uint32_t mine = 0;
+        int largest = 0;  // (kept for reference: the consumer no longer needs the longest queue)
 #pragma unroll
         for (int k = 0; k < NB; k++) {
-            bits[k] = __ballot_sync(0xFFFFFFFFu, ok && pick == k);
-            mine = pick == k ? bits[k] : mine;
+            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok && pick == k);
+            mine = pick == k ? bits : mine;
+            largest = max(largest, __popc(bits));
+            if (lane == k) slot.count[k] = __popc(bits);
         }
-        if (ok) queues[b & 1].q[pick][__popc(mine & lanes_below)] = r;
-    };
-    auto fetch = [&](int b, double2 &r, uint32_t &okbits) {
-        r = make_double2(0.0, 0.0);
-        okbits = 0;
-        if (b < n_blocks) {
-            okbits = mask[b];
-            const int f = b * 32 + lane;
-            if (f < n_frames) r = rec[f];
+        (void)largest;
+        if (ok) slot.q[pick][__popc(mine & lanes_below)] = r;
+        __syncwarp();
+        {   // pad every queue to a multiple of four entries with -0.0 (lane = bucket * 4 + i)
+            const int bucket = lane >> 2, i = lane & 3;
+            if (bucket < NB) {
+                const int c = slot.count[bucket];
+                if (i < ((4 - (c & 3)) & 3)) slot.q[bucket][c + i] = make_double2(-0.0, -0.0);
+            }
         }
     };
-
     acc = 0.0;
     hits = 0;
-    // Records stream from HBM once per pass (1.6 MB per channel, no reuse): loads are issued kDepth blocks ahead of
-    // their use to cover DRAM latency; ring indices are compile-time.
+    // Records stream from HBM once per pass (1.6 MB per channel, no reuse): a producer's loads are issued kDepth of
+    // its blocks ahead of their use to cover DRAM latency; ring indices are compile-time.
     constexpr int kDepth = 4;
     double2 ring_r[kDepth];
     uint32_t ring_ok[kDepth];
 #pragma unroll
-    for (int k = 0; k < kDepth; k++) fetch(k, ring_r[k], ring_ok[k]);
-    uint32_t cur_bits[NB], next_bits[NB];
-#pragma unroll
-    for (int k = 0; k < NB; k++) cur_bits[k] = next_bits[k] = 0;
-    if (n_blocks > 0) stage(0, ring_r[0], ring_ok[0], cur_bits);
-    fetch(kDepth, ring_r[0], ring_ok[0]);
-    __syncwarp();
+    for (int k = 0; k < kDepth; k++) fetch(p + k * P, ring_r[k], ring_ok[k]);
 
-    for (int b0 = 0; b0 < n_blocks; b0 += kDepth) {
+    if (warp == 0) {
+        // consumer: deliberately small, rolled code (it is the critical path and must stay in the instruction cache
+        // next to the producers' large unrolled loop); inlined so that `sh` stays a shared-window address
+        const RefineSum sum = gc_refine_consume(lane, n_blocks, n_chunks, sh);
+        acc = sum.acc;
+        hits = sum.hits;
+        return;
+    }
+    for (int c0 = 0; c0 <= n_chunks; c0 += kDepth) {  // one extra step drains the pipeline
 #pragma unroll
         for (int k = 0; k < kDepth; k++) {
-            const int b = b0 + k;
-            if (b >= n_blocks) break;
-            // (1) classify and queue the NEXT block (independent of the chain below), refill its ring slot
-            const int slot_next = (k + 1) % kDepth;
-            if (b + 1 < n_blocks) stage(b + 1, ring_r[slot_next], ring_ok[slot_next], next_bits);
-            fetch(b + 1 + kDepth, ring_r[slot_next], ring_ok[slot_next]);
-
-            // (2) ordered accumulation of block b (:382-386 / :67-72): lane (bucket, comp) adds its bucket's records
-            // in record order - a pure DADD chain over exactly those records
-            uint32_t mine = 0;
-#pragma unroll
-            for (int kk = 0; kk < NB; kk++) mine = my_bucket == kk ? cur_bits[kk] : mine;
-            const int n_mine = __popc(mine);
-            const double *col = reinterpret_cast<const double *>(queues[b & 1].q[my_bucket & 7]) + my_comp;
-            // eight queue entries per step: the loads are issued together (entries past the end read as -0.0, the
-            // additive identity), then a pure DADD chain
-            const int n_max = __reduce_max_sync(0xFFFFFFFFu, n_mine);
-            for (int j0 = 0; j0 < n_max; j0 += 8) {
-                double v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = (j0 + j < n_mine) ? col[2 * (j0 + j)] : -0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) acc += v[j];
-            }
-            hits += n_mine;
-#pragma unroll
-            for (int kk = 0; kk < NB; kk++) cur_bits[kk] = next_bits[kk];
-            __syncwarp();
+            const int c = c0 + k;
+            if (c > n_chunks) break;
+            const int b = c * P + p;
+            if (b < n_blocks) stage(b, ring_r[k], ring_ok[k], sh.slot[c & 1][p]);
+            fetch(b + kDepth * P, ring_r[k], ring_ok[k]);
+            refine_chunk_barrier();  // chunk c is classified, chunk c-1 is summed: the two buffers swap roles
         }
     }
 }
 
-__global__ void __launch_bounds__(kRefineWarps * 32)
+__global__ void __launch_bounds__(kRefineWarps * 32, 7)  // 7 CTAs per SM: 1024 channels are resident at once
 gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, const uint32_t *__restrict__ accept_mask,
                       int16_t *__restrict__ coefs_out)
 {
-    __shared__ RefineQueues queues[kRefineWarps][2];
-    __shared__ double cent[kRefineWarps][8][3];  // centroids (1, c1, c2)
+    __shared__ RefineShared sh;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * kRefineWarps + warp;
-    if (ch >= tab.n_channels) return;  // whole warp leaves together
+    const int ch = blockIdx.x;
+    if (ch >= tab.n_channels) return;
 
-    double (*best)[3] = cent[warp];
+    double (*best)[3] = sh.cent;
     const int n_frames = div_round_up(tab.n_samples[ch], kGcFrameSamples);
     const int n_blocks = (n_frames + 31) >> 5;
     const double2 *rec = records + tab.rec_off[ch];
     const uint32_t *mask = accept_mask + (tab.rec_off[ch] >> 5);
 
-    if (lane < 8) { best[lane][0] = 1.0; best[lane][1] = 0.0; best[lane][2] = 0.0; }
-    __syncwarp();
+    if (threadIdx.x < 8) { best[threadIdx.x][0] = 1.0; best[threadIdx.x][1] = 0.0; best[threadIdx.x][2] = 0.0; }
+    if (threadIdx.x < 2 * kRefineProducers * 8) sh.slot[threadIdx.x / (kRefineProducers * 8)][(threadIdx.x / 8) % kRefineProducers].count[threadIdx.x & 7] = 0;
+    __syncthreads();
 
     // pass 0 is the plain ordered mean (:63-76); passes 1..6 are the FilterRecords rounds (:79-91): split, then two
     // rounds of reassign + average with 2, 4, 8 centroids.
@@ -386,41 +422,49 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
     for (int pass = 0; pass < 7; pass++) {
         if (pass == 1 || pass == 3 || pass == 5) {
             // split (:82-89): new centroid = (0.01 * (0,-1,0)) + old
-            if (lane < count) {
+            if (warp == 0 && lane < count) {
                 best[count + lane][0] = (0.01 * 0.0) + best[lane][0];
                 best[count + lane][1] = (0.01 * -1.0) + best[lane][1];
                 best[count + lane][2] = (0.01 * 0.0) + best[lane][2];
             }
             count *= 2;
-            __syncwarp();
+            __syncthreads();
         }
+        if (warp == 0 && lane < count) {
+            const double a0 = best[lane][0], a1 = best[lane][1], a2 = best[lane][2];
+            sh.econst[lane][0] = (a0 * a0) + (a1 * a1) + (a2 * a2);
+            sh.econst[lane][1] = (a0 * a1) + (a1 * a2);
+            sh.econst[lane][2] = a0 * a2;
+        }
+        __syncthreads();
         double acc;
         int hits;
-        if (pass == 0) gc_refine_pass<0>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
-        else if (count == 2) gc_refine_pass<2>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
-        else if (count == 4) gc_refine_pass<4>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
-        else gc_refine_pass<8>(lane, n_frames, n_blocks, rec, mask, queues[warp], best, acc, hits);
+        if (pass == 0) gc_refine_pass<0>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else if (count == 2) gc_refine_pass<2>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else if (count == 4) gc_refine_pass<4>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else gc_refine_pass<8>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
 
-        // divide (:73-74 / :388-391) and rebuild the centroids (:76 / :393-394)
-        double mean;
-        if (pass == 0) mean = acc / (double)hits;  // 0/0 = NaN for a silent channel, as in the reference (A.19)
-        else mean = hits > 0 ? acc / (double)hits : acc;
-        const double m1 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2);
-        const double m2 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2 + 1);
-        const int h = __shfl_sync(0xFFFFFFFFu, hits, (lane & 7) * 2);
-        __syncwarp();
-        if (lane < count) {
-            const double m0 = (pass == 0) ? 1.0 : (h > 0 ? 1.0 : 0.0);  // sum of h ones divided by h
-            double o1, o2;
-            gc_centroid_from_mean(m0, m1, m2, o1, o2);
-            best[lane][0] = 1.0;
-            best[lane][1] = o1;
-            best[lane][2] = o2;
+        if (warp == 0) {
+            // divide (:73-74 / :388-391) and rebuild the centroids (:76 / :393-394)
+            double mean;
+            if (pass == 0) mean = acc / (double)hits;  // 0/0 = NaN for a silent channel, as in the reference (A.19)
+            else mean = hits > 0 ? acc / (double)hits : acc;
+            const double m1 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2);
+            const double m2 = __shfl_sync(0xFFFFFFFFu, mean, (lane & 7) * 2 + 1);
+            const int h = __shfl_sync(0xFFFFFFFFu, hits, (lane & 7) * 2);
+            if (lane < count) {
+                const double m0 = (pass == 0) ? 1.0 : (h > 0 ? 1.0 : 0.0);  // sum of h ones divided by h
+                double o1, o2;
+                gc_centroid_from_mean(m0, m1, m2, o1, o2);
+                best[lane][0] = 1.0;
+                best[lane][1] = o1;
+                best[lane][2] = o2;
+            }
         }
-        __syncwarp();
+        __syncthreads();  // the next pass classifies against the new centroids
     }
 
-    if (lane < 16) coefs_out[(int64_t)ch * 16 + lane] = gc_quantise_coef(best[lane >> 1][1 + (lane & 1)]);
+    if (threadIdx.x < 16) coefs_out[(int64_t)ch * 16 + threadIdx.x] = gc_quantise_coef(best[threadIdx.x >> 1][1 + (threadIdx.x & 1)]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -442,8 +486,7 @@ void launch_gc_coef_refine(const GcChannelTable &tab, const double2 *records, co
                            int16_t *coefs_out, cudaStream_t stream)
 {
     if (tab.n_channels <= 0) return;
-    int blocks = (tab.n_channels + kRefineWarps - 1) / kRefineWarps;
-    gc_coef_refine_kernel<<<blocks, kRefineWarps * 32, 0, stream>>>(tab, records, mask, coefs_out);
+    gc_coef_refine_kernel<<<tab.n_channels, kRefineWarps * 32, 0, stream>>>(tab, records, mask, coefs_out);
 }
 
 }  // namespace vgb
