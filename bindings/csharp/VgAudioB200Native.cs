@@ -47,6 +47,18 @@ namespace VGAudio.Native
         public static extern int vgb_gcadpcm_encode_frames(short* pcmInOut, int* sampleCount, short* coefs, int nFrames, byte* adpcmOut);
 
         /// <summary>Maps a VGB_E_* status back to the exception type the managed code path throws.</summary>
+        [StructLayout(LayoutKind.Sequential)]
+        internal struct VgbGcTapParams { public int SampleCount, SamplesPerSeekTableEntry, LoopStart; }
+
+        // GcAdpcmSeekTable.CreateSeekTable + GcAdpcmLoopContext(adpcm, pcm, loopStart) without the CPU decode
+        // (GcAdpcmChannelBuilder.cs:176-202)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int vgb_gcadpcm_seek_entry_count(int sampleCount, int samplesPerEntry);
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern unsafe int vgb_gcadpcm_seek_context_batch(byte** adpcm, int* nBytes, short* coefs, VgbGcTapParams* parameters,
+            int nChannels, short** seekTableOut, short* loopContextOut);
+
         public static void Check(int status)
         {
             if (status == Ok) return;

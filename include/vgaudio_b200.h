@@ -132,6 +132,30 @@ int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offs
                                int16_t *d_pcm, const int64_t *pcm_offset,
                                void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Post-encode channel rebuild: what GcAdpcmChannelBuilder.GetSeekTable / GetLoopContext
+ * (Formats/GcAdpcm/GcAdpcmChannelBuilder.cs:176-202) compute by decoding the whole channel again on the CPU.
+ *   seek table    GcAdpcmSeekTable.CreateSeekTable (GcAdpcmSeekTable.cs:25-38): entry i = (pcm[i*spe - 1], pcm[i*spe - 2]),
+ *                 entry 0 = (0, 0), entries = ceil(sample_count / spe)
+ *   loop context  GcAdpcmLoopContext (GcAdpcmLoopContext.cs:17-26): predictor/scale byte of the frame holding the loop
+ *                 start (GcAdpcmDecoder.GetPredictorScale :56-59), hist1 = pcm[loop_start - 1], hist2 = pcm[loop_start - 2]
+ * Not covered: GcAdpcmAlignment's re-encode of an unaligned loop (GcAdpcmAlignment.cs:20-63).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct vgb_gc_tap_params {
+    int32_t sample_count;
+    int32_t samples_per_seek_table_entry; /* 0: no seek table (GetSeekTable returns null) */
+    int32_t loop_start;                   /* < 0: no loop context */
+} vgb_gc_tap_params;
+
+int32_t vgb_gcadpcm_seek_entry_count(int32_t sample_count, int32_t samples_per_entry);
+
+/* adpcm / n_bytes / coefs as in vgb_gcadpcm_decode_batch.  seek_table_out[c] receives entry_count * 2 shorts (may be
+ * NULL when the channel asks for no table); loop_context_out is [n_channels][3] = pred_scale, hist1, hist2 (zeros for
+ * a channel without a loop; may be NULL when no channel has one). */
+int32_t vgb_gcadpcm_seek_context_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                       const vgb_gc_tap_params *params, int32_t n_channels,
+                                       int16_t *const *seek_table_out, int16_t *loop_context_out);
+
 /* Per-kernel device time (ms, CUDA events on the launching stream) of the most recent *_dev or host call on this
  * thread's workspace: [0] GC coefficient phase 1, [1] GC coefficient refinement, [2] GC encode, [3] GC decode,
  * [4] ADX encode, [5] ADX decode, [6] HCA encode, [7] HCA decode (both kernels).  Only filled when

@@ -526,6 +526,27 @@ void vgo_gc_decode(const uint8_t *adpcm, const int16_t coefs[16], int sample_cou
     }
 }
 
+/* GcAdpcmSeekTable.CreateSeekTable (Formats/GcAdpcm/GcAdpcmSeekTable.cs:25-38) on decoded PCM. out: entries*2 shorts. */
+int vgo_gc_seek_table(const int16_t *pcm, int length, int samples_per_entry, int16_t *out)
+{
+    if (samples_per_entry <= 0) return 0;
+    int entries = vgo_divide_by_round_up(length, samples_per_entry);
+    memset(out, 0, sizeof(int16_t) * 2 * (size_t)entries);
+    for (int i = 1; i < entries; i++) { /* the first entry should always be 0 */
+        out[i * 2] = pcm[i * samples_per_entry - 1];
+        out[i * 2 + 1] = pcm[i * samples_per_entry - 2];
+    }
+    return entries;
+}
+
+/* GcAdpcmLoopContext(adpcm, pcm, loopStart) (Formats/GcAdpcm/GcAdpcmLoopContext.cs:17-26): pred/scale, hist1, hist2. */
+void vgo_gc_loop_context(const uint8_t *adpcm, const int16_t *pcm, int loop_start, int16_t out[3])
+{
+    out[0] = adpcm[loop_start / FRAME_SAMPLES * FRAME_BYTES]; /* GcAdpcmDecoder.GetPredictorScale :56-59 */
+    out[1] = loop_start < 1 ? 0 : pcm[loop_start - 1];
+    out[2] = loop_start < 2 ? 0 : pcm[loop_start - 2];
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Batch drivers = the reference's Parallel.For over channels (Formats/GcAdpcm/GcAdpcmFormat.cs:65-68,
  * :45-48; EncodeChannel :129-135).  This is what bench.py times as the CPU baseline.

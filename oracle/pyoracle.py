@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L.vgo_gc_dsp_encode_frame.restype = None
         L.vgo_gc_decode.argtypes = [vp, vp, i32, C.c_int16, C.c_int16, vp]
         L.vgo_gc_decode.restype = None
+        L.vgo_gc_seek_table.argtypes = [vp, i32, i32, vp]
+        L.vgo_gc_seek_table.restype = i32
+        L.vgo_gc_loop_context.argtypes = [vp, vp, i32, vp]
+        L.vgo_gc_loop_context.restype = None
         L.vgo_gc_encode_batch.argtypes = [vp, i64, i32, i32, vp, vp, i64, i32]
         L.vgo_gc_decode_batch.argtypes = [vp, i64, vp, i32, i32, vp, i64, i32]
         L.vgo_adx_calculate_coefficients.argtypes = [i32, i32, vp]
@@ -200,6 +204,23 @@ def _chan_table(channels):
     arrs = [np.ascontiguousarray(c, dtype=np.int16) for c in channels]
     tab = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     return arrs, tab
+
+
+def gc_seek_table(pcm, samples_per_entry) -> np.ndarray:
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    entries = -(-len(pcm) // samples_per_entry) if samples_per_entry > 0 else 0
+    out = np.zeros(entries * 2, dtype=np.int16)
+    if entries:
+        lib().vgo_gc_seek_table(C.c_void_p(pcm.ctypes.data), len(pcm), samples_per_entry, C.c_void_p(out.ctypes.data))
+    return out
+
+
+def gc_loop_context(adpcm, pcm, loop_start):
+    adpcm = np.ascontiguousarray(adpcm, dtype=np.uint8)
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    out = np.zeros(3, dtype=np.int16)
+    lib().vgo_gc_loop_context(C.c_void_p(adpcm.ctypes.data), C.c_void_p(pcm.ctypes.data), int(loop_start), C.c_void_p(out.ctypes.data))
+    return int(out[0]) & 0xFF, int(out[1]), int(out[2])
 
 
 def hca_params(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None) -> HcaParams:

@@ -63,6 +63,8 @@ void vgo_gc_decode(const uint8_t *adpcm, const int16_t coefs[16], int sample_cou
 /* ---- batch drivers: the reference's Parallel.For over channels (Formats/GcAdpcm/GcAdpcmFormat.cs:58-74,
  * :42-54, :129-135) restated with a pthread pool (dynamic schedule); n_threads <= 0 means all host cores.  Channel c lives at
  * pcm + c*pcm_stride (samples) / adpcm + c*adpcm_stride (bytes).  Returns threads used. ---- */
+int vgo_gc_seek_table(const int16_t *pcm, int length, int samples_per_entry, int16_t *out); /* GcAdpcmSeekTable.cs:25-38 */
+void vgo_gc_loop_context(const uint8_t *adpcm, const int16_t *pcm, int loop_start, int16_t out[3]); /* GcAdpcmLoopContext.cs:17-26 */
 int vgo_gc_encode_batch(const int16_t *pcm, int64_t pcm_stride, int n_channels, int sample_count,
                         int16_t *coefs_out /* [n_channels][16] */, uint8_t *adpcm_out, int64_t adpcm_stride,
                         int n_threads);

@@ -212,3 +212,37 @@ def test_loud_signals_exercise_float32_rounding_regime(vg, oracle):
     _, adpcm2 = vg.gcadpcm.encode_batch(pcm, coefs=rand_coefs)
     for c in range(24):
         assert adpcm2[c].tobytes() == oracle.encode(pcm[c], rand_coefs[c]).tobytes(), c
+
+
+# ---- post-encode channel rebuild: seek table + loop context without keeping the decoded PCM --------
+
+@pytest.mark.parametrize("spe", [0x3800, 1000, 14, 56, 57, 3, 1])
+def test_seek_table_and_loop_context_match_the_oracle(vg, oracle, spe):
+    lens = [30000, 14 * 500, 14 * 500 + 5, 57, 56, 13, 1, 100001]
+    loops = [12345, 0, 1, 56, None, 12, 0, 99999]
+    pcm = [synth.channel(700 + i, n, degenerate=False) for i, n in enumerate(lens)]
+    coefs, adpcm = [], []
+    for x in pcm:
+        c = oracle.calculate_coefficients(x)
+        coefs.append(c)
+        adpcm.append(oracle.encode(x, c))
+    seek, ctx = vg.gcadpcm.seek_table_and_loop_context(adpcm, np.stack(coefs), lens, spe, loops)
+    for i, x in enumerate(pcm):
+        dec = oracle.decode(adpcm[i], coefs[i], lens[i])
+        assert np.array_equal(seek[i], oracle.gc_seek_table(dec, spe)), (i, spe)
+        if loops[i] is None:
+            assert ctx[i] is None
+        else:
+            assert ctx[i] == oracle.gc_loop_context(adpcm[i], dec, loops[i]), (i, loops[i])
+
+
+def test_seek_context_without_table_and_errors(vg, oracle):
+    x = synth.channel(9, 5000)
+    c = oracle.calculate_coefficients(x)
+    a = oracle.encode(x, c)
+    seek, ctx = vg.gcadpcm.seek_table_and_loop_context([a], c.reshape(1, 16), [5000], 0, [2500])
+    assert seek[0] is None
+    dec = oracle.decode(a, c, 5000)
+    assert ctx[0] == oracle.gc_loop_context(a, dec, 2500)
+    with pytest.raises(vg.VgbError):  # loop start past the end of the channel
+        vg.gcadpcm.seek_table_and_loop_context([a], c.reshape(1, 16), [5000], 0, [5001])

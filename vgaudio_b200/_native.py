@@ -36,6 +36,10 @@ class VgbHcaParams(C.Structure):
                                          "sample_count", "looping", "loop_start", "loop_end")]
 
 
+class VgbGcTapParams(C.Structure):
+    _fields_ = [("sample_count", C.c_int32), ("samples_per_seek_table_entry", C.c_int32), ("loop_start", C.c_int32)]
+
+
 class VgbHcaInfo(C.Structure):
     """The HcaInfo fields the codec uses (Codecs/CriHca/HcaInfo.cs:5-48)."""
 
@@ -96,6 +100,8 @@ SIGNATURES = {
     "vgb_hca_query": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "vgb_hca_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_hca_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_gcadpcm_seek_entry_count": (C.c_int32, [C.c_int32, C.c_int32]),
+    "vgb_gcadpcm_seek_context_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),

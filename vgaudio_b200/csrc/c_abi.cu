@@ -664,6 +664,93 @@ int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_b
     return VGB_OK;
 }
 
+int32_t vgb_gcadpcm_seek_entry_count(int32_t sample_count, int32_t samples_per_entry)
+{
+    if (samples_per_entry <= 0 || sample_count <= 0) return 0;
+    return div_round_up(sample_count, samples_per_entry);
+}
+
+int32_t vgb_gcadpcm_seek_context_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                       const vgb_gc_tap_params *params, int32_t n_channels,
+                                       int16_t *const *seek_table_out, int16_t *loop_context_out)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative (%d)", n_channels);
+    if (n_channels == 0) return VGB_OK;
+    if (!adpcm || !n_bytes || !coefs || !params) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<int32_t> counts(n_channels);
+    std::vector<GcTapChannel> taps(n_channels);
+    std::vector<int64_t> tap_off(n_channels), tap_len(n_channels);
+    int64_t slab = 0;
+    bool any_loop = false;
+    for (int c = 0; c < n_channels; c++) {
+        const vgb_gc_tap_params &p = params[c];
+        if (p.sample_count < 0 || n_bytes[c] < 0) return fail(VGB_E_ARG, "channel %d: negative count", c);
+        if (p.samples_per_seek_table_entry < 0) return fail(VGB_E_ARG, "channel %d: negative samples per seek table entry", c);
+        if (n_bytes[c] < gc_sample_count_to_byte_count(p.sample_count))
+            return fail(VGB_E_ARG, "channel %d: audio array length %d is too short for %d samples", c, n_bytes[c], p.sample_count);
+        if (!adpcm[c] && p.sample_count > 0) return fail(VGB_E_ARG, "channel %d: NULL buffer", c);
+        if (p.loop_start > p.sample_count) return fail(VGB_E_ARG, "channel %d: loop start %d past the end (%d samples)", c, p.loop_start, p.sample_count);
+        counts[c] = p.sample_count;
+        const int entries = vgb_gcadpcm_seek_entry_count(p.sample_count, p.samples_per_seek_table_entry);
+        if (entries > 0 && (!seek_table_out || !seek_table_out[c])) return fail(VGB_E_ARG, "channel %d: seek_table_out is NULL", c);
+        if (p.loop_start >= 0) any_loop = true;
+        taps[c].out_off = slab;
+        taps[c].samples_per_entry = p.sample_count > 0 ? p.samples_per_seek_table_entry : 0;
+        taps[c].loop_start = p.loop_start;
+        tap_off[c] = slab * 2;
+        tap_len[c] = (int64_t)entries * 4;
+        slab += (int64_t)align_up((size_t)entries * 2 + 2, 8);
+    }
+    if (any_loop && !loop_context_out) return fail(VGB_E_ARG, "loop_context_out is NULL");
+    GcLayout lay;
+    VGB_TRY(layout_common(lay, counts.data(), nullptr, n_channels, true));
+    layout_pack_offsets(lay);
+
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = g_ctx.stream;
+    const GcWorkspace w = carve(32, n_channels);
+    const size_t o_taps = align_up((size_t)slab * 2 + 16, 256);
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
+    VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
+    VGB_TRY(g_ctx.ws.reserve(w.total));
+    VGB_TRY(g_ctx.misc.reserve(o_taps + taps.size() * sizeof(GcTapChannel)));
+    char *misc = static_cast<char *>(g_ctx.misc.p);
+    std::vector<int64_t> off_b(n_channels), len_b(n_channels);
+    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.adpcm_off[c]; len_b[c] = gc_sample_count_to_byte_count(counts[c]); }
+    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), off_b, adpcm, len_b, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.coefs.p, coefs, (size_t)n_channels * 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(misc + o_taps, taps.data(), taps.size() * sizeof(GcTapChannel), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(misc, 0, (size_t)slab * 2, st));  // entry 0 and absent history samples are zero
+    VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, st));
+    GcChannelTable tab = table_view(g_ctx.ws.p, w, lay.n_channels);
+    launch_gc_taps(static_cast<const uint8_t *>(g_ctx.adpcm.p), tab, static_cast<const int16_t *>(g_ctx.coefs.p),
+                   reinterpret_cast<const GcTapChannel *>(misc + o_taps), reinterpret_cast<int16_t *>(misc), lay.max_frames, st);
+    g_ctx.launches += lay.max_frames > 0 ? 1 : 0;
+    CUDA_TRY(cudaGetLastError());
+    if (seek_table_out) VGB_TRY(copy_channels_out(seek_table_out, misc, tap_off, tap_len, st));
+    std::vector<int16_t> host_slab;
+    if (any_loop) {
+        host_slab.resize((size_t)slab);
+        CUDA_TRY(cudaMemcpyAsync(host_slab.data(), misc, (size_t)slab * 2, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (loop_context_out)
+        for (int c = 0; c < n_channels; c++) {
+            int16_t *ctx = loop_context_out + (size_t)c * 3;
+            ctx[0] = ctx[1] = ctx[2] = 0;
+            const int32_t ls = params[c].loop_start;
+            if (ls < 0 || counts[c] == 0) continue;
+            const int64_t frame_byte = (int64_t)(ls / kGcFrameSamples) * kGcFrameBytes;  // GcAdpcmDecoder.GetPredictorScale (:56-59)
+            if (frame_byte >= n_bytes[c]) return fail(VGB_E_ARG, "channel %d: loop start %d has no frame header in %d bytes", c, ls, n_bytes[c]);
+            ctx[0] = adpcm[c][frame_byte];
+            const int entries = vgb_gcadpcm_seek_entry_count(counts[c], params[c].samples_per_seek_table_entry);
+            ctx[1] = host_slab[(size_t)taps[c].out_off + 2 * entries];
+            ctx[2] = host_slab[(size_t)taps[c].out_off + 2 * entries + 1];
+        }
+    return VGB_OK;
+}
+
 int32_t vgb_gcadpcm_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs,
                                   int32_t n_frames, uint8_t *adpcm_out)
 {

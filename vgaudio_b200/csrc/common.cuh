@@ -55,6 +55,13 @@ struct GcChannelTable {
     int32_t n_channels;
 };
 
+// One channel of a seek-table / loop-context request (gc_decode_kernel<true>).
+struct GcTapChannel {
+    int64_t out_off;            // first short of the channel in the tap slab: [entries * 2 seek shorts][hist1][hist2]
+    int32_t samples_per_entry;  // 0: no seek table
+    int32_t loop_start;         // < 0: no loop context
+};
+
 // One channel of a CRI ADX batch (mirror of CriAdxParameters, Codecs/CriAdx/CriAdxParameters.cs:3-13, plus layout).
 struct AdxChannel {
     int64_t pcm_off;     // sample offset in the PCM slab

@@ -67,9 +67,16 @@ __device__ __forceinline__ void gc_decode_frame(uint32_t w0, uint32_t w1, const 
 
 }  // namespace
 
+// kTaps == false: the decoder proper, every sample goes to `pcm`.
+// kTaps == true : the post-encode channel rebuild of the format layer (GcAdpcmChannelBuilder.GetSeekTable /
+//                 GetLoopContext, Formats/GcAdpcm/GcAdpcmChannelBuilder.cs:176-202): the reference decodes the whole
+//                 channel again only to read pcm[i*spe - 1], pcm[i*spe - 2] (GcAdpcmSeekTable.cs:25-38) and
+//                 pcm[loopStart - 1], pcm[loopStart - 2] (GcAdpcmLoopContext.cs:24-26); here the same decode keeps
+//                 just those samples.  `pcm` is then the tap slab: per channel [entries*2 seek shorts][hist1][hist2].
+template <bool kTaps>
 __global__ void __launch_bounds__(kDecThreads)
 gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
-                 int16_t *__restrict__ pcm, int frame_begin, int frame_end)
+                 int16_t *__restrict__ pcm, int frame_begin, int frame_end, const GcTapChannel *__restrict__ taps)
 {
     __shared__ uint32_t coef_smem[kDecThreads][9];  // 8 (c1 | c2 << 16) pairs per channel, odd pitch: conflict free
     __shared__ __align__(16) uint4 ring_smem[kDecAhead][2][kDecThreads];  // [stage][half of the 32 bytes][thread]
@@ -81,7 +88,32 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
     const int f_hi = min(frame_end, n_frames);
     if (frame_begin >= f_hi) return;
     const uint8_t *src = adpcm + tab.adpcm_off[ch];
-    int16_t *dst = pcm + tab.pcm_off[ch];
+    int16_t *dst = pcm + (kTaps ? taps[ch].out_off : tab.pcm_off[ch]);
+    const int spe = kTaps ? taps[ch].samples_per_entry : 0;
+    const int loop_start = kTaps ? taps[ch].loop_start : -1;
+    const int entries = spe > 0 ? div_round_up(n, spe) : 0;
+    // taps mode: keep the samples of the run [p0, p0 + cnt) (two per word in o[]) that the seek table / loop context want
+    auto keep_taps = [&](int64_t p0, int cnt, const uint32_t (&o)[28]) {
+        auto sample_at = [&](int idx) -> int16_t {  // o[] lives in registers: select instead of indexing
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 28; j++) w = (j == (idx >> 1) && j * 2 < cnt + 1) ? o[j] : w;
+            return (int16_t)((w >> ((idx & 1) * 16)) & 0xFFFFu);
+        };
+        if (spe > 0) {
+            // multiples m of spe with a tap in the run: m - 1 or m - 2 in [p0, p0 + cnt)  <=>  p0 + 1 <= m <= p0 + cnt + 1
+            int64_t m = (p0 + 1 + spe - 1) / spe * spe;
+            if (m == 0) m = spe;  // the first entry is always zero (GcAdpcmSeekTable.cs:31)
+            for (; m <= p0 + cnt + 1; m += spe) {
+                const int64_t i = m / spe;
+                if (i >= entries) break;
+                if (m - 1 >= p0 && m - 1 < p0 + cnt) dst[2 * i] = sample_at((int)(m - 1 - p0));
+                if (m - 2 >= p0 && m - 2 < p0 + cnt) dst[2 * i + 1] = sample_at((int)(m - 2 - p0));
+            }
+        }
+        if (loop_start >= 1 && loop_start - 1 >= p0 && loop_start - 1 < p0 + cnt) dst[2 * entries] = sample_at((int)(loop_start - 1 - p0));
+        if (loop_start >= 2 && loop_start - 2 >= p0 && loop_start - 2 < p0 + cnt) dst[2 * entries + 1] = sample_at((int)(loop_start - 2 - p0));
+    };
     uint32_t *pairs = coef_smem[threadIdx.x];
 #pragma unroll
     for (int p = 0; p < 8; p++) {
@@ -119,9 +151,20 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
         gc_decode_frame(a.z, a.w, pairs, st, o + 7);
         gc_decode_frame(b.x, b.y, pairs, st, o + 14);
         gc_decode_frame(b.z, b.w, pairs, st, o + 21);
-        uint4 *vout = reinterpret_cast<uint4 *>(dst + (int64_t)g * kDecGroupFrames * kGcFrameSamples);
+        if constexpr (kTaps) {
+            const int64_t p0 = (int64_t)g * kDecGroupFrames * kGcFrameSamples;
+            bool hit = false;  // rare: one run in samples_per_entry / 56 holds a tap
+            if (spe > 0) {
+                const int64_t m = (p0 + 57) / spe * spe;  // largest multiple of spe <= p0 + 57
+                hit = m >= p0 + 1 && m > 0;
+            }
+            hit = hit || (loop_start >= 1 && loop_start - 2 < p0 + 56 && loop_start - 1 >= p0);
+            if (hit) keep_taps(p0, 56, o);
+        } else {
+            uint4 *vout = reinterpret_cast<uint4 *>(dst + (int64_t)g * kDecGroupFrames * kGcFrameSamples);
 #pragma unroll
-        for (int j = 0; j < 7; j++) vout[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int j = 0; j < 7; j++) vout[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
@@ -131,10 +174,18 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
         const int bytes = 1 + (take + 1) / 2;  // header + nibble bytes present (SampleCountToByteCount)
         uint32_t w[2] = {0, 0};  // bytes the stream does not hold decode as zero nibbles; those samples are not written
         for (int j = 0; j < bytes; j++) w[j >> 2] |= (uint32_t)src[(int64_t)f * kGcFrameBytes + j] << ((j & 3) * 8);
-        uint32_t o[7];
-        gc_decode_frame(w[0], w[1], pairs, st, o);
-        int16_t *d = dst + (int64_t)f * kGcFrameSamples;
-        for (int s = 0; s < take; s++) d[s] = (int16_t)((o[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu);
+        if constexpr (kTaps) {
+            uint32_t o[28];
+#pragma unroll
+            for (int j = 7; j < 28; j++) o[j] = 0;
+            gc_decode_frame(w[0], w[1], pairs, st, o);
+            keep_taps((int64_t)f * kGcFrameSamples, take, o);
+        } else {
+            uint32_t o[7];
+            gc_decode_frame(w[0], w[1], pairs, st, o);
+            int16_t *d = dst + (int64_t)f * kGcFrameSamples;
+            for (int s = 0; s < take; s++) d[s] = (int16_t)((o[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu);
+        }
     }
 
     tab.hist[2 * ch] = (int16_t)(st.hb1 - 32768);  // carried into the next time slice of the same call
@@ -147,7 +198,15 @@ void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int
     if (tab.n_channels <= 0 || max_frames <= 0) return;
     if (frame_begin >= frame_end || frame_begin >= max_frames) return;
     const int blocks = (tab.n_channels + kDecThreads - 1) / kDecThreads;
-    gc_decode_kernel<<<blocks, kDecThreads, 0, stream>>>(adpcm, tab, coefs, pcm, frame_begin, frame_end);
+    gc_decode_kernel<false><<<blocks, kDecThreads, 0, stream>>>(adpcm, tab, coefs, pcm, frame_begin, frame_end, nullptr);
+}
+
+void launch_gc_taps(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, const GcTapChannel *taps,
+                    int16_t *tap_slab, int max_frames, cudaStream_t stream)
+{
+    if (tab.n_channels <= 0 || max_frames <= 0) return;
+    const int blocks = (tab.n_channels + kDecThreads - 1) / kDecThreads;
+    gc_decode_kernel<true><<<blocks, kDecThreads, 0, stream>>>(adpcm, tab, coefs, tap_slab, 0, INT32_MAX, taps);
 }
 
 }  // namespace vgb

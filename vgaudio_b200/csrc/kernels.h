@@ -24,6 +24,10 @@ void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, c
 void launch_gc_decode(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, int16_t *pcm,
                       int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
 
+// seek table (GcAdpcmSeekTable.cs:25-38) and loop context (GcAdpcmLoopContext.cs:17-26) of already encoded channels
+void launch_gc_taps(const uint8_t *adpcm, const GcChannelTable &tab, const int16_t *coefs, const GcTapChannel *taps,
+                    int16_t *tap_slab, int max_frames, cudaStream_t stream);
+
 // adx.cu — CriAdxCodec.Encode / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171)
 void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
                        cudaStream_t stream);

@@ -206,6 +206,33 @@ def decode(adpcm, coefficients, config: Optional[GcAdpcmParameters] = None) -> n
                         [config] if config else None)[0]
 
 
+# ---- post-encode channel rebuild (GcAdpcmChannelBuilder.GetSeekTable / GetLoopContext) ------------------------------
+def seek_table_and_loop_context(adpcm, coefs, sample_counts, samples_per_seek_table_entry: int = 0, loop_starts=None):
+    """For every channel: GcAdpcmSeekTable.CreateSeekTable(decoded pcm, samplesPerEntry) (GcAdpcmSeekTable.cs:25-38)
+    and GcAdpcmLoopContext(adpcm, decoded pcm, loopStart) (GcAdpcmLoopContext.cs:17-26), without keeping the decoded
+    PCM.  Returns (seek_tables: list of int16[entries*2] or None, loop_contexts: list of (pred_scale, hist1, hist2) or
+    None per channel).  loop_starts: None, or one entry per channel (None / negative = no loop)."""
+    chans = _channel_list(adpcm, _as_u8)
+    n = len(chans)
+    lens = np.array([len(c) for c in chans], dtype=np.int32)
+    co = np.ascontiguousarray(coefs, dtype=np.int16).reshape(n, 16)
+    counts = [int(sample_counts)] * n if np.isscalar(sample_counts) else [int(v) for v in sample_counts]
+    loops = [-1] * n if loop_starts is None else [(-1 if v is None else int(v)) for v in loop_starts]
+    params = (N.VgbGcTapParams * max(n, 1))()
+    tables = []
+    for i in range(n):
+        params[i] = N.VgbGcTapParams(counts[i], samples_per_seek_table_entry, loops[i])
+        entries = N.lib.vgb_gcadpcm_seek_entry_count(counts[i], samples_per_seek_table_entry)
+        tables.append(np.zeros(entries * 2, dtype=np.int16))
+    ctx = np.zeros((max(n, 1), 3), dtype=np.int16)
+    ttab = (C.c_void_p * max(n, 1))(*[t.ctypes.data if t.size else None for t in tables])
+    N.check(N.lib.vgb_gcadpcm_seek_context_batch(_ptr_table(chans), lens.ctypes.data, co.ctypes.data,
+                                                 C.cast(params, C.c_void_p), n, ttab, ctx.ctypes.data))
+    seek = [t if samples_per_seek_table_entry > 0 else None for t in tables]
+    contexts = [(int(ctx[i, 0]) & 0xFF, int(ctx[i, 1]), int(ctx[i, 2])) if loops[i] >= 0 else None for i in range(n)]
+    return seek, contexts
+
+
 def get_predictor_scale(adpcm, sample: int) -> int:
     """GcAdpcmDecoder.GetPredictorScale (GcAdpcmDecoder.cs:56-59): metadata lookup, no arithmetic."""
     return int(adpcm[sample // SAMPLES_PER_FRAME * BYTES_PER_FRAME])
