@@ -499,6 +499,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             const bool trouble0 = (trouble_bits & 0x0000FFFFu) != 0u || (pair_done & 0x00005555u) != 0x00005555u;
             const bool trouble1 = (trouble_bits & 0xFFFF0000u) != 0u || (pair_done & 0x55550000u) != 0x55550000u;
             if (trouble0 || trouble1) {
+                __syncwarp();  // the fast path's frame bytes are overwritten below by another lane of the warp
                 const bool mine = (half ? trouble1 : trouble0) && active;
                 const uint32_t redo = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane, mine, out8);
                 if (mine) packed = redo;

@@ -174,16 +174,18 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
             for (int stage = 0; stage < 6; stage++) {  // (Mdct.cs:148-175)
                 const int block_bits = 6 - stage, half_bits = block_bits - 1;
                 const int block_size = 1 << block_bits, block_half = 1 << half_bits;
-                const int block = i >> half_bits, j = i & (block_half - 1);
-                const int front = (block * block_size + j) * 2, back = front + block_size;
-                const double a = t[front] - t[back];
-                const double b = t[front + 1] - t[back + 1];
-                const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
-                const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
-                t[front] = f0;
-                t[front + 1] = f1;
-                t[back] = a * cs + b * sn;
-                t[back + 1] = a * sn - b * cs;
+                if (i < 32) {  // a 128-point stage has 32 butterflies of two complex pairs each
+                    const int block = i >> half_bits, j = i & (block_half - 1);
+                    const int front = (block * block_size + j) * 2, back = front + block_size;
+                    const double a = t[front] - t[back];
+                    const double b = t[front + 1] - t[back + 1];
+                    const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
+                    const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
+                    t[front] = f0;
+                    t[front + 1] = f1;
+                    t[back] = a * cs + b * sn;
+                    t[back + 1] = a * sn - b * cs;
+                }
                 __syncthreads();
             }
             double *out = spectra + ((size_t)c * kSub + sf) * kBins;
@@ -804,16 +806,18 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
             for (int stage = 0; stage < 6; stage++) {
                 const int block_bits = 6 - stage, half_bits = block_bits - 1;
                 const int block_size = 1 << block_bits, block_half = 1 << half_bits;
-                const int block = i >> half_bits, j = i & (block_half - 1);
-                const int front = (block * block_size + j) * 2, back = front + block_size;
-                const double a = t[front] - t[back];
-                const double b = t[front + 1] - t[back + 1];
-                const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
-                const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
-                t[front] = f0;
-                t[front + 1] = f1;
-                t[back] = a * cs + b * sn;
-                t[back + 1] = a * sn - b * cs;
+                if (i < 32) {  // a 128-point stage has 32 butterflies of two complex pairs each
+                    const int block = i >> half_bits, j = i & (block_half - 1);
+                    const int front = (block * block_size + j) * 2, back = front + block_size;
+                    const double a = t[front] - t[back];
+                    const double b = t[front + 1] - t[back + 1];
+                    const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
+                    const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
+                    t[front] = f0;
+                    t[front + 1] = f1;
+                    t[back] = a * cs + b * sn;
+                    t[back + 1] = a * sn - b * cs;
+                }
                 __syncthreads();
             }
             io[i] = t[T.shuffle[i]] * T.mdct_scale;
