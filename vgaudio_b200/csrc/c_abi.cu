@@ -333,12 +333,6 @@ bool uniform_stride(T *const *ptr, int32_t n, int64_t &stride_bytes)
     return true;
 }
 
-bool all_equal(const std::vector<int32_t> &v)
-{
-    for (size_t i = 1; i < v.size(); i++)
-        if (v[i] != v[0]) return false;
-    return true;
-}
 
 // Host -> device copy of every channel's bytes: one strided 2D copy when the caller's buffers form a slab,
 // else one copy per channel.

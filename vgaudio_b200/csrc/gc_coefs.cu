@@ -247,7 +247,6 @@ struct __align__(16) RefineSlot {
     double2 q[8][33];     // per-bucket queues of one block of 32 records; 33: the 16 accumulator lanes (bucket, comp)
                           // read entry j of all buckets at once, 528-byte rows put them in 16 distinct bank pairs
     int32_t count[8];     // records per bucket (buckets the pass does not use stay 0)
-    int32_t n_max, pad[3];  // largest count
 };
 
 struct RefineShared {
@@ -346,15 +345,12 @@ __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames,
             pick = d[0] < 1.0e30 ? idx[0] : 0;  // nothing below the initial 1.0e30: the index stays 0
         }
         uint32_t mine = 0;
-        int largest = 0;  // (kept for reference: the consumer no longer needs the longest queue)
 #pragma unroll
         for (int k = 0; k < NB; k++) {
             const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok && pick == k);
             mine = pick == k ? bits : mine;
-            largest = max(largest, __popc(bits));
             if (lane == k) slot.count[k] = __popc(bits);
         }
-        (void)largest;
         if (ok) slot.q[pick][__popc(mine & lanes_below)] = r;
         __syncwarp();
         {   // pad every queue to a multiple of four entries with -0.0 (lane = bucket * 4 + i)
