@@ -267,29 +267,28 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     const int32_t bias_c = wmul(32768, wadd(c0, c1));  // undoes the +32768 bias of both history samples
     int32_t p1 = tab.hist[2 * ch] + 32768, p2 = tab.hist[2 * ch + 1] + 32768;  // biased history (newest, older)
 
-    // 16-byte vector v (0..27) of a chunk, zero beyond the encoded sample count (GcAdpcmEncoder.cs:32-34)
-    auto load_vec = [&](int chunk_frame, int v) -> uint4 {
-        uint4 q = make_uint4(0, 0, 0, 0);
-        const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + v * 8;
-        if (v < kEncChunkSamples / 8 && chunk_frame < f_hi && s < n_enc) {
-            q = __ldg(reinterpret_cast<const uint4 *>(src + s));
-            const int valid = (int)min((int64_t)8, (int64_t)n_enc - s);
-            if (valid < 8) {
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    // Stage the 28 16-byte vectors of the chunk starting at `chunk_frame` into buffer b with cp.async (LDGSTS): the
+    // copy needs no registers, so it is issued a whole chunk (~24k cycles) ahead and DRAM latency never shows - a
+    // register-staged load was moved next to its first use by the compiler and cost ~1300 cycles per chunk (ncu).
+    // Bytes past the encoded sample count are zero-filled by the copy itself (src-size operand; GcAdpcmEncoder.cs:32-34).
+    auto stage_chunk = [&](int chunk_frame, int b) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (2 * i >= valid) w[i] = 0;
-                    else if (2 * i + 1 >= valid) w[i] &= 0xFFFFu;
-                }
-                q = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int k = 0; k < 2; k++) {
+            const int v = l16 + 16 * k;
+            if (v < kEncChunkSamples / 8) {
+                const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + v * 8;
+                int64_t valid = chunk_frame < f_hi ? (int64_t)n_enc - s : 0;
+                valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
+                const int16_t *from = valid > 0 ? src + s : src;
+                const unsigned to = (unsigned)__cvta_generic_to_shared(&in_buf[warp][half][b][v * 8]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(to), "l"(from), "r"((int)valid * 2) : "memory");
             }
         }
-        return q;
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto store_chunk = [&](int b, uint4 va, uint4 vb) {
-        uint4 *d = reinterpret_cast<uint4 *>(in_buf[warp][half][b]);
-        d[l16] = va;
-        if (l16 + 16 < kEncChunkSamples / 8) d[l16 + 16] = vb;
+    auto staged_wait = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
     };
     // residual keys of samples 2..13 (raw samples only).  The two candidate lanes of a predictor share the work:
     // lane `cand` takes samples 2+6*cand .. 7+6*cand, one shuffle-xor combines them.
@@ -307,8 +306,8 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     };
 
     int buf = 0;
-    store_chunk(0, load_vec(frame_begin, l16), load_vec(frame_begin, l16 + 16));
-    __syncwarp();
+    stage_chunk(frame_begin, 0);
+    staged_wait();
     // pipeline prologue: samples and residual keys of the first frame
     int32_t x[14];
 #pragma unroll
@@ -317,31 +316,15 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 1));
 
     for (int cf = frame_begin; cf < f_hi_warp; cf += kEncChunkFrames) {
-        // next chunk: pull it into L2 now (no registers held), load it one frame before it is staged into the other
-        // buffer at mid-chunk - the compiler otherwise sinks an early load to its use and exposes DRAM latency
-        {
-            const int64_t s_next = (int64_t)(cf + kEncChunkFrames) * kGcFrameSamples + l16 * 8;
-            if (cf + kEncChunkFrames < f_hi && s_next < n_enc) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + s_next));
-                if (l16 + 16 < kEncChunkSamples / 8 && s_next + 128 < n_enc)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + s_next + 128));
-            }
-        }
-        uint4 next_a = make_uint4(0, 0, 0, 0), next_b = make_uint4(0, 0, 0, 0);
+        // next chunk -> the other buffer (dead since the previous chunk's last frame), awaited before the last frame
+        stage_chunk(cf + kEncChunkFrames, buf ^ 1);
         const int frames_warp = min(kEncChunkFrames, f_hi_warp - cf);
         const int frames_here = max(min(kEncChunkFrames, f_hi - cf), 0);  // this half's share
         const int16_t *chunk = in_buf[warp][half][buf];
         const int16_t *other = in_buf[warp][half][buf ^ 1];
 
         for (int i = 0; i < frames_warp; i++) {
-            if (i == kEncChunkFrames / 2 - 1) {
-                next_a = load_vec(cf + kEncChunkFrames, l16);
-                next_b = load_vec(cf + kEncChunkFrames, l16 + 16);
-            }
-            if (i == kEncChunkFrames / 2) {  // the other buffer was last read 8 frames ago: refill it now
-                store_chunk(buf ^ 1, next_a, next_b);
-                __syncwarp();
-            }
+            if (i == kEncChunkFrames - 1) staged_wait();  // this frame reads the next chunk's first samples
             const bool active = i < frames_here;  // a shorter channel idles while its warp mate finishes
             const int16_t *frame = chunk + i * kGcFrameSamples;
             const int16_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
@@ -513,7 +496,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             for (int j = 0; j < 14; j++) x[j] = xn[j];
             key_rest = key_rest_next;
         }
-        __syncwarp();
+        staged_wait();
 
         // write the chunk's bytes; only the channel's last frame can be partial (:38)
         if (frames_here > 0) {
