@@ -325,9 +325,12 @@ def main():
             e2e_ms = float(tmax.item())
         tl = (C.c_float * 12)()
         N.check(vg.lib.vgb_debug_last_timeline(tl, 12))
+        tc = (C.c_float * 4)()
+        N.check(vg.lib.vgb_debug_last_coefs_done(tc, 4))
         e2e = {"value": round(world * samples_per_step / (e2e_ms / 1e3) / 1e6, 3), "unit": "Msamples/s",
-               "timeline_ms": {"note": "per channel group: [H2D landed, kernels done, D2H done] since first copy",
-                               "groups": [[round(tl[3 * g + k], 1) for k in range(3)] for g in range(4) if tl[3 * g] >= 0]},
+               "timeline_ms": {"note": "ms since the first copy was enqueued, per pipeline group: [H2D landed, kernels done, D2H done]; a uniform batch is one group whose encode runs in 8 time slices with the D2H of a slice overlapping the next",
+                               "groups": [[round(tl[3 * g + k], 1) for k in range(3)] for g in range(4) if tl[3 * g] >= 0],
+                               "coefs_done": [round(tc[g], 1) for g in range(4) if tl[3 * g] >= 0]},
                "h2d_bytes_per_step": int(n_ch * n * 2), "d2h_bytes_per_step": int(n_ch * n_bytes + n_ch * 32),
                "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
                "api": "vgb_gcadpcm_encode_batch (host pointers, pinned), wall clock around the synchronous call"}

@@ -166,6 +166,8 @@ int32_t vgb_last_kernel_ms(float *ms_out, int32_t n);
 /* Device timeline of the last host GC-ADPCM encode call, ms since its first copy was enqueued: per channel group
  * [H2D landed, kernels finished, D2H finished] (evidence of the copy/compute overlap; bench.py reports it). */
 int32_t vgb_debug_last_timeline(float *ms_out, int32_t n);
+/* same call, per channel group: when its coefficient kernels finished (ms since the first copy was enqueued) */
+int32_t vgb_debug_last_coefs_done(float *ms_out, int32_t n);
 
 /* Debug/test taps (tests/ only): run coefficient phase 1 and return, per frame, the direct-form pair and the
  * accept flag the refinement consumes.  Host buffers; dir_out [frames][2] doubles, accepted_out [frames] bytes. */

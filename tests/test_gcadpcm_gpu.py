@@ -246,3 +246,18 @@ def test_seek_context_without_table_and_errors(vg, oracle):
     assert ctx[0] == oracle.gc_loop_context(a, dec, 2500)
     with pytest.raises(vg.VgbError):  # loop start past the end of the channel
         vg.gcadpcm.seek_table_and_loop_context([a], c.reshape(1, 16), [5000], 0, [5001])
+
+
+def test_uniform_slab_takes_the_time_sliced_pipeline(vg, oracle):
+    """64+ equally long channels handed over as one slab go through the time-sliced host pipeline (encode cut into frame
+    ranges with the history carried between launches, D2H of a slice overlapping the next slice): same bytes as the
+    oracle, progress deltas summing to the frame total (GcAdpcmFormat.cs:62)."""
+    n_ch, n = 72, 14 * 1100 + 9  # 1101 frames, partial last frame
+    pcm = np.stack([synth.channel(800 + c, n, degenerate=False) for c in range(n_ch)])
+    seen = []
+    coefs, adpcm = vg.gcadpcm.encode_batch(pcm, progress=seen.append)
+    assert sum(seen) == n_ch * 1101 and len(seen) > 1
+    for c in range(0, n_ch, 7):
+        co = oracle.calculate_coefficients(pcm[c])
+        assert np.array_equal(coefs[c], co), c
+        assert np.array_equal(adpcm[c], oracle.encode(pcm[c], co)), c

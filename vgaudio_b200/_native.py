@@ -105,6 +105,7 @@ SIGNATURES = {
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "vgb_debug_last_coefs_done": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_gcadpcm_debug_records": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -93,8 +94,9 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[kMaxGroups] = {};
-    cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_out[kMaxGroups] = {}, ev_t0 = nullptr;
+    cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_out[kMaxGroups] = {}, ev_mid[kMaxGroups] = {}, ev_t0 = nullptr;
     int last_groups = 0;
+    cudaEvent_t ev_slice[16] = {};   // encode time slices of the uniform-batch pipeline
     DevBuf pcm, adpcm, coefs, ws, misc;
     bool timing = false;
     cudaEvent_t ev[2 * kTimers] = {};
@@ -127,8 +129,10 @@ int32_t ensure_ready_locked()
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_in[g]));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_done[g]));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_out[g]));
+        CUDA_TRY(cudaEventCreate(&g_ctx.ev_mid[g]));
     }
     CUDA_TRY(cudaEventCreate(&g_ctx.ev_t0));
+    for (auto &ev : g_ctx.ev_slice) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : g_ctx.ev) CUDA_TRY(cudaEventCreate(&ev));
     g_ctx.ready = true;
     return VGB_OK;
@@ -273,7 +277,7 @@ void layout_pack_offsets(GcLayout &lay)
 // Kernel sequence of one encode call on `stream` (device pointers only).
 int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *d_coefs_in, int16_t *d_coefs_out,
                       uint8_t *d_adpcm, void *d_ws, const GcWorkspace &w, cudaStream_t stream, bool do_encode,
-                      bool timed = true, bool tables_uploaded = false)
+                      bool timed = true, bool tables_uploaded = false, cudaEvent_t after_coefs = nullptr)
 {
     const bool was_timing = g_ctx.timing;
     if (!timed) g_ctx.timing = false;  // the kernel timers describe single-stream (_dev) calls only
@@ -296,6 +300,7 @@ int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *
     } else if (d_coefs_in != d_coefs_out) {
         CUDA_TRY(cudaMemcpyAsync(d_coefs_out, d_coefs_in, (size_t)lay.n_channels * 32, cudaMemcpyDeviceToDevice, stream));
     }
+    if (after_coefs) CUDA_TRY(cudaEventRecord(after_coefs, stream));
     if (do_encode) {
         tick(2, true, stream);
         launch_gc_encode(d_pcm, tab, d_coefs_out, d_adpcm, lay.max_frames, 0, INT_MAX, stream);
@@ -410,9 +415,9 @@ GcLayout sub_layout(const GcLayout &full, int c0, int c1)
     return g;
 }
 
-// One host call = up to kMaxGroups channel groups pipelined over three kinds of streams: the H2D copy of group g+1,
-// the kernels of group g and the D2H copy of group g-1 overlap (a channel cannot be split in time - its coefficients
-// need all of its samples - but channels are independent).
+// One host call, pipelined over three kinds of streams (input copies, kernels, output copies).  A uniform batch is cut
+// in TIME (see below); otherwise up to kMaxGroups channel groups: the H2D copy of group g+1, the kernels of group g and
+// the D2H copy of group g-1 overlap (channels are independent; a channel's coefficients need all of its samples).
 int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
                          const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out, uint8_t *const *adpcm_out,
                          vgb_progress_cb cb, void *user, bool do_encode)
@@ -429,8 +434,85 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     }
     layout_pack_offsets(lay);
 
+    // ---- uniform batch (every channel the same length, the caller's buffers one slab each): TIME-sliced pipeline.
+    // Pipelining over channel groups overlaps copies with kernels, but the kernels of different groups then share the
+    // SMs and the latency-bound encoder of one group is slowed by the issue-hungry coefficient kernels of the next
+    // (measured: 4 groups 160 ms vs 155 ms with no overlap at all).  For a uniform batch the ENCODE is cut in time
+    // instead - every slice is the same channels, a later frame range, history carried in the table - so nothing
+    // runs beside the coefficient kernels and each slice's D2H overlaps the next slice's encode.
+    {
+        int64_t in_stride = 0, out_stride = 0;
+        bool uniform = do_encode && n_channels >= 64 && !coefs_in && uniform_stride(pcm, n_channels, in_stride) &&
+                       uniform_stride(adpcm_out, n_channels, out_stride);
+        for (int c = 1; c < n_channels && uniform; c++)
+            uniform = lay.n_samples[c] == lay.n_samples[0] && lay.enc_count[c] == lay.enc_count[0];
+        if (std::getenv("VGB_ENCODE_GROUPS")) uniform = false;  // tuning knob forces the channel-group pipeline
+        const int frames = uniform ? div_round_up(lay.enc_count[0], kGcFrameSamples) : 0;
+        if (uniform && frames >= 16 * 64) {
+            std::lock_guard<std::mutex> lock(g_ctx.mu);
+            VGB_TRY(ensure_ready_locked());
+            const GcWorkspace w = carve(lay.rec_total, n_channels);
+            VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
+            VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
+            VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
+            VGB_TRY(g_ctx.ws.reserve(w.total));
+            CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+            int16_t *d_coefs = static_cast<int16_t *>(g_ctx.coefs.p);
+            cudaStream_t st = g_ctx.s_comp[0];
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_t0, g_ctx.s_in));
+            g_ctx.last_groups = 1;
+            VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, g_ctx.s_in));
+            const int64_t d_in_pitch = (lay.pcm_off[1] - lay.pcm_off[0]) * 2, d_out_pitch = lay.adpcm_off[1] - lay.adpcm_off[0];
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g_ctx.pcm.p) + lay.pcm_off[0] * 2, (size_t)d_in_pitch, pcm[0], (size_t)in_stride,
+                                       (size_t)lay.n_samples[0] * 2, (size_t)n_channels, cudaMemcpyHostToDevice, g_ctx.s_in));
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_in[0], g_ctx.s_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_in[0], 0));
+            // coefficient kernels alone on the device, then the encode in slices of whole 16-frame chunks
+            VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), lay, nullptr, d_coefs, static_cast<uint8_t *>(g_ctx.adpcm.p),
+                                  g_ctx.ws.p, w, st, /*do_encode=*/false, /*timed=*/false, /*tables_uploaded=*/true, g_ctx.ev_mid[0]));
+            GcChannelTable tab = table_view(g_ctx.ws.p, w, n_channels);
+            const int n_slices = 8;
+            const int per_slice = (div_round_up(frames, n_slices) + 15) / 16 * 16;
+            const int64_t total_bytes = gc_sample_count_to_byte_count(lay.enc_count[0]);
+            int used = 0;
+            for (int k = 0; k < n_slices; k++) {
+                const int f0 = k * per_slice, f1 = std::min(frames, (k + 1) * per_slice);
+                if (f0 >= f1) break;
+                launch_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), tab, d_coefs, static_cast<uint8_t *>(g_ctx.adpcm.p),
+                                 lay.max_frames, f0, f1, st);
+                g_ctx.launches += 1;
+                CUDA_TRY(cudaEventRecord(g_ctx.ev_slice[k], st));
+                CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_slice[k], 0));
+                const int64_t b0 = (int64_t)f0 * kGcFrameBytes, b1 = std::min((int64_t)f1 * kGcFrameBytes, total_bytes);
+                if (b1 > b0)
+                    CUDA_TRY(cudaMemcpy2DAsync(adpcm_out[0] + b0, (size_t)out_stride, static_cast<char *>(g_ctx.adpcm.p) + lay.adpcm_off[0] + b0,
+                                               (size_t)d_out_pitch, (size_t)(b1 - b0), (size_t)n_channels, cudaMemcpyDeviceToHost, g_ctx.s_out));
+                used = k + 1;
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_done[0], st));
+            CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_mid[0], 0));
+            CUDA_TRY(cudaMemcpyAsync(coefs_out, d_coefs, (size_t)n_channels * 32, cudaMemcpyDeviceToHost, g_ctx.s_out));
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_out[0], g_ctx.s_out));
+            // progress: frames of each finished slice (IProgressReport.ReportAdd deltas sum to SetTotal)
+            int64_t reported = 0;
+            for (int k = 0; k < used; k++) {
+                CUDA_TRY(cudaEventSynchronize(g_ctx.ev_slice[k]));
+                const int64_t upto = (int64_t)std::min(frames, (k + 1) * per_slice) * n_channels;
+                if (cb && upto > reported) cb(user, upto - reported);
+                reported = std::max(reported, upto);
+            }
+            CUDA_TRY(cudaEventSynchronize(g_ctx.ev_out[0]));
+            return VGB_OK;
+        }
+    }
+
     // channel groups with roughly equal sample totals (boundaries on channel indices, order preserved)
     int n_groups = n_channels >= 64 ? kMaxGroups : 1;
+    if (const char *env = std::getenv("VGB_ENCODE_GROUPS")) {  // tuning knob: 1..kMaxGroups
+        const int want = std::atoi(env);
+        if (want >= 1 && want <= kMaxGroups && n_channels >= want) n_groups = want;
+    }
     std::vector<int> bound(n_groups + 1, n_channels);
     bound[0] = 0;
     {
@@ -490,7 +572,7 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
         VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), glay[g],
                               d_coefs_in ? d_coefs_in + (size_t)c0 * 16 : nullptr, d_coefs_out + (size_t)c0 * 16,
                               static_cast<uint8_t *>(g_ctx.adpcm.p), static_cast<char *>(g_ctx.ws.p) + ws_at[g], gws[g],
-                              st, do_encode, /*timed=*/false, /*tables_uploaded=*/true));
+                              st, do_encode, /*timed=*/false, /*tables_uploaded=*/true, g_ctx.ev_mid[g]));
         CUDA_TRY(cudaEventRecord(g_ctx.ev_done[g], st));
     }
     // stage 3: D2H of each group's results on the output stream
@@ -900,6 +982,17 @@ int32_t vgb_debug_last_timeline(float *ms_out, int32_t n)
         CUDA_TRY(cudaEventElapsedTime(&ms_out[3 * g + 1], g_ctx.ev_t0, g_ctx.ev_done[g]));
         CUDA_TRY(cudaEventElapsedTime(&ms_out[3 * g + 2], g_ctx.ev_t0, g_ctx.ev_out[g]));
     }
+    return VGB_OK;
+}
+
+int32_t vgb_debug_last_coefs_done(float *ms_out, int32_t n)
+{
+    if (!ms_out || n < 0) return fail(VGB_E_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    for (int i = 0; i < n; i++) ms_out[i] = -1.0f;
+    if (!g_ctx.ready) return VGB_OK;
+    for (int g = 0; g < g_ctx.last_groups && g < n; g++)
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[g], g_ctx.ev_t0, g_ctx.ev_mid[g]));
     return VGB_OK;
 }
 

@@ -89,9 +89,9 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
     if (frame_begin >= f_hi) return;
     const uint8_t *src = adpcm + tab.adpcm_off[ch];
     int16_t *dst = pcm + (kTaps ? taps[ch].out_off : tab.pcm_off[ch]);
-    const int spe = kTaps ? taps[ch].samples_per_entry : 0;
+    const int spe = kTaps ? taps[ch].samples_per_entry : 1;  // (1: keeps the dead divisions of the decoder proper defined)
     const int loop_start = kTaps ? taps[ch].loop_start : -1;
-    const int entries = spe > 0 ? div_round_up(n, spe) : 0;
+    const int entries = (kTaps && spe > 0) ? div_round_up(n, spe) : 0;
     // taps mode: keep the samples of the run [p0, p0 + cnt) (two per word in o[]) that the seek table / loop context want
     auto keep_taps = [&](int64_t p0, int cnt, const uint32_t (&o)[28]) {
         auto sample_at = [&](int idx) -> int16_t {  // o[] lives in registers: select instead of indexing
@@ -100,7 +100,7 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
             for (int j = 0; j < 28; j++) w = (j == (idx >> 1) && j * 2 < cnt + 1) ? o[j] : w;
             return (int16_t)((w >> ((idx & 1) * 16)) & 0xFFFFu);
         };
-        if (spe > 0) {
+        if (kTaps && spe > 0) {
             // multiples m of spe with a tap in the run: m - 1 or m - 2 in [p0, p0 + cnt)  <=>  p0 + 1 <= m <= p0 + cnt + 1
             int64_t m = (p0 + 1 + spe - 1) / spe * spe;
             if (m == 0) m = spe;  // the first entry is always zero (GcAdpcmSeekTable.cs:31)
