@@ -463,14 +463,35 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
             g_ctx.last_groups = 1;
             VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, g_ctx.s_in));
             const int64_t d_in_pitch = (lay.pcm_off[1] - lay.pcm_off[0]) * 2, d_out_pitch = lay.adpcm_off[1] - lay.adpcm_off[0];
-            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g_ctx.pcm.p) + lay.pcm_off[0] * 2, (size_t)d_in_pitch, pcm[0], (size_t)in_stride,
-                                       (size_t)lay.n_samples[0] * 2, (size_t)n_channels, cudaMemcpyHostToDevice, g_ctx.s_in));
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_in[0], g_ctx.s_in));
-            CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_in[0], 0));
-            // coefficient kernels alone on the device, then the encode in slices of whole 16-frame chunks
-            VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), lay, nullptr, d_coefs, static_cast<uint8_t *>(g_ctx.adpcm.p),
-                                  g_ctx.ws.p, w, st, /*do_encode=*/false, /*timed=*/false, /*tables_uploaded=*/true, g_ctx.ev_mid[0]));
+            // H2D in 4 time slices (2-D copies: the same sample range of every channel), the per-frame record kernel of a
+            // slice running under the next slice's copy; then the refinement, alone on the device
             GcChannelTable tab = table_view(g_ctx.ws.p, w, n_channels);
+            {
+                char *ws_b = static_cast<char *>(g_ctx.ws.p);
+                double2 *records = reinterpret_cast<double2 *>(ws_b + w.off_records);
+                uint32_t *mask = reinterpret_cast<uint32_t *>(ws_b + w.off_mask);
+                const int in_slices = 4;
+                const int n_all = lay.n_samples[0];
+                const int a_frames = div_round_up(n_all, kGcFrameSamples);
+                const int per_in = (div_round_up(a_frames, in_slices) + 255) / 256 * 256;  // whole record-kernel tiles
+                for (int k = 0; k < in_slices; k++) {
+                    const int f0 = k * per_in, f1 = std::min(a_frames, (k + 1) * per_in);
+                    if (f0 >= f1) break;
+                    const int64_t s0 = (int64_t)f0 * kGcFrameSamples, s1 = std::min((int64_t)f1 * kGcFrameSamples, (int64_t)n_all);
+                    CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g_ctx.pcm.p) + (lay.pcm_off[0] + s0) * 2, (size_t)d_in_pitch,
+                                               reinterpret_cast<const char *>(pcm[0]) + s0 * 2, (size_t)in_stride, (size_t)(s1 - s0) * 2,
+                                               (size_t)n_channels, cudaMemcpyHostToDevice, g_ctx.s_in));
+                    CUDA_TRY(cudaEventRecord(g_ctx.ev_slice[8 + k], g_ctx.s_in));
+                    CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_slice[8 + k], 0));
+                    launch_gc_coef_frames(static_cast<const int16_t *>(g_ctx.pcm.p), tab, records, mask, lay.max_frames, f0, f1, st);
+                    g_ctx.launches += 1;
+                }
+                CUDA_TRY(cudaEventRecord(g_ctx.ev_in[0], g_ctx.s_in));
+                launch_gc_coef_refine(tab, records, mask, d_coefs, st);
+                g_ctx.launches += 1;
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(g_ctx.ev_mid[0], st));
+            }
             const int n_slices = 8;
             const int per_slice = (div_round_up(frames, n_slices) + 15) / 16 * 16;
             const int64_t total_bytes = gc_sample_count_to_byte_count(lay.enc_count[0]);
