@@ -593,6 +593,7 @@ struct BitWindow {
     const uint32_t *words;
     int n_words, next;
     uint64_t win;
+    uint32_t ahead;  // words[next], fetched when the previous refill happened: the load is off the bit chain
     int avail;
     __device__ uint32_t word(int i) const { return i < n_words ? words[i] : 0u; }
     __device__ void open(const uint32_t *w, int n)
@@ -600,13 +601,18 @@ struct BitWindow {
         words = w; n_words = n;
         win = ((uint64_t)word(0) << 32) | word(1);
         avail = 64; next = 2;
+        ahead = word(2);
     }
     __device__ uint32_t peek(int count) const { return (uint32_t)((win >> 1) >> (63 - count)); }  // count 0..32
     __device__ void skip(int count)
     {
         win <<= count;
         avail -= count;
-        if (avail <= 32) { win |= (uint64_t)word(next++) << (32 - avail); avail += 32; }
+        if (avail <= 32) {
+            win |= (uint64_t)ahead << (32 - avail);
+            avail += 32;
+            ahead = word(++next);
+        }
     }
     __device__ int read(int count) { const uint32_t v = peek(count); skip(count); return (int)v; }
 };
@@ -627,8 +633,11 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
                          int32_t *__restrict__ status_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint8_t s_dbits[8][16], s_maxbits[16];
-    __shared__ int8_t s_dval[8][16];
+    // prefix-code tables packed for the serial parser: for resolution < 8 the 16 (length, value) pairs of
+    // QuantizedSpectrumBits / QuantizedSpectrumValue as two 64-bit words (4 bits per code) - a code then costs two
+    // shifts instead of a dependent shared-memory lookup on the bit chain
+    __shared__ unsigned long long s_lens64[16], s_vals64[16];
+    __shared__ uint8_t s_maxbits[16];
     const int nch = cfg.channel_count;
     double *spectra = reinterpret_cast<double *>(smem_raw);                   // [nch][8][128]
     double *work = spectra + (size_t)nch * kSub * kBins;                      // [2][128]
@@ -651,10 +660,16 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
             if (4 * w + j < cfg.frame_size) v |= (uint32_t)src[4 * w + j] << (24 - 8 * j);
         words[w] = v;
     }
-    if (tid < 128) {  // the small code tables move next to the parser
-        s_dbits[tid >> 4][tid & 15] = T.dequantize_bits[tid >> 4][tid & 15];
-        s_dval[tid >> 4][tid & 15] = T.dequantize_value[tid >> 4][tid & 15];
-        if (tid < 16) s_maxbits[tid] = T.quantized_max_bits[tid];
+    if (tid < 16) {
+        unsigned long long lens = 0, vals = 0;
+        if (tid < 8)
+            for (int code = 0; code < 16; code++) {
+                lens |= (unsigned long long)(T.dequantize_bits[tid][code] & 15u) << (4 * code);
+                vals |= (unsigned long long)((unsigned)T.dequantize_value[tid][code] & 15u) << (4 * code);
+            }
+        s_lens64[tid] = lens;
+        s_vals64[tid] = vals;
+        s_maxbits[tid] = T.quantized_max_bits[tid];
     }
     if (tid < nch) {
         chs[tid].type = cfg.channel_type[tid];
@@ -714,20 +729,29 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
                 for (int c = 0; c < nch; c++) {
                     const HcaChannelState &ch = chs[c];
                     int *q = quantized + ((size_t)c * kSub + sf) * kBins;
-                    for (int b = 0; b < ch.coded_count; b++) {
-                        const int resolution = ch.resolution[b];
-                        int bits = s_maxbits[resolution];
-                        const int code = (int)r.peek(bits);
-                        int v;
-                        if (resolution < 8) {
-                            bits = s_dbits[resolution][code];
-                            v = s_dval[resolution][code];
-                        } else {
-                            v = code / 2 * (1 - (code % 2 * 2));
-                            if (v == 0) bits--;
+                    const int n_coded = ch.coded_count;
+                    // the band's descriptor (max code length, packed tables) does not depend on the bit position:
+                    // it is fetched one band ahead so that only shifts sit on the serial chain
+                    int res = n_coded > 0 ? ch.resolution[0] : 0;
+                    int mbits = s_maxbits[res];
+                    unsigned long long lens = s_lens64[res], vals = s_vals64[res];
+                    for (int b = 0; b < n_coded; b++) {
+                        const int res_next = b + 1 < n_coded ? ch.resolution[b + 1] : 0;
+                        const int mbits_next = s_maxbits[res_next];
+                        const unsigned long long lens_next = s_lens64[res_next], vals_next = s_vals64[res_next];
+                        const int code = (int)r.peek(mbits);
+                        int v, bits;
+                        if (mbits <= 4) {  // resolution < 8: prefix code
+                            bits = (int)((lens >> (4 * code)) & 15u);
+                            v = (int)((unsigned)(vals >> (4 * code)) << 28) >> 28;  // signed nibble
+                        } else {           // sign-magnitude, the sign bit is absent for zero
+                            const int mag = code >> 1;
+                            v = (code & 1) ? -mag : mag;
+                            bits = mbits - (mag == 0 ? 1 : 0);
                         }
                         q[b] = v;
                         r.skip(bits);
+                        res = res_next; mbits = mbits_next; lens = lens_next; vals = vals_next;
                     }
                 }
         } else {
