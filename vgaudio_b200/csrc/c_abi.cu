@@ -1630,9 +1630,10 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
     cudaStream_t st = g_ctx.stream;
     const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
     const size_t o_edge = align_up(o_status + (size_t)n_streams * 4, 256);
+    const size_t o_parsed = align_up(o_edge + (size_t)frames_total * nch * 2 * 128 * sizeof(double), 256);
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)fb + 16));
-    VGB_TRY(g_ctx.misc.reserve(o_edge + (size_t)frames_total * nch * 2 * 128 * sizeof(double)));
+    VGB_TRY(g_ctx.misc.reserve(o_parsed + hca_decode_parsed_bytes(cfg, frames_total)));
     char *misc = static_cast<char *>(g_ctx.misc.p);
     VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, frames, in_len, st));
     CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
@@ -1641,10 +1642,11 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
     CUDA_TRY(cudaMemsetAsync(g_ctx.pcm.p, 0, (size_t)ps * 2, st));
     tick(7, true, st);
     CUDA_TRY(launch_hca_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
-                               max_frames, cfg, g_hca_tables.view, reinterpret_cast<double *>(misc + o_edge),
+                               max_frames, frames_total, cfg, g_hca_tables.view, reinterpret_cast<uint8_t *>(misc + o_parsed),
+                               reinterpret_cast<double *>(misc + o_edge),
                                static_cast<int16_t *>(g_ctx.pcm.p), reinterpret_cast<int32_t *>(misc + o_status), st));
     tick(7, false, st);
-    g_ctx.launches += 2;
+    g_ctx.launches += 3;
     std::vector<int32_t> status(n_streams, 0);
     CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
     VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));

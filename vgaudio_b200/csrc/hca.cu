@@ -575,7 +575,8 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
 // ==========================================================================================================
 // The only state the reference carries between frames is the IMDCT overlap buffer (Mdct.cs:114-117), and that is a
 // pure function of the previous subframe's DCT-IV output.  So decoding splits into two embarrassingly parallel
-// kernels: (A) one CTA per (stream, frame): parse the bitstream (one thread - prefix codes are serial), dequantise,
+// kernels: (P) one THREAD per frame parses the bitstream (prefix codes are serial inside a frame, frames are independent)
+// into a record of scale factors, resolutions and quantised coefficients; (A) one CTA per (stream, frame): dequantise,
 // rebuild the high band and intensity-stereo band, run the eight DCT-IV, window + overlap-add subframes 1..7, convert
 // to int16 and write the samples the container asks for (CopyPcmToOutput, CriHcaDecoder.cs:26-37); the two addends of
 // subframe 0 (2 KB per channel-frame) are parked in HBM; (B) one CTA per (stream, frame, channel) adds frame k's head
@@ -585,37 +586,6 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
 // with whatever the previous frame left in its buffers - state we deliberately do not carry).
 
 namespace {
-
-// BitReader.ReadInt / PeekInt (Utilities/BitReader.cs:51-99) over a frame held as big-endian 32-bit words: a 64-bit
-// window keeps the next bits left-aligned, so a read is a shift and a refill happens once per 32 consumed bits.
-// Bits past the end of the frame read as zero, like the reference.
-struct BitWindow {
-    const uint32_t *words;
-    int n_words, next;
-    uint64_t win;
-    uint32_t ahead;  // words[next], fetched when the previous refill happened: the load is off the bit chain
-    int avail;
-    __device__ uint32_t word(int i) const { return i < n_words ? words[i] : 0u; }
-    __device__ void open(const uint32_t *w, int n)
-    {
-        words = w; n_words = n;
-        win = ((uint64_t)word(0) << 32) | word(1);
-        avail = 64; next = 2;
-        ahead = word(2);
-    }
-    __device__ uint32_t peek(int count) const { return (uint32_t)((win >> 1) >> (63 - count)); }  // count 0..32
-    __device__ void skip(int count)
-    {
-        win <<= count;
-        avail -= count;
-        if (avail <= 32) {
-            win |= (uint64_t)ahead << (32 - avail);
-            avail += 32;
-            ahead = word(++next);
-        }
-    }
-    __device__ int read(int count) { const uint32_t v = peek(count); skip(count); return (int)v; }
-};
 
 // PcmFloatToShort (CriHcaDecoder.cs:168-181)
 __device__ __forceinline__ int16_t hca_pcm_float_to_short(double x)
@@ -627,39 +597,27 @@ __device__ __forceinline__ int16_t hca_pcm_float_to_short(double x)
 
 }  // namespace
 
-__global__ void __launch_bounds__(128)
-hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__restrict__ streams, HcaConfig cfg,
-                         HcaTables T, double *__restrict__ edge, int16_t *__restrict__ pcm,
-                         int32_t *__restrict__ status_out)
+// ---- parsed-frame record (HBM scratch between the two decoder kernels), per channel:
+//   [0,128) scale factors, [128,256) resolutions, [256,264) intensity, [264,272) HFR scales, [272, 272 + 2048) the
+//   8 x 128 quantised coefficients as int16
+constexpr int kRecScale = 0, kRecRes = 128, kRecIntensity = 256, kRecHfr = 264, kRecQuant = 272;
+constexpr int kRecChannelBytes = kRecQuant + kSub * kBins * 2;  // 2320
+constexpr int kParseThreads = 64;
+
+// CriHcaPacking.UnpackFrame (CriHcaPacking.cs:10-229), ONE THREAD PER FRAME.  Parsing a frame is inherently serial
+// (prefix codes), and a CTA-per-frame kernel that parks 127 threads behind one parser spent 90 % of its warp
+// instructions at 1/32 lane efficiency (ncu).  Frames are independent, so here the 32 lanes of a warp parse 32
+// different frames; the per-band code descriptors come from shared memory, everything on the bit chain is shifts.
+__global__ void __launch_bounds__(kParseThreads)
+hca_decode_parse_kernel(const uint8_t *__restrict__ frames, const HcaStream *__restrict__ streams, int n_streams,
+                        int64_t total_frames, HcaConfig cfg, HcaTables T, uint8_t *__restrict__ parsed,
+                        int32_t *__restrict__ status_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // prefix-code tables packed for the serial parser: for resolution < 8 the 16 (length, value) pairs of
-    // QuantizedSpectrumBits / QuantizedSpectrumValue as two 64-bit words (4 bits per code) - a code then costs two
-    // shifts instead of a dependent shared-memory lookup on the bit chain
     __shared__ unsigned long long s_lens64[16], s_vals64[16];
-    __shared__ uint8_t s_maxbits[16];
-    const int nch = cfg.channel_count;
-    double *spectra = reinterpret_cast<double *>(smem_raw);                   // [nch][8][128]
-    double *work = spectra + (size_t)nch * kSub * kBins;                      // [2][128]
-    int *quantized = reinterpret_cast<int *>(work + 2 * kBins);               // [nch][8][128]
-    HcaChannelState *chs = reinterpret_cast<HcaChannelState *>(quantized + (size_t)nch * kSub * kBins);
-    uint8_t *frame_buf = reinterpret_cast<uint8_t *>(chs + nch);
-
-    const int tid = threadIdx.x;
-    const int s = blockIdx.y, k = blockIdx.x;
-    const HcaStream st = streams[s];
-    if (k >= st.frame_count) return;
-
-    const uint8_t *src = frames + st.frames_off + (int64_t)k * cfg.frame_size;
-    uint32_t *words = reinterpret_cast<uint32_t *>(frame_buf);  // big-endian words, zero beyond the frame
-    const int n_words = (cfg.frame_size + 3) >> 2;
-    for (int w = tid; w < n_words; w += blockDim.x) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (4 * w + j < cfg.frame_size) v |= (uint32_t)src[4 * w + j] << (24 - 8 * j);
-        words[w] = v;
-    }
+    __shared__ uint8_t s_maxbits[16], s_curve[64];
+    uint8_t *sres = smem_raw;  // [nch][128][kParseThreads] resolutions of this thread's frame (thread fastest)
+    const int nch = cfg.channel_count, tid = threadIdx.x;
     if (tid < 16) {
         unsigned long long lens = 0, vals = 0;
         if (tid < 8)
@@ -671,95 +629,162 @@ hca_decode_unpack_kernel(const uint8_t *__restrict__ frames, const HcaStream *__
         s_vals64[tid] = vals;
         s_maxbits[tid] = T.quantized_max_bits[tid];
     }
-    if (tid < nch) {
-        chs[tid].type = cfg.channel_type[tid];
-        chs[tid].coded_count = cfg.channel_type[tid] == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
-    }
+    if (tid < 59) s_curve[tid] = T.scale_to_resolution[tid];
     __syncthreads();
 
-    // ---- UnpackFrame: serial bit parsing by one thread
-    if (tid == 0) {
-        BitWindow r;
-        r.open(words, n_words);
-        int status = 0;
-        if (r.read(16) != 0xffff) status = VGB_HCA_BAD_SYNC;
-        const int noise_level = r.read(9);
-        const int eval_boundary = r.read(7);
-        for (int c = 0; c < nch && !status; c++) {
-            HcaChannelState &ch = chs[c];
-            ch.delta_bits = r.read(3);  // ReadScaleFactors (:108-126)
-            if (ch.delta_bits == 0) {
-                for (int b = 0; b < kBins; b++) ch.scale_factors[b] = 0;
-            } else if (ch.delta_bits >= 6) {
-                for (int b = 0; b < ch.coded_count; b++) ch.scale_factors[b] = r.read(6);
-                for (int b = ch.coded_count; b < kBins; b++) ch.scale_factors[b] = 0;
-            } else {  // DeltaDecode (:183-208)
-                ch.scale_factors[0] = r.read(6);
-                const int max_delta = 1 << (ch.delta_bits - 1);
-                for (int b = 1; b < ch.coded_count; b++) {
-                    const int delta = r.read(ch.delta_bits) - (max_delta - 1);  // ReadOffsetBinary, OffsetBias.Positive
+    const int64_t fi = (int64_t)blockIdx.x * kParseThreads + tid;
+    if (fi >= total_frames) return;
+    int lo = 0, hi = n_streams - 1;  // the stream this frame belongs to: last one whose first frame index <= fi
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (streams[mid].dct_off <= fi) lo = mid; else hi = mid - 1;
+    }
+    const int s = lo;
+    const HcaStream st = streams[s];
+    const int64_t k = fi - st.dct_off;
+    const uint8_t *src = frames + st.frames_off + k * cfg.frame_size;
+    uint8_t *rec = parsed + fi * ((int64_t)nch * kRecChannelBytes);
+    const int frame_size = cfg.frame_size;
+
+    // BitReader.ReadInt / PeekInt (Utilities/BitReader.cs:51-99) over the frame's bytes in HBM: a 64-bit window keeps the
+    // next bits left-aligned, so a read is a shift; a refill happens once per 32 consumed bits from a word fetched at the
+    // previous refill; bits past the end of the frame read as zero, like the reference
+    auto word = [&](int i) -> uint32_t {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (4 * i + j < frame_size) v |= (uint32_t)__ldg(src + 4 * i + j) << (24 - 8 * j);
+        return v;
+    };
+    uint64_t win = ((uint64_t)word(0) << 32) | word(1);
+    int avail = 64, next = 2;
+    uint32_t ahead = word(2);
+    auto peek = [&](int count) -> uint32_t { return (uint32_t)((win >> 1) >> (63 - count)); };
+    auto skip = [&](int count) {
+        win <<= count;
+        avail -= count;
+        if (avail <= 32) {
+            win |= (uint64_t)ahead << (32 - avail);
+            avail += 32;
+            ahead = word(++next);
+        }
+    };
+    auto read = [&](int count) -> int { const uint32_t v = peek(count); skip(count); return (int)v; };
+
+    int status = 0;
+    if (read(16) != 0xffff) status = VGB_HCA_BAD_SYNC;
+    const int noise_level = read(9);
+    const int eval_boundary = read(7);
+    for (int c = 0; c < nch && !status; c++) {
+        uint8_t *rc = rec + (size_t)c * kRecChannelBytes;
+        const int type = cfg.channel_type[c];
+        const int coded = type == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
+        const int delta_bits = read(3);  // ReadScaleFactors (:108-126)
+        int prev = 0;
+        for (int b = 0; b < kBins; b++) {
+            int sf = 0;
+            if (b < coded && delta_bits != 0) {
+                if (delta_bits >= 6 || b == 0) {
+                    sf = read(6);
+                } else {  // DeltaDecode (:183-208)
+                    const int max_delta = 1 << (delta_bits - 1);
+                    const int delta = read(delta_bits) - (max_delta - 1);  // ReadOffsetBinary, OffsetBias.Positive
                     if (delta < max_delta) {
-                        const int value = ch.scale_factors[b - 1] + delta;
-                        if (value < 0 || value > 63) { status = VGB_HCA_BAD_DELTA; break; }
-                        ch.scale_factors[b] = value;
+                        sf = prev + delta;
+                        if (sf < 0 || sf > 63) { status = VGB_HCA_BAD_DELTA; sf = 0; }
                     } else {
-                        ch.scale_factors[b] = r.read(6);
+                        sf = read(6);
                     }
                 }
-                for (int b = ch.coded_count; b < kBins; b++) ch.scale_factors[b] = 0;
             }
-            if (status) break;
-            for (int b = 0; b < kBins; b++) {
-                int res = 0;
-                if (b < ch.coded_count)
-                    res = hca_resolution(T, ch.scale_factors[b], b < eval_boundary ? noise_level - 1 : noise_level);  // ATH curve unused
-                ch.resolution[b] = res;
+            prev = sf;
+            int res = 0;
+            if (b < coded && sf != 0) {  // CalculateResolution (CriHcaPacking.cs:60-69), ATH curve unused
+                int pos = (b < eval_boundary ? noise_level - 1 : noise_level) - 5 * sf / 2 + 2;
+                pos = min(max(pos, 0), 58);
+                res = s_curve[pos];
             }
-            if (ch.type == 2) {
-                for (int i = 0; i < kSub; i++) {
-                    ch.intensity[i] = r.read(4);
-                    if (ch.intensity[i] > 14) { status = VGB_HCA_BAD_INDEX; ch.intensity[i] = 14; }
-                }
-            } else if (cfg.hfr_group_count > 0) {
-                for (int i = 0; i < cfg.hfr_group_count; i++) ch.hfr_scales[i] = r.read(6);
-            }
+            rc[kRecScale + b] = (uint8_t)sf;
+            rc[kRecRes + b] = (uint8_t)res;
+            sres[((size_t)c * kBins + b) * kParseThreads + tid] = (uint8_t)res;
         }
-        if (!status) {
-            for (int sf = 0; sf < kSub; sf++)  // ReadSpectralCoefficients (:144-181)
-                for (int c = 0; c < nch; c++) {
-                    const HcaChannelState &ch = chs[c];
-                    int *q = quantized + ((size_t)c * kSub + sf) * kBins;
-                    const int n_coded = ch.coded_count;
-                    // the band's descriptor (max code length, packed tables) does not depend on the bit position:
-                    // it is fetched one band ahead so that only shifts sit on the serial chain
-                    int res = n_coded > 0 ? ch.resolution[0] : 0;
-                    int mbits = s_maxbits[res];
-                    unsigned long long lens = s_lens64[res], vals = s_vals64[res];
-                    for (int b = 0; b < n_coded; b++) {
-                        const int res_next = b + 1 < n_coded ? ch.resolution[b + 1] : 0;
-                        const int mbits_next = s_maxbits[res_next];
-                        const unsigned long long lens_next = s_lens64[res_next], vals_next = s_vals64[res_next];
-                        const int code = (int)r.peek(mbits);
-                        int v, bits;
-                        if (mbits <= 4) {  // resolution < 8: prefix code
-                            bits = (int)((lens >> (4 * code)) & 15u);
-                            v = (int)((unsigned)(vals >> (4 * code)) << 28) >> 28;  // signed nibble
-                        } else {           // sign-magnitude, the sign bit is absent for zero
-                            const int mag = code >> 1;
-                            v = (code & 1) ? -mag : mag;
-                            bits = mbits - (mag == 0 ? 1 : 0);
-                        }
-                        q[b] = v;
-                        r.skip(bits);
-                        res = res_next; mbits = mbits_next; lens = lens_next; vals = vals_next;
-                    }
-                }
-        } else {
-            atomicCAS(status_out + s, 0, status);
-            for (int e = 0; e < nch * kSub * kBins; e++) quantized[e] = 0;
-            for (int c = 0; c < nch; c++)
-                for (int b = 0; b < kBins; b++) { chs[c].scale_factors[b] = 0; chs[c].resolution[b] = 0; }
+        if (status) break;
+        for (int i = 0; i < 8; i++) { rc[kRecIntensity + i] = 0; rc[kRecHfr + i] = 0; }
+        if (type == 2) {
+            for (int i = 0; i < kSub; i++) {
+                int v = read(4);
+                if (v > 14) { status = VGB_HCA_BAD_INDEX; v = 14; }
+                rc[kRecIntensity + i] = (uint8_t)v;
+            }
+        } else if (cfg.hfr_group_count > 0) {
+            for (int i = 0; i < cfg.hfr_group_count; i++) rc[kRecHfr + i] = (uint8_t)read(6);
         }
+    }
+    if (!status) {
+        for (int sf = 0; sf < kSub; sf++)  // ReadSpectralCoefficients (:144-181)
+            for (int c = 0; c < nch; c++) {
+                const int type = cfg.channel_type[c];
+                const int coded = type == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
+                int16_t *q = reinterpret_cast<int16_t *>(rec + (size_t)c * kRecChannelBytes + kRecQuant) + sf * kBins;
+                const uint8_t *rb = sres + (size_t)c * kBins * kParseThreads + tid;
+                int res = coded > 0 ? rb[0] : 0;
+                for (int b = 0; b < coded; b++) {
+                    const int res_next = b + 1 < coded ? rb[(size_t)(b + 1) * kParseThreads] : 0;
+                    const int mbits = s_maxbits[res];
+                    const unsigned long long lens = s_lens64[res], vals = s_vals64[res];
+                    const int code = (int)peek(mbits);
+                    // both code families, selected without a branch (lanes parse different frames)
+                    const int bits_p = (int)((lens >> (4 * code)) & 15u);
+                    const int v_p = (int)((unsigned)(vals >> (4 * code)) << 28) >> 28;
+                    const int mag = code >> 1;
+                    const int v_s = (code & 1) ? -mag : mag;
+                    const int bits_s = mbits - (mag == 0 ? 1 : 0);
+                    const bool prefix = mbits <= 4;
+                    q[b] = (int16_t)(prefix ? v_p : v_s);
+                    skip(prefix ? bits_p : bits_s);
+                    res = res_next;
+                }
+                for (int b = coded; b < kBins; b++) q[b] = 0;
+            }
+    } else {
+        atomicCAS(status_out + s, 0, status);
+        for (int e = 0; e < nch * kRecChannelBytes; e++) rec[e] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+hca_decode_unpack_kernel(const uint8_t *__restrict__ parsed, const HcaStream *__restrict__ streams, HcaConfig cfg,
+                         HcaTables T, double *__restrict__ edge, int16_t *__restrict__ pcm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nch = cfg.channel_count;
+    double *spectra = reinterpret_cast<double *>(smem_raw);                   // [nch][8][128]
+    double *work = spectra + (size_t)nch * kSub * kBins;                      // [2][128]
+    int *quantized = reinterpret_cast<int *>(work + 2 * kBins);               // [nch][8][128]
+    HcaChannelState *chs = reinterpret_cast<HcaChannelState *>(quantized + (size_t)nch * kSub * kBins);
+
+    const int tid = threadIdx.x;
+    const int s = blockIdx.y, k = blockIdx.x;
+    const HcaStream st = streams[s];
+    if (k >= st.frame_count) return;
+
+    // ---- the frame as hca_decode_parse_kernel left it: scale factors, resolutions, side information, quantised
+    // coefficients (coalesced reads of the record)
+    const uint8_t *rec = parsed + ((int64_t)st.dct_off + k) * ((int64_t)nch * kRecChannelBytes);
+    for (int c = 0; c < nch; c++) {
+        const uint8_t *rc = rec + (size_t)c * kRecChannelBytes;
+        HcaChannelState &ch = chs[c];
+        if (tid == 0) {
+            ch.type = cfg.channel_type[c];
+            ch.coded_count = cfg.channel_type[c] == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
+        }
+        ch.scale_factors[tid] = rc[kRecScale + tid];
+        ch.resolution[tid] = rc[kRecRes + tid];
+        if (tid < kSub) { ch.intensity[tid] = rc[kRecIntensity + tid]; ch.hfr_scales[tid] = rc[kRecHfr + tid]; }
+        const int16_t *rq = reinterpret_cast<const int16_t *>(rc + kRecQuant);
+        int *q = quantized + (size_t)c * kSub * kBins;
+#pragma unroll
+        for (int j = 0; j < kSub; j++) q[j * kBins + tid] = rq[j * kBins + tid];
     }
     __syncthreads();
 
@@ -896,19 +921,32 @@ size_t hca_decode_smem_bytes(const HcaConfig &cfg)
 {
     const size_t nch = (size_t)cfg.channel_count;
     return nch * kSub * kBins * sizeof(double) + 2 * kBins * sizeof(double) + nch * kSub * kBins * sizeof(int) +
-           nch * sizeof(HcaChannelState) + (size_t)((cfg.frame_size + 15) & ~15) + 16;
+           nch * sizeof(HcaChannelState) + 16;
+}
+
+size_t hca_decode_parsed_bytes(const HcaConfig &cfg, int64_t total_frames)
+{
+    return (size_t)total_frames * (size_t)cfg.channel_count * kRecChannelBytes;
 }
 
 cudaError_t launch_hca_decode(const uint8_t *frames, const HcaStream *streams, int n_streams, int max_frames,
-                              const HcaConfig &cfg, const HcaTables &tables, double *edge_scratch, int16_t *pcm,
-                              int32_t *status_out, cudaStream_t stream)
+                              int64_t total_frames, const HcaConfig &cfg, const HcaTables &tables, uint8_t *parsed_scratch,
+                              double *edge_scratch, int16_t *pcm, int32_t *status_out, cudaStream_t stream)
 {
-    if (n_streams <= 0 || max_frames <= 0) return cudaSuccess;
+    if (n_streams <= 0 || max_frames <= 0 || total_frames <= 0) return cudaSuccess;
+    const size_t smem_p = (size_t)cfg.channel_count * kBins * kParseThreads;
+    cudaError_t e = cudaFuncSetAttribute(hca_decode_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks_p = (unsigned)((total_frames + kParseThreads - 1) / kParseThreads);
+    hca_decode_parse_kernel<<<blocks_p, kParseThreads, smem_p, stream>>>(frames, streams, n_streams, total_frames, cfg, tables,
+                                                                         parsed_scratch, status_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     const size_t smem = hca_decode_smem_bytes(cfg);
-    cudaError_t e = cudaFuncSetAttribute(hca_decode_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(hca_decode_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid_a((unsigned)max_frames, (unsigned)n_streams);
-    hca_decode_unpack_kernel<<<grid_a, 128, smem, stream>>>(frames, streams, cfg, tables, edge_scratch, pcm, status_out);
+    hca_decode_unpack_kernel<<<grid_a, 128, smem, stream>>>(parsed_scratch, streams, cfg, tables, edge_scratch, pcm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid_b((unsigned)max_frames, (unsigned)cfg.channel_count, (unsigned)n_streams);

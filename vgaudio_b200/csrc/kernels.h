@@ -41,8 +41,10 @@ cudaError_t launch_hca_encode(const int16_t *pcm, const HcaStream *streams, int 
 
 // CriHcaPacking.UnpackFrame + CriHcaDecoder.DecodeFrame (Codecs/CriHca/CriHcaDecoder.cs:62-192)
 size_t hca_decode_smem_bytes(const HcaConfig &cfg);
+size_t hca_decode_parsed_bytes(const HcaConfig &cfg, int64_t total_frames);  // scratch between the parse and frame kernels
 cudaError_t launch_hca_decode(const uint8_t *frames, const HcaStream *streams, int n_streams, int max_frames,
-                              const HcaConfig &cfg, const HcaTables &tables, double *edge_scratch, int16_t *pcm,
-                              int32_t *status_out, cudaStream_t stream);  // edge_scratch: 2*128 doubles per channel-frame
+                              int64_t total_frames, const HcaConfig &cfg, const HcaTables &tables, uint8_t *parsed_scratch,
+                              double *edge_scratch, int16_t *pcm, int32_t *status_out,
+                              cudaStream_t stream);  // edge_scratch: 2*128 doubles per channel-frame
 
 }  // namespace vgb
