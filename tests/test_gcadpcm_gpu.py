@@ -261,3 +261,42 @@ def test_uniform_slab_takes_the_time_sliced_pipeline(vg, oracle):
         co = oracle.calculate_coefficients(pcm[c])
         assert np.array_equal(coefs[c], co), c
         assert np.array_equal(adpcm[c], oracle.encode(pcm[c], co)), c
+
+
+@pytest.mark.parametrize("multiple,loop_start,loop_end", [(0x3800, 5000, 40000), (14336, 14336, 30000), (8, 1001, 9000),
+                                                           (100, 33, 50), (1024, 5, 70000)])
+def test_loop_alignment_matches_the_reference_composition(vg, oracle, multiple, loop_start, loop_end):
+    """GcAdpcmAlignment (GcAdpcmAlignment.cs:20-63): decode, rebuild the tail so that the loop start lands on a multiple,
+    re-encode it from the reconstructed history, decode again - checked against the same steps done with the oracle."""
+    n = 72000
+    pcm = [synth.channel(900 + c, n, degenerate=False) for c in range(3)]
+    coefs = [oracle.calculate_coefficients(x) for x in pcm]
+    adpcm = [oracle.encode(x, c) for x, c in zip(pcm, coefs)]
+    got = vg.formats.align_loops(adpcm, np.stack(coefs), multiple, loop_start, loop_end)
+    for c in range(3):
+        if loop_start % multiple == 0:
+            assert not got[c].alignment_needed
+            continue
+        aligned_start = loop_start + (multiple - loop_start % multiple)
+        count = loop_end + aligned_start - loop_start
+        keep_frames = loop_end // 14
+        keep = keep_frames * 14
+        to_encode = count - keep
+        old = oracle.decode(adpcm[c], coefs[c], loop_end)
+        want_pcm = np.zeros(count, np.int16)
+        want_pcm[:loop_end] = old
+        tail = np.zeros(to_encode, np.int16)
+        tail[:loop_end - keep] = old[keep:loop_end]
+        cur = loop_end - keep
+        while cur < to_encode:
+            k = min(loop_end - loop_start, to_encode - cur)
+            tail[cur:cur + k] = want_pcm[loop_start:loop_start + k]
+            cur += loop_end - loop_start
+        h1 = int(old[keep - 1]) if keep >= 1 else 0
+        h2 = int(old[keep - 2]) if keep >= 2 else 0
+        new_adpcm = oracle.encode(tail, coefs[c], to_encode, h1, h2)
+        want_adpcm = np.concatenate([adpcm[c][:keep_frames * 8], new_adpcm])
+        want_pcm[keep:keep + to_encode] = oracle.decode(new_adpcm, coefs[c], to_encode, h1, h2)
+        assert got[c].alignment_needed and got[c].loop_start_aligned == aligned_start and got[c].sample_count_aligned == count
+        assert np.array_equal(got[c].adpcm_aligned, want_adpcm), c
+        assert np.array_equal(got[c].pcm_aligned, want_pcm), c
