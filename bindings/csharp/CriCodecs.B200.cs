@@ -34,6 +34,13 @@ namespace VGAudio.Native
     {
         private const string Lib = "vgaudio_b200";
 
+        // InterleaveExtensions.Interleave / DeInterleave for byte payloads (Utilities/Interleave.cs:9-41, :81-117)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int vgb_interleave(byte** inputs, int count, int inSize, int interleaveSize, int outSize, byte* output);
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int vgb_deinterleave(byte* input, int length, int interleaveSize, int count, int outSize, byte** outputs);
+
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         public static extern int vgb_adx_encoded_byte_count(int pcmLength, int padding, int frameSize);
 

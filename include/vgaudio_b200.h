@@ -156,9 +156,29 @@ int32_t vgb_gcadpcm_seek_context_batch(const uint8_t *const *adpcm, const int32_
                                        const vgb_gc_tap_params *params, int32_t n_channels,
                                        int16_t *const *seek_table_out, int16_t *loop_context_out);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Block (de)interleave of channel payloads: InterleaveExtensions.Interleave / DeInterleave
+ * (Utilities/Interleave.cs:9-166), the byte shuffle the container writers / readers run next to the codec path
+ * (AdxWriter.cs:131, BrstmWriter.cs:294, WaveReader.cs:47 ...).  Blocks of interleave_size bytes per channel, a shorter
+ * last block on either side, only min(in, out) blocks / bytes copied, the rest of the output zero; out_size == -1
+ * means in_size.  The _dev entry points work on n_items payloads resident in HBM (strides in bytes), which is how the
+ * shuffle fuses behind an encode; the host entry points handle one payload like the reference calls.
+ * ------------------------------------------------------------------------------------------------------- */
+int32_t vgb_interleave_dev(const void *d_in, int64_t in_channel_stride, int64_t in_item_stride, void *d_out, int64_t out_item_stride,
+                           int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, void *cuda_stream);
+int32_t vgb_deinterleave_dev(const void *d_in, int64_t in_item_stride, void *d_out, int64_t out_channel_stride, int64_t out_item_stride,
+                             int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, void *cuda_stream);
+/* inputs[count] of in_size bytes -> output of out_size * count bytes (T[] Interleave<T>(this T[][] inputs, ...), :9-41) */
+int32_t vgb_interleave(const uint8_t *const *inputs, int32_t count, int32_t in_size, int32_t interleave_size, int32_t out_size,
+                       uint8_t *output);
+/* input of `length` bytes -> outputs[count] of out_size bytes (T[][] DeInterleave<T>(this T[] input, ...), :81-117);
+ * VGB_E_ARG when length is not divisible by count (ArgumentOutOfRangeException) */
+int32_t vgb_deinterleave(const uint8_t *input, int32_t length, int32_t interleave_size, int32_t count, int32_t out_size,
+                         uint8_t *const *outputs);
+
 /* Per-kernel device time (ms, CUDA events on the launching stream) of the most recent *_dev or host call on this
  * thread's workspace: [0] GC coefficient phase 1, [1] GC coefficient refinement, [2] GC encode, [3] GC decode,
- * [4] ADX encode, [5] ADX decode, [6] HCA encode, [7] HCA decode (both kernels).  Only filled when
+ * [4] ADX encode, [5] ADX decode, [6] HCA encode, [7] HCA decode (all kernels), [8] interleave, [9] deinterleave.  Only filled when
  * vgb_set_kernel_timing(1) was called; bench.py / tools/secondary_bench.py use it for the roofline objects. */
 int32_t vgb_set_kernel_timing(int32_t enabled);
 int32_t vgb_last_kernel_ms(float *ms_out, int32_t n);

@@ -223,6 +223,32 @@ def gc_loop_context(adpcm, pcm, loop_start):
     return int(out[0]) & 0xFF, int(out[1]), int(out[2])
 
 
+def interleave(inputs, interleave_size, output_size=-1) -> np.ndarray:
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8).ravel() for a in inputs]
+    count, in_size = len(arrs), arrs[0].size
+    out_size = in_size if output_size == -1 else output_size
+    out = np.zeros(out_size * count, dtype=np.uint8)
+    tab = (C.c_void_p * count)(*[a.ctypes.data for a in arrs])
+    L = lib()
+    L.vgo_interleave.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.vgo_interleave(tab, count, in_size, interleave_size, out_size, out.ctypes.data)
+    return out
+
+
+def deinterleave(data, interleave_size, output_count, output_size=-1):
+    data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    in_size = data.size // output_count
+    out_size = in_size if output_size == -1 else output_size
+    outs = [np.zeros(out_size, dtype=np.uint8) for _ in range(output_count)]
+    tab = (C.c_void_p * output_count)(*[o.ctypes.data for o in outs])
+    L = lib()
+    L.vgo_deinterleave.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.vgo_deinterleave.restype = C.c_int
+    if L.vgo_deinterleave(data.ctypes.data, data.size, interleave_size, output_count, out_size, tab) != 0:
+        raise ValueError("The input array length must be divisible by the number of outputs.")
+    return outs
+
+
 def hca_params(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None) -> HcaParams:
     """loop = (loop_start, loop_end) in samples or None (Pcm16Format.Looping / LoopStart / LoopEnd)."""
     looping, ls, le = (1, int(loop[0]), int(loop[1])) if loop else (0, 0, 0)

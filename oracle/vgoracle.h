@@ -110,6 +110,10 @@ void vgo_hca_imdct_run(const double *spectra, int n, double *blocks_out);       
 void vgo_hca_mdct_tables(double *sin_out, double *cos_out, int *shuffle_out, int bits); /* :183-208 */
 uint16_t vgo_crc16(const uint8_t *data, int size);                               /* Crc16.Compute, poly 0x8005 */
 
+/* ---- Utilities/Interleave.cs:9-41, :81-117 (bytes) ---- */
+int vgo_interleave(const uint8_t *const *inputs, int count, int in_size, int interleave_size, int out_size, uint8_t *output);
+int vgo_deinterleave(const uint8_t *input, int length, int interleave_size, int count, int out_size, uint8_t *const *outputs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ import vgaudio_b200 as vg  # noqa: E402
 from vgaudio_b200 import _native as N  # noqa: E402
 from vgaudio_b200 import synth  # noqa: E402
 
-SLOT = {"gc_decode": 3, "adx_encode": 4, "adx_decode": 5, "hca_encode": 6, "hca_decode": 7}
+SLOT = {"gc_decode": 3, "adx_encode": 4, "adx_decode": 5, "hca_encode": 6, "hca_decode": 7, "interleave": 8, "deinterleave": 9}
 
 
 def peak_gbs():
@@ -37,12 +37,12 @@ def peak_gbs():
 def timed(fn, slot, reps=3):
     fn()
     best, kms = None, None
-    buf = (C.c_float * 8)()
+    buf = (C.c_float * 10)()
     for _ in range(reps):
         t0 = time.perf_counter()
         fn()
         dt = time.perf_counter() - t0
-        N.check(vg.lib.vgb_last_kernel_ms(buf, 8))
+        N.check(vg.lib.vgb_last_kernel_ms(buf, 10))
         if best is None or dt < best:
             best, kms = dt, float(buf[slot])
     return best, kms
@@ -63,7 +63,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=0.25)
     ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--only", default="gcdec,adx,hca")
+    ap.add_argument("--only", default="gcdec,adx,hca,interleave")
     a = ap.parse_args()
     only = set(a.only.split(","))
     N.check(vg.lib.vgb_set_kernel_timing(1))
@@ -107,6 +107,35 @@ def main():
         infos2, frames2 = vg.crihca.encode_batch(streams2, 48000)
         fbytes2 = sum(f.size for f in frames2)
         out["hca_encode_stereo_high"] = entry(n_st // 2 * 2 * n, dt, kms, n_st // 2 * 2 * n * 2 + fbytes2, {"streams": n_st // 2})
+    if "interleave" in only:  # device-resident block interleave of .dsp-like payloads (0x2000-byte blocks, 2 channels)
+        import torch
+        items, count, interleave = max(64, int(8192 * a.scale)), 2, 0x2000
+        in_size = gc_bytes = ((n + 13) // 14) * 8
+        out_size = -(-in_size // interleave) * interleave  # the writers pad the last block
+        src = torch.randint(0, 256, (items, count, in_size), dtype=torch.uint8, device="cuda")
+        dst = torch.zeros((items, count * out_size), dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def run_i():
+            N.check(vg.lib.vgb_interleave_dev(src.data_ptr(), in_size, count * in_size, dst.data_ptr(), count * out_size, items, count,
+                                              in_size, interleave, out_size, stream))
+            torch.cuda.synchronize()
+        dt, kms = timed(run_i, SLOT["interleave"])
+        e = entry(items * count * in_size, dt, kms, items * count * (in_size + out_size), {"items": items, "channels": count, "interleave": interleave})
+        e["unit_note"] = "Msamples_per_s fields count BYTES here"
+        out["interleave_dev"] = e
+        back = torch.zeros((items, count, in_size), dtype=torch.uint8, device="cuda")
+
+        def run_d():
+            N.check(vg.lib.vgb_deinterleave_dev(dst.data_ptr(), count * out_size, back.data_ptr(), in_size, count * in_size, items, count,
+                                                out_size, interleave, in_size, stream))
+            torch.cuda.synchronize()
+        dt, kms = timed(run_d, SLOT["deinterleave"])
+        e = entry(items * count * in_size, dt, kms, items * count * (in_size + out_size), {"items": items, "channels": count, "interleave": interleave})
+        e["unit_note"] = "Msamples_per_s fields count BYTES here"
+        e["round_trip_equal"] = bool(torch.equal(back, src))
+        out["deinterleave_dev"] = e
+        del gc_bytes
     print(json.dumps(out))
 
 

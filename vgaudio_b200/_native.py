@@ -102,6 +102,12 @@ SIGNATURES = {
     "vgb_hca_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_gcadpcm_seek_entry_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "vgb_gcadpcm_seek_context_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vgb_interleave_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                       C.c_int32, C.c_int64, C.c_void_p]),
+    "vgb_deinterleave_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                         C.c_int32, C.c_int64, C.c_void_p]),
+    "vgb_interleave": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vgb_deinterleave": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vgb_set_kernel_timing": (C.c_int32, [C.c_int32]),
     "vgb_last_kernel_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -85,7 +85,7 @@ struct DevBuf {
     }
 };
 
-constexpr int kTimers = 8;  // 0 coef phase 1, 1 coef refine, 2 gc encode, 3 gc decode, 4 adx encode, 5 adx decode, 6 hca encode, 7 hca decode
+constexpr int kTimers = 10;  // 0 coef phase 1, 1 coef refine, 2 gc encode, 3 gc decode, 4 adx encode, 5 adx decode, 6 hca encode, 7 hca decode, 8 interleave, 9 deinterleave
 constexpr int kMaxGroups = 4;  // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
 
 struct Context {
@@ -1656,6 +1656,108 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
         if (status[s] == VGB_HCA_BAD_DELTA) return fail(VGB_E_DATA, "stream %d: scale factor delta out of range", s);
         if (status[s] == VGB_HCA_BAD_INDEX) return fail(VGB_E_DATA, "stream %d: intensity index out of range", s);
     }
+    return VGB_OK;
+}
+
+// ---- block (de)interleave (Utilities/Interleave.cs:9-166) ---------------------------------------------------------
+namespace {
+int32_t interleave_check(int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size)
+{
+    if (n_items < 0 || count <= 0) return fail(VGB_E_ARG, "bad item / channel count");
+    if (interleave_size <= 0) return fail(VGB_E_ARG, "interleave size must be positive");
+    if (in_size < 0 || out_size < 0) return fail(VGB_E_ARG, "negative size");
+    return VGB_OK;
+}
+}  // namespace
+
+int32_t vgb_interleave_dev(const void *d_in, int64_t in_channel_stride, int64_t in_item_stride, void *d_out, int64_t out_item_stride,
+                           int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, void *cuda_stream)
+{
+    if (out_size == -1) out_size = in_size;
+    VGB_TRY(interleave_check(n_items, count, in_size, interleave_size, out_size));
+    if (n_items == 0 || out_size == 0) return VGB_OK;
+    if (!d_in || !d_out) return fail(VGB_E_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    tick(8, true, st);
+    CUDA_TRY(launch_interleave(d_in, in_channel_stride, in_item_stride, d_out, out_item_stride, n_items, count, in_size, interleave_size,
+                               out_size, st));
+    tick(8, false, st);
+    g_ctx.launches += 1;
+    return VGB_OK;
+}
+
+int32_t vgb_deinterleave_dev(const void *d_in, int64_t in_item_stride, void *d_out, int64_t out_channel_stride, int64_t out_item_stride,
+                             int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, void *cuda_stream)
+{
+    if (out_size == -1) out_size = in_size;
+    VGB_TRY(interleave_check(n_items, count, in_size, interleave_size, out_size));
+    if (n_items == 0 || out_size == 0) return VGB_OK;
+    if (!d_in || !d_out) return fail(VGB_E_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    tick(9, true, st);
+    CUDA_TRY(launch_deinterleave(d_in, in_item_stride, d_out, out_channel_stride, out_item_stride, n_items, count, in_size,
+                                 interleave_size, out_size, st));
+    tick(9, false, st);
+    g_ctx.launches += 1;
+    return VGB_OK;
+}
+
+int32_t vgb_interleave(const uint8_t *const *inputs, int32_t count, int32_t in_size, int32_t interleave_size, int32_t out_size,
+                       uint8_t *output)
+{
+    if (out_size == -1) out_size = in_size;
+    VGB_TRY(interleave_check(1, count, in_size, interleave_size, out_size));
+    if (out_size == 0) return VGB_OK;
+    if (!inputs || !output) return fail(VGB_E_ARG, "NULL argument");
+    for (int c = 0; c < count; c++)
+        if (!inputs[c] && in_size > 0) return fail(VGB_E_ARG, "inputs[%d] is NULL", c);
+    const int64_t pitch = (int64_t)align_up((size_t)in_size, 16), out_bytes = (int64_t)out_size * count;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx.mu);
+        VGB_TRY(ensure_ready_locked());
+        VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
+        VGB_TRY(g_ctx.adpcm.reserve((size_t)out_bytes + 16));
+        for (int c = 0; c < count; c++)
+            if (in_size > 0)
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(g_ctx.pcm.p) + c * pitch, inputs[c], (size_t)in_size, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    VGB_TRY(vgb_interleave_dev(g_ctx.pcm.p, pitch, 0, g_ctx.adpcm.p, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    CUDA_TRY(cudaMemcpyAsync(output, g_ctx.adpcm.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    return VGB_OK;
+}
+
+int32_t vgb_deinterleave(const uint8_t *input, int32_t length, int32_t interleave_size, int32_t count, int32_t out_size,
+                         uint8_t *const *outputs)
+{
+    if (count <= 0) return fail(VGB_E_ARG, "bad channel count");
+    if (length < 0 || length % count != 0)  // ArgumentOutOfRangeException (Interleave.cs:84-86)
+        return fail(VGB_E_ARG, "The input array length (%d) must be divisible by the number of outputs.", length);
+    const int32_t in_size = length / count;
+    if (out_size == -1) out_size = in_size;
+    VGB_TRY(interleave_check(1, count, in_size, interleave_size, out_size));
+    if (out_size == 0) return VGB_OK;
+    if ((!input && length > 0) || !outputs) return fail(VGB_E_ARG, "NULL argument");
+    for (int c = 0; c < count; c++)
+        if (!outputs[c]) return fail(VGB_E_ARG, "outputs[%d] is NULL", c);
+    const int64_t pitch = (int64_t)align_up((size_t)out_size, 16);
+    {
+        std::lock_guard<std::mutex> lock(g_ctx.mu);
+        VGB_TRY(ensure_ready_locked());
+        VGB_TRY(g_ctx.adpcm.reserve((size_t)length + 16));
+        VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
+        if (length > 0) CUDA_TRY(cudaMemcpyAsync(g_ctx.adpcm.p, input, (size_t)length, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    VGB_TRY(vgb_deinterleave_dev(g_ctx.adpcm.p, 0, g_ctx.pcm.p, pitch, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    for (int c = 0; c < count; c++)
+        CUDA_TRY(cudaMemcpyAsync(outputs[c], static_cast<char *>(g_ctx.pcm.p) + c * pitch, (size_t)out_size, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
     return VGB_OK;
 }
 

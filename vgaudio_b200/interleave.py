@@ -1,0 +1,34 @@
+"""Host-side mirror of VGAudio.Utilities.InterleaveExtensions (Utilities/Interleave.cs:9-166) for byte payloads over the
+C ABI: the block (de)interleave the container writers / readers run next to the codec path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+def interleave(inputs: Sequence[np.ndarray], interleave_size: int, output_size: int = -1) -> np.ndarray:
+    """T[] Interleave<T>(this T[][] inputs, int interleaveSize, int outputSize = -1) for bytes."""
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8).ravel() for a in inputs]
+    if len({a.size for a in arrs}) > 1:
+        raise ValueError("Inputs must be of equal length")  # ArgumentOutOfRangeException (:15-16)
+    count, in_size = len(arrs), arrs[0].size
+    out_size = in_size if output_size == -1 else output_size
+    out = np.zeros(out_size * count, dtype=np.uint8)
+    tab = (C.c_void_p * count)(*[a.ctypes.data for a in arrs])
+    N.check(N.lib.vgb_interleave(tab, count, in_size, interleave_size, out_size, out.ctypes.data))
+    return out
+
+
+def deinterleave(data: np.ndarray, interleave_size: int, output_count: int, output_size: int = -1) -> List[np.ndarray]:
+    """T[][] DeInterleave<T>(this T[] input, int interleaveSize, int outputCount, int outputSize = -1) for bytes."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    in_size = data.size // max(output_count, 1)
+    out_size = in_size if output_size == -1 else output_size
+    outs = [np.zeros(out_size, dtype=np.uint8) for _ in range(output_count)]
+    tab = (C.c_void_p * max(output_count, 1))(*[o.ctypes.data for o in outs])
+    N.check(N.lib.vgb_deinterleave(data.ctypes.data, data.size, interleave_size, output_count, out_size, tab))
+    return outs
