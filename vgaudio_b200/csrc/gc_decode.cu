@@ -31,6 +31,14 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
+// a*b + c as ONE multiply-add the compiler may not re-associate (it otherwise moves the nibble term onto the chain)
+__device__ __forceinline__ int32_t dec_imad(int32_t a, int32_t b, int32_t c)
+{
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 struct DecState {
     int32_t hb1, hb2;  // biased history (+32768): newest, older
 };
@@ -39,22 +47,24 @@ struct DecState {
 __device__ __forceinline__ void gc_decode_frame(uint32_t w0, uint32_t w1, const uint32_t *coef_pairs, DecState &st, uint32_t *out)
 {
     const uint32_t head = w0 & 0xFFu;
-    const int sp = (int)(head & 0xFu);
-    const int32_t scale = (int32_t)((1u << sp) * 2048u);
+    const int sp = (int)(head & 0xFu);  // scale = (1 << sp) * 2048 (GcAdpcmDecoder.cs:28)
     // a hostile header may select pairs 8..15: the reference would throw; we wrap to stay in bounds
     const uint32_t pair = coef_pairs[(head >> 4) & 7u];
     const int32_t c1 = (int32_t)(int16_t)(pair & 0xFFFFu), c2 = (int32_t)pair >> 16;
-    const int32_t k = wsub(1024, wmul(32768, wadd(c1, c2)));  // rounding constant minus the bias of both histories
+    int32_t k = wsub(1024, wmul(32768, wadd(c1, c2)));  // rounding constant minus the bias of both histories
+    asm("" : "+r"(k));                                    // one register, not a multiply re-derived for every sample
+    const int down = 17 - sp;                                   // nibble at bit 28 -> nibble * 2^(sp + 11)
     int32_t hb1 = st.hb1, hb2 = st.hb2;
 #pragma unroll
     for (int s = 0; s < 14; s++) {
         const int byte = 1 + s / 2;
         const uint32_t word = byte < 4 ? w0 : w1;
         const int lo_bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);                 // position of the nibble's lowest bit
-        const int32_t q = (int32_t)(word << (28 - lo_bit)) >> 28;              // Helpers.GetHighNibbleSigned/Low (:50-56)
-        const int32_t t = wadd(wmul(c2, hb2), wadd(wmul(scale, q), k));        // off the chain
-        const int32_t v = wadd(wmul(c1, hb1), t);                              // chain: IMAD
-        const int32_t ob = __viaddmin_s32_relu(v >> 11, 32768, 65535);         // chain: SHF, VIADDMNMX.RELU
+        // Helpers.GetHighNibbleSigned/Low (:50-56) times the scale in two shifts: |nibble * scale| <= 2^29, exact
+        const int32_t sq = (int32_t)(word << (28 - lo_bit)) >> down;
+        const int32_t t = dec_imad(c2, hb2, wadd(sq, k));                      // off the chain
+        const int32_t v = dec_imad(c1, hb1, t);                                // chain: IMAD
+        const int32_t ob = __viaddmin_s32_relu(v >> 11, 32768, 65535);         // chain: shift+bias, clamp
         hb2 = hb1;
         hb1 = ob;
         if (s & 1) out[s / 2] |= (uint32_t)ob << 16; else out[s / 2] = (uint32_t)ob;
