@@ -53,16 +53,15 @@ __device__ __forceinline__ void gc_decode_frame(uint32_t w0, uint32_t w1, const 
     const int32_t c1 = (int32_t)(int16_t)(pair & 0xFFFFu), c2 = (int32_t)pair >> 16;
     int32_t k = wsub(1024, wmul(32768, wadd(c1, c2)));  // rounding constant minus the bias of both histories
     asm("" : "+r"(k));                                    // one register, not a multiply re-derived for every sample
-    const int down = 17 - sp;                                   // nibble at bit 28 -> nibble * 2^(sp + 11)
+    const int32_t scale = (int32_t)((1u << sp) * 2048u);
     int32_t hb1 = st.hb1, hb2 = st.hb2;
 #pragma unroll
     for (int s = 0; s < 14; s++) {
         const int byte = 1 + s / 2;
         const uint32_t word = byte < 4 ? w0 : w1;
         const int lo_bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);                 // position of the nibble's lowest bit
-        // Helpers.GetHighNibbleSigned/Low (:50-56) times the scale in two shifts: |nibble * scale| <= 2^29, exact
-        const int32_t sq = (int32_t)(word << (28 - lo_bit)) >> down;
-        const int32_t t = dec_imad(c2, hb2, wadd(sq, k));                      // off the chain
+        const int32_t q = (int32_t)(word << (28 - lo_bit)) >> 28;              // Helpers.GetHighNibbleSigned/Low (:50-56)
+        const int32_t t = dec_imad(c2, hb2, dec_imad(q, scale, k));            // off the chain
         const int32_t v = dec_imad(c1, hb1, t);                                // chain: IMAD
         const int32_t ob = __viaddmin_s32_relu(v >> 11, 32768, 65535);         // chain: shift+bias, clamp
         hb2 = hb1;
