@@ -11,6 +11,8 @@
 // (encoder, four 16-byte chunks) or 8 frames' 144 bytes (decoder, nine chunks) into the thread's own shared-memory ring
 // two steps ahead, results leave as halfword / 16-byte stores straight from registers (partial sectors merge in L2), so
 // DRAM latency never reaches the recurrence.  Other frame sizes / padded streams / a partial last frame take the general loop.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,6 +39,14 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// a*b + c as ONE multiply-add the compiler may not re-associate
+__device__ __forceinline__ int32_t adx_imad(int32_t a, int32_t b, int32_t c)
+{
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 __global__ void __launch_bounds__(kAdxThreads)
@@ -260,19 +270,40 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
                 }
                 int32_t scale = (int16_t)(((b0 << 8) | b1) & 0x1FFF);
                 scale = (int16_t)(c.type == 4 ? (1 << ((12 - scale) & 31)) : scale + 1);
+                // history kept with a +32768 bias (hb = h + 32768) so that Clamp16 is one VIMNMX.RELU; the bias is folded
+                // into per-frame constants (sums wrap like the reference's int32), the multiply-adds are pinned so that
+                // only IMAD -> shift(+add) -> clamp sits on the chain
+                const int32_t bias0 = wmul(-32768, c0), bias1 = wmul(-32768, c1);
+                int32_t hb1 = hist1 + 32768, hb2 = hist2 + 32768;
                 uint32_t o[16];
+                // the version test is hoisted: two copies of the 32-sample loop instead of predicating both variants
+                auto samples = [&](auto is_v4) {
 #pragma unroll
-                for (int s2 = 0; s2 < 32; s2++) {
-                    const int byte = base + 2 + (s2 >> 1);
-                    const int lo_bit = (byte & 3) * 8 + ((s2 & 1) ? 0 : 4);
-                    int32_t sample = (int32_t)(w[byte >> 2] << (28 - lo_bit)) >> 28;
-                    if (v4) sample = wadd(wmul(scale, sample), wadd(wmul(hist1, c0), wmul(hist2, c1)) >> 12);
-                    else sample = wadd(wadd(wmul(scale, sample), wmul(hist1, c0) >> 12), wmul(hist2, c1) >> 12);
-                    const int32_t out = clamp16(sample);
-                    hist2 = hist1;
-                    hist1 = out;
-                    if (s2 & 1) o[s2 >> 1] |= (uint32_t)out << 16; else o[s2 >> 1] = (uint32_t)out & 0xFFFFu;
-                }
+                    for (int s2 = 0; s2 < 32; s2++) {
+                        const int byte = base + 2 + (s2 >> 1);
+                        const int lo_bit = (byte & 3) * 8 + ((s2 & 1) ? 0 : 4);
+                        const int32_t q = (int32_t)(w[byte >> 2] << (28 - lo_bit)) >> 28;
+                        const int32_t sq = adx_imad(scale, q, 32768);                         // off the chain
+                        int32_t biased;                                                        // sample + 32768
+                        if (decltype(is_v4)::value) {
+                            const int32_t t = adx_imad(c1, hb2, wadd(bias0, bias1));          // off the chain
+                            biased = wadd(adx_imad(c0, hb1, t) >> 12, sq);
+                        } else {
+                            const int32_t t = wadd(adx_imad(c1, hb2, bias1) >> 12, sq);       // off the chain
+                            biased = wadd(adx_imad(c0, hb1, bias0) >> 12, t);
+                        }
+                        const int32_t ob = __viaddmin_s32_relu(biased, 0, 65535);              // clamp16(sample) + 32768
+                        hb2 = hb1;
+                        hb1 = ob;
+                        if (s2 & 1) o[s2 >> 1] |= (uint32_t)ob << 16; else o[s2 >> 1] = (uint32_t)ob;
+                    }
+                };
+                if (v4) samples(std::true_type{}); else samples(std::false_type{});
+#pragma unroll
+                for (int j = 0; j < 16; j++) o[j] ^= 0x80008000u;
+                hist1 = hb1 - 32768;
+                hist2 = hb2 - 32768;
+
                 uint4 *vout = reinterpret_cast<uint4 *>(dst + ((int64_t)g * kAdxDecGroup + fr) * 32);  // pcm_off % 8 == 0
 #pragma unroll
                 for (int j = 0; j < 4; j++) vout[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
