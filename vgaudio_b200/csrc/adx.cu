@@ -126,23 +126,29 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
             uint16_t *out16 = reinterpret_cast<uint16_t *>(dst + (int64_t)f * 18);  // adpcm_off is even
             const uint32_t hdr0 = ((uint32_t)(scale_out >> 8) & 0x1fu) | (c.type == 2 ? (uint32_t)(c.filter << 5) : 0u);
             out16[0] = (uint16_t)((hdr0 & 0xFFu) | (((uint32_t)scale_out & 0xFFu) << 8));  // :140-141
-            uint32_t hw = 0;
+            // pass 2 (:122-138); the version test is hoisted (two copies of the loop instead of predicating both).
+            // Clamp16(scale * q) (:131) is the identity here: scale <= 0x1000 (:151-163) and q in [-8, 7] give a product
+            // in [-32768, 28672], so it is left out of the dependent chain.
+            auto pass2 = [&](auto is_v4) {
+                uint32_t hw = 0;
 #pragma unroll
-            for (int i = 0; i < 32; i++) {  // pass 2 (:122-138)
-                int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
-                const int32_t raw = x[i] - predicted;
-                const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
-                const int32_t q = adx_short_to_nibble(scaled);
-                const int32_t decoded_distance = clamp16(wmul(scale, q));
-                if (v4) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
-                const int32_t recon = clamp16(decoded_distance + predicted);
-                h2 = h1;
-                h1 = recon;
-                // byte = (q_even << 4) | q_odd; halfword = byte0 | byte1 << 8
-                const int sh = ((i & 1) ? 0 : 4) + ((i & 2) ? 8 : 0);
-                hw |= ((uint32_t)q & 0xFu) << sh;
-                if ((i & 3) == 3) { out16[1 + (i >> 2)] = (uint16_t)hw; hw = 0; }
-            }
+                for (int i = 0; i < 32; i++) {
+                    int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
+                    const int32_t raw = x[i] - predicted;
+                    const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
+                    const int32_t q = adx_short_to_nibble(scaled);
+                    const int32_t decoded_distance = wmul(scale, q);
+                    if (decltype(is_v4)::value) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
+                    const int32_t recon = clamp16(decoded_distance + predicted);
+                    h2 = h1;
+                    h1 = recon;
+                    // byte = (q_even << 4) | q_odd; halfword = byte0 | byte1 << 8
+                    const int sh = ((i & 1) ? 0 : 4) + ((i & 2) ? 8 : 0);
+                    hw |= ((uint32_t)q & 0xFu) << sh;
+                    if ((i & 3) == 3) { out16[1 + (i >> 2)] = (uint16_t)hw; hw = 0; }
+                }
+            };
+            if (v4) pass2(std::true_type{}); else pass2(std::false_type{});
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         f_first = whole;
