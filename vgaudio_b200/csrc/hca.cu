@@ -67,15 +67,17 @@ __device__ __forceinline__ int hca_coef_bits(const HcaTables &T, int resolution,
 }
 
 struct BlockSum {  // integer sum over the 128 threads of the CTA, result in every thread
-    int *scratch;  // 4 ints of shared memory
-    __device__ int operator()(int v) const
+    int *scratch;  // 2 x 4 ints of shared memory, used alternately: ONE barrier per sum (a warp can be at most one call
+    int parity;    // ahead of the slowest reader, and that call writes the other half)
+    __device__ int operator()(int v)
     {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        int *mine = scratch + 4 * parity;
+        parity ^= 1;
+        if ((threadIdx.x & 31) == 0) mine[threadIdx.x >> 5] = v;
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-        __syncthreads();
-        return scratch[0] + scratch[1] + scratch[2] + scratch[3];
+        return mine[0] + mine[1] + mine[2] + mine[3];
     }
 };
 
@@ -135,7 +137,7 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
     const HcaStream st = streams[s];
     const int k = blockIdx.x;  // frame index
     if (k >= st.frame_count) return;
-    const BlockSum block_sum{red};
+    BlockSum block_sum{red, 0};
 
     // ---- channel set-up (CriHcaFrame ctor :18-33)
     if (tid < nch) {
