@@ -29,7 +29,7 @@ def launches(path, out_md, command):
     ours = OrderedDict()
     other = 0.0
     for name, ms, grid in rows:
-        head = name.split("(")[0]
+        head = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").split("(")[0]
         if "vgb::" in head or head.startswith(("gc_", "adx_", "hca_")):
             short = head.split("vgb::")[-1].split("<")[0]
             ours.setdefault((short, grid), []).append(ms)
