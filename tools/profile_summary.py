@@ -31,7 +31,7 @@ def launches(path, out_md, command):
     for name, ms, grid in rows:
         head = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").split("(")[0]
         if "vgb::" in head or head.startswith(("gc_", "adx_", "hca_")):
-            short = head.split("vgb::")[-1].split("<")[0]
+            short = head.split("vgb::")[1].split("<")[0] if "vgb::" in head else head.split("<")[0]
             ours.setdefault((short, grid), []).append(ms)
         else:
             other += ms
