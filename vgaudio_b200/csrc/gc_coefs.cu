@@ -344,14 +344,16 @@ __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames,
             }
             pick = d[0] < 1.0e30 ? idx[0] : 0;  // nothing below the initial 1.0e30: the index stays 0
         }
-        uint32_t mine = 0;
-#pragma unroll
-        for (int k = 0; k < NB; k++) {
-            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok && pick == k);
-            mine = pick == k ? bits : mine;
-            if (lane == k) slot.count[k] = __popc(bits);
+        // lanes that picked the same bucket find each other with ONE match instead of a ballot per bucket; records that
+        // were not accepted form their own group (key NB) and are not queued
+        if (lane < NB) slot.count[lane] = 0;
+        const uint32_t mine = __match_any_sync(0xFFFFFFFFu, ok ? pick : NB);
+        __syncwarp();
+        if (ok) {
+            const int rank = __popc(mine & lanes_below);
+            if (rank == 0) slot.count[pick] = __popc(mine);  // the group's first lane publishes its size
+            slot.q[pick][rank] = r;
         }
-        if (ok) slot.q[pick][__popc(mine & lanes_below)] = r;
         __syncwarp();
         {   // pad every queue to a multiple of four entries with -0.0 (lane = bucket * 4 + i)
             const int bucket = lane >> 2, i = lane & 3;
