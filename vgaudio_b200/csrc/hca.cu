@@ -325,7 +325,29 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
     };
     header_lengths();
 
-    // ---- CalculateUsedBits (:554-597): integer sum over channels x bands x subframes -> block reduction
+    // ---- CalculateUsedBits (:554-597): integer sum over channels x bands x subframes -> block reduction.  The two
+    // searches below probe it ~17 times with different (noise level, boundary); what changes between probes is only
+    // the RESOLUTION of a band, so the cost of a band's eight coefficients is tabulated once for all 16 resolutions
+    // (the same hca_coef_bits arithmetic) and a probe is one table read per band.
+    uint8_t *band_bits = reinterpret_cast<uint8_t *>(red + 8);  // [nch][128][16], sums <= 8 * 12
+    for (int c = 0; c < nch; c++) {
+        const int b = tid;
+        double x[kSub];
+#pragma unroll
+        for (int sf = 0; sf < kSub; sf++) x[sf] = scaled[((size_t)c * kBins + b) * kSub + sf];
+        uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int res = 0; res < 16; res++) {
+            int w = 0;
+            if (b < chs[c].coded_count) {
+#pragma unroll
+                for (int sf = 0; sf < kSub; sf++) w += hca_coef_bits(T, res, x[sf]);
+            }
+            packed[res >> 2] |= (uint32_t)w << ((res & 3) * 8);
+        }
+        *reinterpret_cast<uint4 *>(band_bits + ((size_t)c * kBins + b) * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    __syncthreads();
     auto used_bits = [&](int noise_level, int eval_boundary) -> int {
         int mine = 0;
         for (int c = 0; c < nch; c++) {
@@ -333,8 +355,7 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
             if (b < chs[c].coded_count) {
                 const int noise = b < eval_boundary ? noise_level - 1 : noise_level;
                 const int resolution = hca_resolution(T, chs[c].scale_factors[b], noise);
-#pragma unroll
-                for (int sf = 0; sf < kSub; sf++) mine += hca_coef_bits(T, resolution, scaled[((size_t)c * kBins + b) * kSub + sf]);
+                mine += band_bits[((size_t)c * kBins + b) * 16 + resolution];
             }
             if (tid == 0) mine += chs[c].header_bits;
         }
@@ -960,7 +981,7 @@ size_t hca_encode_smem_bytes(const HcaConfig &cfg)
 {
     const size_t nch = (size_t)cfg.channel_count;
     return 2 * nch * kSub * kBins * sizeof(double) + 4 * kBins * sizeof(double) + nch * sizeof(HcaChannelState) +
-           (size_t)((cfg.frame_size + 15) & ~15) + 8 * sizeof(int) + 16;
+           (size_t)((cfg.frame_size + 15) & ~15) + 8 * sizeof(int) + nch * kBins * 16 + 16;
 }
 
 cudaError_t launch_hca_encode(const int16_t *pcm, const HcaStream *streams, int n_streams, int max_frames,
