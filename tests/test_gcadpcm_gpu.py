@@ -300,3 +300,17 @@ def test_loop_alignment_matches_the_reference_composition(vg, oracle, multiple, 
         assert got[c].alignment_needed and got[c].loop_start_aligned == aligned_start and got[c].sample_count_aligned == count
         assert np.array_equal(got[c].adpcm_aligned, want_adpcm), c
         assert np.array_equal(got[c].pcm_aligned, want_pcm), c
+
+
+def test_shutdown_releases_everything_and_the_next_call_reinitialises(vg, oracle):
+    """vgb_shutdown frees the device slabs, streams, events and the HCA table blob; the next call brings all of it back."""
+    x = synth.channel(21, 5000)
+    co = oracle.calculate_coefficients(x)
+    want = oracle.encode(x, co)
+    info0, frames0 = vg.crihca.encode([x], 48000)
+    for _ in range(2):
+        assert vg.lib.vgb_shutdown() == 0
+        coefs, adpcm = vg.gcadpcm.encode_batch([x])
+        assert np.array_equal(coefs[0], co) and np.array_equal(adpcm[0], want)
+        info1, frames1 = vg.crihca.encode([x], 48000)
+        assert np.array_equal(frames0, frames1)

@@ -106,6 +106,8 @@ struct Context {
 
 Context g_ctx;
 
+void hca_tables_release_locked();  // defined next to the HCA table store
+
 int32_t ensure_ready_locked()
 {
     if (g_ctx.ready) {
@@ -702,7 +704,15 @@ int32_t vgb_shutdown(void)
         cudaEventDestroy(g_ctx.ev_in[g]);
         cudaEventDestroy(g_ctx.ev_done[g]);
         cudaEventDestroy(g_ctx.ev_out[g]);
+        cudaEventDestroy(g_ctx.ev_mid[g]);
     }
+    for (auto &ev : g_ctx.ev_slice) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    if (g_ctx.ev_t0) cudaEventDestroy(g_ctx.ev_t0);
+    g_ctx.ev_t0 = nullptr;
+    hca_tables_release_locked();
     g_ctx.ready = false;
     return VGB_OK;
 }
@@ -1399,6 +1409,13 @@ struct HcaTableStore {
     void *blob = nullptr;
     HcaTables view{};
 } g_hca_tables;
+
+void hca_tables_release_locked()
+{
+    if (g_hca_tables.blob) cudaFree(g_hca_tables.blob);
+    g_hca_tables.blob = nullptr;
+    g_hca_tables.ready = false;
+}
 
 int32_t hca_tables_ready_locked()
 {
