@@ -77,3 +77,39 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in text and "vgoracle" not in text and "libvgoracle" not in text, f
+
+
+# ---- host logic that needs no device: CriHcaEncoder.Initialize (CriHcaEncoder.cs:61-114) in the library vs the oracle --------
+
+@pytest.mark.parametrize("nch", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_hca_query_matches_the_oracle_over_a_parameter_grid(vg, oracle, nch):
+    import ctypes as C
+    from vgaudio_b200 import _native as N
+    checked = 0
+    for rate in (8000, 22050, 32000, 44100, 48000, 96000):
+        for quality in (0, 1, 2, 3, 4, 5):
+            for bitrate, limit in ((0, False), (0, True), (64000 * nch, False), (24000, True)):
+                for n, loop in ((48000, None), (100000, (5000, 90000)), (2049, (2048, 2049)), (30000, (0, 30000)), (1, None)):
+                    p = N.VgbHcaParams(quality, bitrate, int(limit), nch, rate, n, 1 if loop else 0, loop[0] if loop else 0,
+                                       loop[1] if loop else 0)
+                    info = N.VgbHcaInfo()
+                    rc = vg.lib.vgb_hca_query(C.byref(p), C.byref(info))
+                    op = oracle.HcaParams(quality, bitrate, int(limit), nch, rate, n, 1 if loop else 0, loop[0] if loop else 0,
+                                          loop[1] if loop else 0)
+                    try:
+                        want = oracle.hca_init(op)
+                    except ValueError:
+                        assert rc != 0
+                        continue
+                    if want.frame_size < 8:  # "Bitrate is set too low." is raised by the library at query time
+                        assert rc != 0
+                        continue
+                    assert rc == 0, (rate, quality, bitrate, limit, n, loop)
+                    assert info.as_dict() == want.as_dict(), (rate, quality, bitrate, limit, n, loop)
+                    checked += 1
+    assert checked > 300
+
+
+def test_seek_entry_count_helper(vg):
+    f = vg.lib.vgb_gcadpcm_seek_entry_count
+    assert [f(n, spe) for n, spe in ((0, 100), (1, 100), (100, 100), (101, 100), (14336 * 3 + 1, 14336), (50, 0))] == [0, 1, 1, 2, 4, 0]

@@ -1306,7 +1306,9 @@ int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h, HcaVirtual *vir
     {
         const int bitrate = h.bitrate;
         int cutoff = cutoff0;
-        h.frame_size = (int)((int64_t)bitrate * 1024 / h.sample_rate / 8);
+        // `bitrate * 1024 / SampleRate / 8` in C# int arithmetic (CriHcaEncoder.cs:322): the product wraps above 2^31
+        // (e.g. 6 channels x 96 kHz at Highest); the reference then ends with a negative frame size and fails
+        h.frame_size = wmul(bitrate, 1024) / h.sample_rate / 8;
         int hfr_ratio, cutoff_ratio;
         if (h.channel_count <= 1 || pcm_bitrate / bitrate <= 6) { hfr_ratio = 6; cutoff_ratio = 12; }
         else { hfr_ratio = 8; cutoff_ratio = 16; }
@@ -1325,7 +1327,8 @@ int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h, HcaVirtual *vir
         h.hfr_group_count = groups;
         h.bands_per_hfr_group = per_group;
     }
-    if (h.frame_size < 8) return fail(VGB_E_DATA, "Bitrate is set too low.");
+    if (h.frame_size < 8)
+        return fail(VGB_E_DATA, h.frame_size < 0 ? "frame size overflows (bitrate * 1024 exceeds int32, as in the reference)" : "Bitrate is set too low.");
     if (h.bands_per_hfr_group > 0) {
         h.hfr_band_count = h.total_band_count - h.base_band_count - h.stereo_band_count;
         h.hfr_group_count = hca_div_up(h.hfr_band_count, h.bands_per_hfr_group);
