@@ -42,6 +42,9 @@ namespace VGAudio.Native
         public static extern int vgb_deinterleave(byte* input, int length, int interleaveSize, int count, int outSize, byte** outputs);
 
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        public static extern int vgb_adx_calculate_coefficients(int highpassFrequency, int sampleRate, short* coefsOut);
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         public static extern int vgb_adx_encoded_byte_count(int pcmLength, int padding, int frameSize);
 
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]

@@ -211,6 +211,10 @@ typedef struct vgb_adx_params {
     int32_t filter;              /* Fixed only: 0..3 */
 } vgb_adx_params;
 
+/* CriAdxCodec.CalculateCoefficients(highpassFreq, sampleRate) (CriAdxCodec.cs:173-184): the two Q12 prediction
+ * coefficients of the Linear / Exponential types.  Pure host arithmetic (doubles, truncating casts). */
+int32_t vgb_adx_calculate_coefficients(int32_t highpass_frequency, int32_t sample_rate, int16_t *coefs_out);
+
 /* frameCount * FrameSize of CriAdxCodec.Encode (CriAdxCodec.cs:59-61,67) */
 int32_t vgb_adx_encoded_byte_count(int32_t pcm_length, int32_t padding, int32_t frame_size);
 

@@ -113,3 +113,18 @@ def test_hca_query_matches_the_oracle_over_a_parameter_grid(vg, oracle, nch):
 def test_seek_entry_count_helper(vg):
     f = vg.lib.vgb_gcadpcm_seek_entry_count
     assert [f(n, spe) for n, spe in ((0, 100), (1, 100), (100, 100), (101, 100), (14336 * 3 + 1, 14336), (50, 0))] == [0, 1, 1, 2, 4, 0]
+
+
+def test_adx_host_helpers_match_the_oracle(vg, oracle):
+    """CriAdxCodec.CalculateCoefficients and the encoded size formula: host arithmetic, no device needed."""
+    import numpy as np
+    out = np.zeros(2, dtype=np.int16)
+    for rate in list(range(4000, 200001, 997)) + [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 88200, 96000, 192000]:
+        for hp in (0, 1, 100, 500, 1000, rate // 4):
+            assert vg.lib.vgb_adx_calculate_coefficients(hp, rate, out.ctypes.data) == 0
+            assert out.tolist() == oracle.adx_coefficients(hp, rate).tolist(), (hp, rate)
+    L = oracle.lib()
+    for n in (0, 1, 31, 32, 33, 1000, 123457):
+        for padding in (0, 1, 31, 32, 100):
+            for fs in (18, 34, 6):
+                assert vg.lib.vgb_adx_encoded_byte_count(n, padding, fs) == L.vgo_adx_encoded_byte_count(n, padding, fs), (n, padding, fs)

@@ -1135,6 +1135,14 @@ const int16_t kAdxFixed[4][2] = {{0, 0}, {0x0F00, 0}, {0x1CC0, (int16_t)0xF300},
 
 extern "C" {
 
+int32_t vgb_adx_calculate_coefficients(int32_t highpass_frequency, int32_t sample_rate, int16_t *coefs_out)
+{
+    if (!coefs_out) return fail(VGB_E_ARG, "coefs_out is NULL");
+    if (sample_rate <= 0) return fail(VGB_E_ARG, "sample rate must be positive");
+    adx_calc_coefs(highpass_frequency, sample_rate, coefs_out[0], coefs_out[1]);
+    return VGB_OK;
+}
+
 int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
                              int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out, vgb_progress_cb cb,
                              void *user)
