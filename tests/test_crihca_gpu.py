@@ -15,7 +15,7 @@ def _streams(n_streams, nch, n, first=100):
     return [[synth.channel(first + s * nch + c, n, degenerate=False) for c in range(nch)] for s in range(n_streams)]
 
 
-@pytest.mark.parametrize("nch,quality", [(1, 2), (2, 2), (1, 1), (2, 5), (1, 5), (2, 3), (3, 4), (6, 2), (8, 5)])
+@pytest.mark.parametrize("nch,quality", [(1, 2), (2, 2), (1, 1), (2, 5), (1, 5), (2, 3), (3, 4), (6, 2), (8, 5), (4, 2), (5, 3), (7, 2), (4, 5), (7, 5)])
 def test_frames_byte_identical_to_oracle(vg, oracle, nch, quality):
     n = 20000
     streams = _streams(3, nch, n)
@@ -80,7 +80,7 @@ def test_errors(vg):
 
 # ---- decoder: CUDA PCM (vgb_hca_decode_batch) against the oracle's CriHcaDecoder restatement, bit-exact int16 --------
 
-@pytest.mark.parametrize("nch,quality", [(1, 2), (2, 2), (1, 1), (2, 5), (1, 5), (2, 3), (3, 4), (6, 2), (8, 5)])
+@pytest.mark.parametrize("nch,quality", [(1, 2), (2, 2), (1, 1), (2, 5), (1, 5), (2, 3), (3, 4), (6, 2), (8, 5), (4, 2), (5, 3), (7, 2), (4, 5), (7, 5)])
 def test_decode_bit_exact_with_oracle(vg, oracle, nch, quality):
     streams = _streams(3, nch, 20000, first=300)
     infos, frames = vg.crihca.encode_batch(streams, 48000, vg.crihca.CriHcaParameters(quality=quality))
