@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgoracle.so")
+LIB_PATH = os.environ.get("VGORACLE_LIB") or os.path.join(_HERE, "libvgoracle.so")  # VGORACLE_LIB: e.g. the `make asan` build
 
 
 def build(force: bool = False) -> str:
