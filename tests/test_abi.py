@@ -128,3 +128,20 @@ def test_adx_host_helpers_match_the_oracle(vg, oracle):
         for padding in (0, 1, 31, 32, 100):
             for fs in (18, 34, 6):
                 assert vg.lib.vgb_adx_encoded_byte_count(n, padding, fs) == L.vgo_adx_encoded_byte_count(n, padding, fs), (n, padding, fs)
+
+
+def test_gc_math_helpers_equal_the_oracle_on_a_dense_range(vg, oracle):
+    """GcAdpcmMath (GcAdpcmMath.cs:7-47): the library's host helpers against the oracle's restatement for every argument in a
+    dense range (the oracle itself is pinned to the reference's KAT tables in test_oracle_gcadpcm.py)."""
+    L = oracle.lib()
+    pairs = [("vgb_gcadpcm_sample_count_to_byte_count", "vgo_gc_sample_count_to_byte_count"),
+             ("vgb_gcadpcm_byte_count_to_sample_count", "vgo_gc_byte_count_to_sample_count"),
+             ("vgb_gcadpcm_sample_count_to_nibble_count", "vgo_gc_sample_count_to_nibble_count"),
+             ("vgb_gcadpcm_nibble_count_to_sample_count", "vgo_gc_nibble_count_to_sample_count"),
+             ("vgb_gcadpcm_sample_to_nibble", "vgo_gc_sample_to_nibble"),
+             ("vgb_gcadpcm_nibble_to_sample", "vgo_gc_nibble_to_sample")]
+    values = list(range(0, 3000)) + [10 ** 6 + k for k in range(40)] + [2 ** 30 + k for k in range(20)]
+    for ours, theirs in pairs:
+        f, g = getattr(vg.lib, ours), getattr(L, theirs)
+        for v in values:
+            assert f(v) == g(v), (ours, v)
