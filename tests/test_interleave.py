@@ -62,3 +62,18 @@ def test_gpu_deinterleave_errors(vg):
         vg.interleave.deinterleave(np.zeros(7, np.uint8), 2, 2)
     with pytest.raises(ValueError):
         vg.interleave.interleave([np.zeros(4, np.uint8), np.zeros(5, np.uint8)], 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("count,n,extra", [(1, 1000, 0), (2, 48000, 0), (6, 777, 0), (2, 100, 3), (8, 1, 0)])
+def test_gpu_wav_sample_interleave_round_trip(vg, count, n, extra):
+    """ShortToInterleavedByte / InterleavedByteToShort (Interleave.cs:170-208) as 2-byte block (de)interleaves."""
+    rng = np.random.default_rng(5)
+    chans = [rng.integers(-32768, 32768, n, dtype=np.int16) for _ in range(count)]
+    data = vg.interleave.short_to_interleaved_byte(chans)
+    want = np.stack(chans, axis=1).astype("<i2").tobytes()  # sample-major, little-endian
+    assert data.tobytes() == want
+    padded = np.concatenate([data, np.zeros(extra, np.uint8)])
+    back = vg.interleave.interleaved_byte_to_short(padded, count)
+    for c in range(count):
+        assert np.array_equal(back[c], chans[c])

@@ -32,3 +32,20 @@ def deinterleave(data: np.ndarray, interleave_size: int, output_count: int, outp
     tab = (C.c_void_p * max(output_count, 1))(*[o.ctypes.data for o in outs])
     N.check(N.lib.vgb_deinterleave(data.ctypes.data, data.size, interleave_size, output_count, out_size, tab))
     return outs
+
+
+def short_to_interleaved_byte(channels: Sequence[np.ndarray]) -> np.ndarray:
+    """byte[] ShortToInterleavedByte(this short[][] input) (Interleave.cs:170-187): the WAV writer's sample interleave -
+    little-endian 16-bit samples, i.e. a 2-byte block interleave of the channels' bytes."""
+    arrs = [np.ascontiguousarray(c, dtype="<i2") for c in channels]
+    return interleave([a.view(np.uint8) for a in arrs], 2)
+
+
+def interleaved_byte_to_short(data: np.ndarray, output_count: int) -> List[np.ndarray]:
+    """short[][] InterleavedByteToShort(this byte[] input, int outputCount) (Interleave.cs:189-208): the WAV reader's
+    front end (WaveReader.cs:47-51).  Trailing bytes that do not fill a sample of every channel are ignored, as in
+    the reference (itemCount = input.Length / 2 / outputCount)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    items = data.size // 2 // output_count
+    outs = deinterleave(data[: items * 2 * output_count], 2, output_count)
+    return [o.view("<i2").astype(np.int16) for o in outs]
