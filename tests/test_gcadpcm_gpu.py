@@ -248,15 +248,24 @@ def test_seek_context_without_table_and_errors(vg, oracle):
         vg.gcadpcm.seek_table_and_loop_context([a], c.reshape(1, 16), [5000], 0, [5001])
 
 
-def test_uniform_slab_takes_the_time_sliced_pipeline(vg, oracle):
-    """64+ equally long channels handed over as one slab go through the time-sliced host pipeline (encode cut into frame
-    ranges with the history carried between launches, D2H of a slice overlapping the next slice): same bytes as the
-    oracle, progress deltas summing to the frame total (GcAdpcmFormat.cs:62)."""
+@pytest.mark.parametrize("groups", [1, 3, 16])
+def test_host_pipeline_over_channel_groups(vg, oracle, groups):
+    """The host call pipelines channel groups (H2D of group g+1 under the kernels of group g, D2H of group g-1): same
+    bytes as the oracle for any group count, progress deltas (one per group) summing to the frame total
+    (GcAdpcmFormat.cs:62).  VGB_ENCODE_GROUPS forces the group count."""
     n_ch, n = 72, 14 * 1100 + 9  # 1101 frames, partial last frame
     pcm = np.stack([synth.channel(800 + c, n, degenerate=False) for c in range(n_ch)])
     seen = []
-    coefs, adpcm = vg.gcadpcm.encode_batch(pcm, progress=seen.append)
-    assert sum(seen) == n_ch * 1101 and len(seen) > 1
+    saved = os.environ.get("VGB_ENCODE_GROUPS")
+    os.environ["VGB_ENCODE_GROUPS"] = str(groups)
+    try:
+        coefs, adpcm = vg.gcadpcm.encode_batch(pcm, progress=seen.append)
+    finally:
+        if saved is None:
+            os.environ.pop("VGB_ENCODE_GROUPS", None)
+        else:
+            os.environ["VGB_ENCODE_GROUPS"] = saved
+    assert sum(seen) == n_ch * 1101 and len(seen) == groups
     for c in range(0, n_ch, 7):
         co = oracle.calculate_coefficients(pcm[c])
         assert np.array_equal(coefs[c], co), c

@@ -5,6 +5,7 @@
 // No codec arithmetic happens on the CPU here; without a CUDA device every codec entry point fails (VGB_E_CUDA).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cmath>
@@ -86,22 +87,23 @@ struct DevBuf {
 };
 
 constexpr int kTimers = 10;  // 0 coef phase 1, 1 coef refine, 2 gc encode, 3 gc decode, 4 adx encode, 5 adx decode, 6 hca encode, 7 hca decode, 8 interleave, 9 deinterleave
-constexpr int kMaxGroups = 4;  // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
+constexpr int kMaxGroups = 16;   // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
+constexpr int kCompStreams = 4;  // kernel streams the groups rotate over
 
 struct Context {
     std::mutex mu;
     bool ready = false;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[kMaxGroups] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[kCompStreams] = {};
     cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_out[kMaxGroups] = {}, ev_mid[kMaxGroups] = {}, ev_t0 = nullptr;
     int last_groups = 0;
-    cudaEvent_t ev_slice[16] = {};   // encode time slices of the uniform-batch pipeline
     DevBuf pcm, adpcm, coefs, ws, misc;
     bool timing = false;
     cudaEvent_t ev[2 * kTimers] = {};
     bool ev_used[kTimers] = {};
     std::atomic<int64_t> launches{0};
+    GcSegArgs last_seg{};            // bookkeeping of the most recent encode launch (vgb_gcadpcm_debug_splice_stats)
 };
 
 Context g_ctx;
@@ -126,15 +128,14 @@ int32_t ensure_ready_locked()
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_out, cudaStreamNonBlocking));
+    for (int g = 0; g < kCompStreams; g++) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_comp[g], cudaStreamNonBlocking));
     for (int g = 0; g < kMaxGroups; g++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.s_comp[g], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_in[g]));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_done[g]));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_out[g]));
         CUDA_TRY(cudaEventCreate(&g_ctx.ev_mid[g]));
     }
     CUDA_TRY(cudaEventCreate(&g_ctx.ev_t0));
-    for (auto &ev : g_ctx.ev_slice) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : g_ctx.ev) CUDA_TRY(cudaEventCreate(&ev));
     g_ctx.ready = true;
     return VGB_OK;
@@ -165,6 +166,7 @@ struct GcLayout {
 // Workspace carve-up (every region 256-byte aligned).  [0, table_bytes) is the host-built table blob.
 struct GcWorkspace {
     size_t off_pcm_off, off_adpcm_off, off_rec_off, off_n_samples, off_enc_count, off_hist, off_records, off_mask;
+    size_t off_trace, off_used_start, off_stats;  // time-parallel encode bookkeeping (GcSegArgs)
     size_t table_bytes;
     size_t total;
 };
@@ -184,6 +186,9 @@ GcWorkspace carve(int64_t rec_total_frames, int32_t n_channels)
     w.table_bytes = o;
     w.off_records = take((size_t)rec_total_frames * sizeof(double2));
     w.off_mask = take((size_t)(rec_total_frames / 32 + 1) * 4);
+    w.off_trace = take((size_t)rec_total_frames * 4);
+    w.off_used_start = take(n * kGcMaxSegments * 4);
+    w.off_stats = take(64);
     w.total = o;
     return w;
 }
@@ -203,6 +208,17 @@ GcChannelTable table_view(void *ws, const GcWorkspace &w, int32_t n_channels)
     t.hist = reinterpret_cast<int16_t *>(b + w.off_hist);
     t.n_channels = n_channels;
     return t;
+}
+
+GcSegArgs seg_view(void *ws, const GcWorkspace &w, int32_t seg_count)
+{
+    char *b = static_cast<char *>(ws);
+    GcSegArgs a;
+    a.trace = reinterpret_cast<uint32_t *>(b + w.off_trace);
+    a.used_start = reinterpret_cast<uint32_t *>(b + w.off_used_start);
+    a.stats = reinterpret_cast<unsigned long long *>(b + w.off_stats);
+    a.seg_count = seg_count;
+    return a;
 }
 
 int32_t upload_tables(const GcLayout &lay, const GcWorkspace &w, void *ws, cudaStream_t stream)
@@ -276,6 +292,13 @@ void layout_pack_offsets(GcLayout &lay)
     lay.adpcm_total = ab + 16;
 }
 
+int max_encode_frames(const GcLayout &lay)
+{
+    int32_t m = 0;
+    for (int c = 0; c < lay.n_channels; c++) m = std::max(m, div_round_up(lay.enc_count[c], kGcFrameSamples));
+    return m;
+}
+
 // Kernel sequence of one encode call on `stream` (device pointers only).
 int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *d_coefs_in, int16_t *d_coefs_out,
                       uint8_t *d_adpcm, void *d_ws, const GcWorkspace &w, cudaStream_t stream, bool do_encode,
@@ -304,10 +327,13 @@ int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *
     }
     if (after_coefs) CUDA_TRY(cudaEventRecord(after_coefs, stream));
     if (do_encode) {
+        const int enc_frames = max_encode_frames(lay);
+        const GcSegArgs seg = seg_view(d_ws, w, gc_encode_pick_segments(lay.n_channels, enc_frames));
         tick(2, true, stream);
-        launch_gc_encode(d_pcm, tab, d_coefs_out, d_adpcm, lay.max_frames, 0, INT_MAX, stream);
+        launch_gc_encode(d_pcm, tab, d_coefs_out, d_adpcm, lay.max_frames, 0, INT_MAX, seg, stream);
         tick(2, false, stream);
-        g_ctx.launches += lay.max_frames > 0 ? 1 : 0;
+        g_ctx.launches += lay.max_frames > 0 ? (seg.seg_count > 1 ? 3 : 1) : 0;
+        g_ctx.last_seg = seg;
     }
     CUDA_TRY(cudaGetLastError());
     return VGB_OK;
@@ -382,7 +408,7 @@ int32_t copy_channels_in(char *d_base, const std::vector<int64_t> &d_off_bytes, 
     bool same = true;
     for (int c = 1; c < n; c++) same = same && bytes[c] == bytes[0];
     int64_t hstride = 0;
-    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride)) {
+    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride) && hstride >= bytes[0]) {  // overlapping rows: per-channel copies
         const int64_t dstride = d_off_bytes[1] - d_off_bytes[0];
         bool dsame = true;
         for (int c = 2; c < n; c++) dsame = dsame && (d_off_bytes[c] - d_off_bytes[c - 1] == dstride);
@@ -410,7 +436,7 @@ int32_t copy_channels_out(T *const *h_ptr, const char *d_base, const std::vector
     bool same = true;
     for (int c = 1; c < n; c++) same = same && bytes[c] == bytes[0];
     int64_t hstride = 0;
-    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride)) {
+    if (same && n > 1 && bytes[0] > 0 && uniform_stride(h_ptr, n, hstride) && hstride >= bytes[0]) {
         const int64_t dstride = d_off_bytes[1] - d_off_bytes[0];
         bool dsame = true;
         for (int c = 2; c < n; c++) dsame = dsame && (d_off_bytes[c] - d_off_bytes[c - 1] == dstride);
@@ -450,9 +476,9 @@ GcLayout sub_layout(const GcLayout &full, int c0, int c1)
     return g;
 }
 
-// One host call, pipelined over three kinds of streams (input copies, kernels, output copies).  A uniform batch is cut
-// in TIME (see below); otherwise up to kMaxGroups channel groups: the H2D copy of group g+1, the kernels of group g and
-// the D2H copy of group g-1 overlap (channels are independent; a channel's coefficients need all of its samples).
+// One host call, pipelined over three kinds of streams (input copies, kernels, output copies) in up to kMaxGroups
+// channel groups: the H2D copy of group g+1, the kernels of group g and the D2H copy of group g-1 overlap (channels
+// are independent; a channel's coefficients need all of its samples).
 int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
                          const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out, uint8_t *const *adpcm_out,
                          vgb_progress_cb cb, void *user, bool do_encode)
@@ -470,103 +496,18 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     }
     layout_pack_offsets(lay);
 
-    // ---- uniform batch (every channel the same length, the caller's buffers one slab each): TIME-sliced pipeline.
-    // Pipelining over channel groups overlaps copies with kernels, but the kernels of different groups then share the
-    // SMs and the latency-bound encoder of one group is slowed by the issue-hungry coefficient kernels of the next
-    // (measured: 4 groups 160 ms vs 155 ms with no overlap at all).  For a uniform batch the ENCODE is cut in time
-    // instead - every slice is the same channels, a later frame range, history carried in the table - so nothing
-    // runs beside the coefficient kernels and each slice's D2H overlaps the next slice's encode.
+    // channel groups with roughly equal sample totals (boundaries on channel indices, order preserved).  The encoder is
+    // throughput bound since it runs time-parallel (gc_encode.cu), so kernels of neighbouring groups share the SMs
+    // without slowing each other: the PCIe copy of group g+1 hides the kernels of group g.
+    int n_groups = 1;
     {
-        int64_t in_stride = 0, out_stride = 0;
-        bool uniform = do_encode && n_channels >= 64 && !coefs_in && uniform_stride(pcm, n_channels, in_stride) &&
-                       uniform_stride(adpcm_out, n_channels, out_stride);
-        for (int c = 1; c < n_channels && uniform; c++)
-            uniform = lay.n_samples[c] == lay.n_samples[0] && lay.enc_count[c] == lay.enc_count[0];
-        if (std::getenv("VGB_ENCODE_GROUPS")) uniform = false;  // tuning knob forces the channel-group pipeline
-        const int frames = uniform ? div_round_up(lay.enc_count[0], kGcFrameSamples) : 0;
-        if (uniform && frames >= 16 * 64) {
-            std::lock_guard<std::mutex> lock(g_ctx.mu);
-            VGB_TRY(ensure_ready_locked());
-            const GcWorkspace w = carve(lay.rec_total, n_channels);
-            VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
-            VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
-            VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
-            VGB_TRY(g_ctx.ws.reserve(w.total));
-            CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
-            int16_t *d_coefs = static_cast<int16_t *>(g_ctx.coefs.p);
-            cudaStream_t st = g_ctx.s_comp[0];
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_t0, g_ctx.s_in));
-            g_ctx.last_groups = 1;
-            VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, g_ctx.s_in));
-            const int64_t d_in_pitch = (lay.pcm_off[1] - lay.pcm_off[0]) * 2, d_out_pitch = lay.adpcm_off[1] - lay.adpcm_off[0];
-            // H2D in 4 time slices (2-D copies: the same sample range of every channel), the per-frame record kernel of a
-            // slice running under the next slice's copy; then the refinement, alone on the device
-            GcChannelTable tab = table_view(g_ctx.ws.p, w, n_channels);
-            {
-                char *ws_b = static_cast<char *>(g_ctx.ws.p);
-                double2 *records = reinterpret_cast<double2 *>(ws_b + w.off_records);
-                uint32_t *mask = reinterpret_cast<uint32_t *>(ws_b + w.off_mask);
-                const int in_slices = 4;
-                const int n_all = lay.n_samples[0];
-                const int a_frames = div_round_up(n_all, kGcFrameSamples);
-                const int per_in = (div_round_up(a_frames, in_slices) + 255) / 256 * 256;  // whole record-kernel tiles
-                for (int k = 0; k < in_slices; k++) {
-                    const int f0 = k * per_in, f1 = std::min(a_frames, (k + 1) * per_in);
-                    if (f0 >= f1) break;
-                    const int64_t s0 = (int64_t)f0 * kGcFrameSamples, s1 = std::min((int64_t)f1 * kGcFrameSamples, (int64_t)n_all);
-                    if (k == 0) try_pin(pcm[0], (size_t)(in_stride * (n_channels - 1) + (int64_t)n_all * 2));
-                    CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g_ctx.pcm.p) + (lay.pcm_off[0] + s0) * 2, (size_t)d_in_pitch,
-                                               reinterpret_cast<const char *>(pcm[0]) + s0 * 2, (size_t)in_stride, (size_t)(s1 - s0) * 2,
-                                               (size_t)n_channels, cudaMemcpyHostToDevice, g_ctx.s_in));
-                    CUDA_TRY(cudaEventRecord(g_ctx.ev_slice[8 + k], g_ctx.s_in));
-                    CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_slice[8 + k], 0));
-                    launch_gc_coef_frames(static_cast<const int16_t *>(g_ctx.pcm.p), tab, records, mask, lay.max_frames, f0, f1, st);
-                    g_ctx.launches += 1;
-                }
-                CUDA_TRY(cudaEventRecord(g_ctx.ev_in[0], g_ctx.s_in));
-                launch_gc_coef_refine(tab, records, mask, d_coefs, st);
-                g_ctx.launches += 1;
-                CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaEventRecord(g_ctx.ev_mid[0], st));
-            }
-            const int n_slices = 8;
-            const int per_slice = (div_round_up(frames, n_slices) + 15) / 16 * 16;
-            const int64_t total_bytes = gc_sample_count_to_byte_count(lay.enc_count[0]);
-            int used = 0;
-            for (int k = 0; k < n_slices; k++) {
-                const int f0 = k * per_slice, f1 = std::min(frames, (k + 1) * per_slice);
-                if (f0 >= f1) break;
-                launch_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), tab, d_coefs, static_cast<uint8_t *>(g_ctx.adpcm.p),
-                                 lay.max_frames, f0, f1, st);
-                g_ctx.launches += 1;
-                CUDA_TRY(cudaEventRecord(g_ctx.ev_slice[k], st));
-                CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_slice[k], 0));
-                const int64_t b0 = (int64_t)f0 * kGcFrameBytes, b1 = std::min((int64_t)f1 * kGcFrameBytes, total_bytes);
-                if (b1 > b0)
-                    CUDA_TRY(cudaMemcpy2DAsync(adpcm_out[0] + b0, (size_t)out_stride, static_cast<char *>(g_ctx.adpcm.p) + lay.adpcm_off[0] + b0,
-                                               (size_t)d_out_pitch, (size_t)(b1 - b0), (size_t)n_channels, cudaMemcpyDeviceToHost, g_ctx.s_out));
-                used = k + 1;
-            }
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_done[0], st));
-            CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_mid[0], 0));
-            CUDA_TRY(cudaMemcpyAsync(coefs_out, d_coefs, (size_t)n_channels * 32, cudaMemcpyDeviceToHost, g_ctx.s_out));
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_out[0], g_ctx.s_out));
-            // progress: frames of each finished slice (IProgressReport.ReportAdd deltas sum to SetTotal)
-            int64_t reported = 0;
-            for (int k = 0; k < used; k++) {
-                CUDA_TRY(cudaEventSynchronize(g_ctx.ev_slice[k]));
-                const int64_t upto = (int64_t)std::min(frames, (k + 1) * per_slice) * n_channels;
-                if (cb && upto > reported) cb(user, upto - reported);
-                reported = std::max(reported, upto);
-            }
-            CUDA_TRY(cudaEventSynchronize(g_ctx.ev_out[0]));
-            return VGB_OK;
-        }
+        int64_t total = 0;
+        for (int c = 0; c < n_channels; c++) total += lay.n_samples[c];
+        // a group should carry at least ~32 MB of PCM (a few ms of PCIe time) and 32 channels
+        const int64_t by_bytes = total / (16 << 20), by_channels = n_channels / 32;
+        n_groups = (int)std::min<int64_t>(kMaxGroups / 2, std::min<int64_t>(by_bytes, by_channels));
+        if (n_groups < 1) n_groups = 1;
     }
-
-    // channel groups with roughly equal sample totals (boundaries on channel indices, order preserved)
-    int n_groups = n_channels >= 64 ? kMaxGroups : 1;
     if (const char *env = std::getenv("VGB_ENCODE_GROUPS")) {  // tuning knob: 1..kMaxGroups
         const int want = std::atoi(env);
         if (want >= 1 && want <= kMaxGroups && n_channels >= want) n_groups = want;
@@ -586,6 +527,17 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
 
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
+    // every exit, including the error returns below, leaves no copy in flight on caller memory (pins are released
+    // and the buffers may be freed as soon as this function returns)
+    struct PipelineDrain {
+        ~PipelineDrain()
+        {
+            cudaStreamSynchronize(g_ctx.s_in);
+            for (auto st : g_ctx.s_comp) cudaStreamSynchronize(st);
+            cudaStreamSynchronize(g_ctx.s_out);
+            (void)cudaGetLastError();
+        }
+    } drain;
     std::vector<GcLayout> glay(n_groups);
     std::vector<GcWorkspace> gws(n_groups);
     std::vector<size_t> ws_at(n_groups);
@@ -625,7 +577,7 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     // stage 2: kernels of each group on its own stream, as soon as its PCM has landed
     for (int g = 0; g < n_groups; g++) {
         const int c0 = bound[g];
-        cudaStream_t st = g_ctx.s_comp[g];
+        cudaStream_t st = g_ctx.s_comp[g % kCompStreams];
         CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_in[g], 0));
         VGB_TRY(run_gc_encode(static_cast<const int16_t *>(g_ctx.pcm.p), glay[g],
                               d_coefs_in ? d_coefs_in + (size_t)c0 * 16 : nullptr, d_coefs_out + (size_t)c0 * 16,
@@ -686,6 +638,9 @@ int32_t vgb_shutdown(void)
     if (!g_ctx.ready) return VGB_OK;
     cudaSetDevice(g_ctx.device);
     cudaStreamSynchronize(g_ctx.stream);
+    cudaStreamSynchronize(g_ctx.s_in);
+    for (auto st : g_ctx.s_comp) cudaStreamSynchronize(st);
+    cudaStreamSynchronize(g_ctx.s_out);
     g_ctx.pcm.release();
     g_ctx.adpcm.release();
     g_ctx.coefs.release();
@@ -699,16 +654,12 @@ int32_t vgb_shutdown(void)
     g_ctx.stream = nullptr;
     cudaStreamDestroy(g_ctx.s_in);
     cudaStreamDestroy(g_ctx.s_out);
+    for (int g = 0; g < kCompStreams; g++) cudaStreamDestroy(g_ctx.s_comp[g]);
     for (int g = 0; g < kMaxGroups; g++) {
-        cudaStreamDestroy(g_ctx.s_comp[g]);
         cudaEventDestroy(g_ctx.ev_in[g]);
         cudaEventDestroy(g_ctx.ev_done[g]);
         cudaEventDestroy(g_ctx.ev_out[g]);
         cudaEventDestroy(g_ctx.ev_mid[g]);
-    }
-    for (auto &ev : g_ctx.ev_slice) {
-        if (ev) cudaEventDestroy(ev);
-        ev = nullptr;
     }
     if (g_ctx.ev_t0) cudaEventDestroy(g_ctx.ev_t0);
     g_ctx.ev_t0 = nullptr;
@@ -1061,6 +1012,21 @@ int32_t vgb_debug_last_coefs_done(float *ms_out, int32_t n)
     if (!g_ctx.ready) return VGB_OK;
     for (int g = 0; g < g_ctx.last_groups && g < n; g++)
         CUDA_TRY(cudaEventElapsedTime(&ms_out[g], g_ctx.ev_t0, g_ctx.ev_mid[g]));
+    return VGB_OK;
+}
+
+/* Bookkeeping of the most recent time-parallel encode launch: out[0] segments per channel, out[1] frames re-encoded by
+ * the boundary run-ons, out[2] by the cascade, out[3] boundaries the cascade had to repair.  Synchronises the device. */
+int32_t vgb_gcadpcm_debug_splice_stats(uint64_t *out4)
+{
+    if (!out4) return fail(VGB_E_ARG, "out4 is NULL");
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (!g_ctx.ready || !g_ctx.last_seg.stats) return VGB_OK;
+    unsigned long long st[4] = {};
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(st, g_ctx.last_seg.stats, sizeof st, cudaMemcpyDeviceToHost));
+    out4[0] = (uint64_t)g_ctx.last_seg.seg_count; out4[1] = st[0]; out4[2] = st[1]; out4[3] = st[2];
     return VGB_OK;
 }
 

@@ -55,6 +55,16 @@ struct GcChannelTable {
     int32_t n_channels;
 };
 
+// Time-parallel encoding (gc_encode.cu): segment bookkeeping of one encode launch, all in the caller's workspace.
+constexpr int kGcMinSegFrames = 256;  // no segment shorter than this (run-ons at the boundaries must stay a small share)
+constexpr int kGcMaxSegments = 256;
+struct GcSegArgs {
+    uint32_t *trace;             // [rec_off[ch] + frame] the pair (hist1 + 32768) | (hist2 + 32768) << 16 a frame hands on
+    uint32_t *used_start;        // [ch][seg_count] the pair a boundary's run-on started from
+    unsigned long long *stats;   // [0] frames re-encoded by run-ons, [1] by the cascade, [2] boundaries left to the cascade
+    int32_t seg_count;
+};
+
 // One channel of a seek-table / loop-context request (gc_decode_kernel<true>).
 struct GcTapChannel {
     int64_t out_off;            // first short of the channel in the tap slab: [entries * 2 seek shorts][hist1][hist2]

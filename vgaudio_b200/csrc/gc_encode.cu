@@ -31,6 +31,9 @@
 // the float32 rounding provably cannot move the result (gc_attempt_fast's exit test); the few lanes that fail the
 // test recompute their pass with the general exact path (wrapping int32 arithmetic + the float32-rounding-aware
 // integer quantiser).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -40,6 +43,10 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kEncChunkFrames = 16;                                   // frames staged per chunk
 constexpr int kEncChunkSamples = kEncChunkFrames * kGcFrameSamples;   // 224 samples = 448 B = 28 x 16 B
 constexpr int kEncWarps = 2;                                          // channels per CTA
+#ifndef VGB_ENC_BLOCKS_PER_SM
+#define VGB_ENC_BLOCKS_PER_SM 8
+#endif
+constexpr int kEncChainBlocksPerSm = VGB_ENC_BLOCKS_PER_SM;               // register budget of the chain launch: 8 CTAs x 2 warps = 4 warps per sub-partition
 constexpr uint32_t kErrSat = (1u << 27) - 1;                          // single-REDUX argmin while err < 2^27 - 1
 
 template <bool kGeneral>
@@ -209,7 +216,39 @@ __device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1,
     return __shfl_sync(kFull, mine, half * 16 + (int)(min_lo & 15u));
 }
 
-// grid: one HALF-WARP per channel (two channels per warp); encodes frames [frame_begin, frame_end) of every channel,
+// ---------------------------------------------------------------------------------------------------------
+// TIME-PARALLEL ENCODING (speculate -> verify -> splice).  Frames of a channel are serial only through the two
+// reconstructed samples a frame hands to the next (:40-41).  Quantise/reconstruct is error feedback, so a chain that
+// starts from a WRONG history re-locks onto the true chain after a few frames (measured with the oracle on the
+// synthetic set: median ~10 frames, tail < 1000), and once two chains agree on (hist1, hist2) after the same frame
+// they agree forever (a frame's output is a pure function of its samples, the coefficients and the entering pair).
+// So the frame range [frame_begin, frame_end) of every channel is cut into seg_count segments of seg_len frames
+// (a multiple of 16) and encoded by three launches of the same kernel body:
+//   kGcChain    (grid.y = segment)   segment 0 starts from the true history, segment s > 0 from the RAW samples
+//               before its first frame; each writes its frame bytes and, per frame, the pair it hands on
+//               (`trace`, 4 B per frame).
+//   kGcRunOn    (grid.y = boundary)  the chain of segment s-1 runs on into segment s from its own end state
+//               (trace[lo-1]), overwriting bytes and trace, until the pair after a frame equals the one recorded
+//               there: from that frame on the recorded chain IS the true chain.  Each boundary notes the start pair
+//               it used; boundaries run in parallel and stay inside their segment.
+//   kGcCascade  (one pass per channel) repairs the rare boundary whose predecessor did not splice inside its segment
+//               (its end pair changed after the successor had used it): it runs on serially, across segment ends if
+//               need be, until a splice or the end of the channel - the reference's plain serial loop as the last
+//               resort - and stores the final history.
+// Exact by construction: every byte that stays was produced by a frame step from the true entering pair; the only
+// test is equality of two int16 pairs.  Invariant the splice relies on: inside a segment, (bytes[k], trace[k]) is
+// always the step from trace[k-1]; only a segment's first frame may sit on a seam.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGcChain = 0, kGcRunOn = 1, kGcCascade = 2;
+
+// frames per segment of a channel with `range_frames` frames to encode (device and host agree on this)
+__host__ __device__ __forceinline__ int gc_seg_len(int range_frames, int seg_count)
+{
+    const int per = (div_round_up(range_frames, seg_count > 0 ? seg_count : 1) + kEncChunkFrames - 1) / kEncChunkFrames * kEncChunkFrames;
+    return per < kGcMinSegFrames ? kGcMinSegFrames : per;
+}
+
+// grid.x: one HALF-WARP per channel (two channels per warp); encodes frames [frame_begin, frame_end) of every channel,
 // carrying the history in tab.hist between launches (frame_begin must be a multiple of 16).
 //
 // Lane16 = predictor*2 + candidate: the 8 predictors of a channel are searched in parallel and, for each, two
@@ -237,9 +276,10 @@ __device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1,
 //     `raw` only if (diff + half) lies within 128 of a multiple of 2^shift ("near"), and then by one - invisible
 //     to the clamped nibble when |raw| >= 15, but it could flip the overflow-bump test at 248 (`over >= 240`);
 //   * some |diff| >= 2^29 ("huge", hostile coefficients only): the biased sums could wrap.
-__global__ void __launch_bounds__(kEncWarps * 32)
+template <int kMode>
+__global__ void __launch_bounds__(kEncWarps * 32, kMode == kGcChain ? kEncChainBlocksPerSm : 1)
 gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
-                 uint8_t *__restrict__ adpcm, int frame_begin, int frame_end)
+                 uint8_t *__restrict__ adpcm, int frame_begin, int frame_end, GcSegArgs sa)
 {
     __shared__ __align__(16) int16_t in_buf[kEncWarps][2][2][kEncChunkSamples];   // [warp][half][buffer]
     __shared__ __align__(16) uint8_t out_buf[kEncWarps][2][kEncChunkFrames * kGcFrameBytes];
@@ -254,18 +294,19 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
 
     const int n_enc = live ? tab.enc_count[ch] : 0;
     const int n_frames = div_round_up(n_enc, kGcFrameSamples);
-    const int f_hi = min(frame_end, n_frames);                          // this half's end
-    const int f_hi_warp = max(f_hi, __shfl_xor_sync(kFull, f_hi, 16));  // the warp runs until both halves are done
-    if (frame_begin >= f_hi_warp) return;
+    const int f_end = min(frame_end, n_frames);                         // this channel's end of the frame range
+    const int range_frames = max(f_end - frame_begin, 0);
+    const int seg_len = gc_seg_len(range_frames, sa.seg_count);         // this channel's frames per segment
     const int total_bytes = gc_sample_count_to_byte_count(n_enc);
 
     const int16_t *src = pcm + tab.pcm_off[ch];
     uint8_t *dst = adpcm + tab.adpcm_off[ch];
+    uint32_t *trace = sa.trace + tab.rec_off[ch];                       // [frame] pair handed on: hist1+32768 | (hist2+32768) << 16
+    uint32_t *used_start = sa.used_start + (int64_t)ch * sa.seg_count;  // [segment] pair the boundary's run-on started from
     const int32_t c0 = coefs[(int64_t)ch * 16 + 2 * pred];
     const int32_t c1 = coefs[(int64_t)ch * 16 + 2 * pred + 1];
     const int32_t nc0 = -c0, nc1 = -c1;
     const int32_t bias_c = wmul(32768, wadd(c0, c1));  // undoes the +32768 bias of both history samples
-    int32_t p1 = tab.hist[2 * ch] + 32768, p2 = tab.hist[2 * ch + 1] + 32768;  // biased history (newest, older)
 
     // Stage the 28 16-byte vectors of the chunk starting at `chunk_frame` into buffer b with cp.async (LDGSTS): the
     // copy needs no registers, so it is issued a whole chunk (~24k cycles) ahead and DRAM latency never shows - a
@@ -277,7 +318,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             const int v = l16 + 16 * k;
             if (v < kEncChunkSamples / 8) {
                 const int64_t s = (int64_t)chunk_frame * kGcFrameSamples + v * 8;
-                int64_t valid = chunk_frame < f_hi ? (int64_t)n_enc - s : 0;
+                int64_t valid = (int64_t)n_enc - s;
                 valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
                 const int16_t *from = valid > 0 ? src + s : src;
                 const unsigned to = (unsigned)__cvta_generic_to_shared(&in_buf[warp][half][b][v * 8]);
@@ -305,30 +346,76 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         return k;
     };
 
+    // ---- jobs: a chain job is one segment; a run-on job is one segment boundary; the cascade walks the boundaries ----
+    const int job_first = kMode == kGcChain ? (int)blockIdx.y : (kMode == kGcRunOn ? (int)blockIdx.y + 1 : 1);
+    const int job_last = kMode == kGcCascade ? sa.seg_count - 1 : job_first;
+    int truth_upto = 0;           // cascade: frames below this index were finished by an earlier job of this pass
+    int reencoded = 0;            // run-on / cascade statistics (frames encoded again)
+    int32_t p1 = 0, p2 = 0;       // biased history (newest, older)
+
+    for (int job = job_first; job <= job_last; job++) {
+        const int seg_lo = frame_begin + job * seg_len;   // this half's first frame (a multiple of 16 past frame_begin)
+        bool need = live && seg_lo < f_end;
+        uint32_t start_pair = 0;
+        if (kMode == kGcChain) {
+            if (need) {
+                if (job == 0) {
+                    p1 = tab.hist[2 * ch] + 32768; p2 = tab.hist[2 * ch + 1] + 32768;
+                } else {  // speculative start: the raw samples in front of the segment
+                    p1 = src[(int64_t)seg_lo * kGcFrameSamples - 1] + 32768; p2 = src[(int64_t)seg_lo * kGcFrameSamples - 2] + 32768;
+                }
+            }
+        } else {
+            if (kMode == kGcCascade) __syncwarp();  // trace words written by other lanes in an earlier job
+            if (need) start_pair = trace[seg_lo - 1];
+            if (kMode == kGcRunOn) {
+                if (need && l16 == 0) used_start[job] = start_pair;
+            } else {
+                need = need && seg_lo >= truth_upto && start_pair != used_start[job];
+            }
+            p1 = (int32_t)(start_pair & 0xFFFFu); p2 = (int32_t)(start_pair >> 16);
+        }
+        // chain / run-on stay inside their segment; the cascade may run to the end of the channel
+        const int seg_hi = kMode == kGcCascade ? f_end : min(seg_lo + seg_len, f_end);
+        const int len = need ? seg_hi - seg_lo : 0;
+        const int len_warp = max(len, __shfl_xor_sync(kFull, len, 16));  // the warp runs until both halves are done
+        if (len_warp == 0) continue;
+        bool spliced = false;      // run-on: the recorded chain was met, the rest of it is final
+        int done = 0;              // frames this half has encoded in this job
+
     int buf = 0;
-    stage_chunk(frame_begin, 0);
+    stage_chunk(seg_lo, 0);
     staged_wait();
-    // pipeline prologue: samples and residual keys of the first frame
-    int32_t x[14];
-#pragma unroll
-    for (int j = 0; j < 14; j++) x[j] = in_buf[warp][half][0][j];
+    // pipeline prologue: residual keys of the first frame
     uint32_t key_rest = key_rest_partial(in_buf[warp][half][0]);
     key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 1));
 
-    for (int cf = frame_begin; cf < f_hi_warp; cf += kEncChunkFrames) {
+    for (int rc = 0; rc < len_warp; rc += kEncChunkFrames) {
+        const int cf = seg_lo + rc;                                            // this half's chunk
         // next chunk -> the other buffer (dead since the previous chunk's last frame), awaited before the last frame
         stage_chunk(cf + kEncChunkFrames, buf ^ 1);
-        const int frames_warp = min(kEncChunkFrames, f_hi_warp - cf);
-        const int frames_here = max(min(kEncChunkFrames, f_hi - cf), 0);  // this half's share
+        const int frames_warp = min(kEncChunkFrames, len_warp - rc);
+        const int frames_here = max(min(kEncChunkFrames, len - rc), 0);    // this half's share
         const int16_t *chunk = in_buf[warp][half][buf];
         const int16_t *other = in_buf[warp][half][buf ^ 1];
+        uint32_t tr = 0;           // lane l16 keeps the pair frame cf + l16 hands on
+        uint32_t tr_old = 0;       // run-on: the pair recorded there by the chain being met
+        if (kMode != kGcChain && l16 < frames_here && !spliced) tr_old = trace[cf + l16];
+        int frames_done = 0;
+        bool all_done = false;
 
         for (int i = 0; i < frames_warp; i++) {
             if (i == kEncChunkFrames - 1) staged_wait();  // this frame reads the next chunk's first samples
-            const bool active = i < frames_here;  // a shorter channel idles while its warp mate finishes
+            const bool active = i < frames_here && !spliced;  // a finished half idles while its warp mate goes on
             const int16_t *frame = chunk + i * kGcFrameSamples;
             const int16_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
             const int32_t p1_in = p1, p2_in = p2;
+            // the frame's samples (same address for the 16 lanes of a half: broadcast).  Not carried in registers from
+            // the previous frame: the kernel is issue bound once several warps share a sub-partition, and 14 registers
+            // fewer per thread buy another resident warp
+            int32_t x[14];
+#pragma unroll
+            for (int j = 0; j < 14; j++) x[j] = frame[j];
 
             // ---------------- head ----------------
             const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(p2, p1, x[0], c0, c1, 0, -bias_c),
@@ -340,7 +427,6 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             uint64_t err = 0;
             int sp = 0;
             int32_t q1 = p1, q2 = p2;  // newest two reconstructed samples of that pass (biased)
-            int32_t xn[14];
             uint32_t key_rest_next = 0;
             bool resolved = false;     // this lane's predictor already has its chain-ending pass
 
@@ -361,15 +447,24 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 const int lsh = 32 - shift;
                 const uint32_t near_c = 128u << lsh;
                 const uint32_t near_k = (1u << lsh) + near_c;   // (tn << lsh) + near_c with tn = tm1 + 1
+                const int32_t lmul = (int32_t)(1u << lsh);
 
-                // ---------------- phase A: recurrence ----------------
-                int32_t tmv[14], rawv[14], qbv[14], obv[14];
+                // ---------------- recurrence, with the pass's bookkeeping folded in ----------------
+                // range of raw (maxOverflow), distance to a rounding threshold, squared error (exact; < 2^36) and
+                // nibble packing ride along as independent work; nothing per sample is kept in registers.  The integer
+                // ALU pipe is the busiest unit of this kernel (ncu: 80 % against 28 % for the multiply-add pipe), so
+                // adds and shifts of the side work are written as multiply-adds wherever that is exact.
                 int32_t r1 = p1_in, r2 = p2_in;
+                int32_t rmin = 0, rmax = 0, raw_even = 0;
+                uint32_t nearmin = 0xFFFFFFFFu;
+                uint64_t e0 = 0, e1s = 0;
+                uint32_t nw0 = 0, nw1 = 0;
 #pragma unroll
                 for (int s = 0; s < 14; s++) {
                     const int32_t wt = imad(x[s], 2048, base_m);
+                    const int32_t wh = imad(x[s], 2048, base_m - half_q);
                     const int32_t an = imad(r2, nc1, wt);          // r2 terms: one step off the chain
-                    const int32_t ah = an - half_q;
+                    const int32_t ah = imad(r2, nc1, wh);          // an - half
                     const int32_t gn = imad(r2, c1, base_g);
                     const int32_t tm1 = imad(r1, nc0, an);         // diff + half - 1          <- chain
                     const int32_t e1 = imad(r1, nc0, ah);          // diff - 1: negative iff diff <= 0
@@ -380,38 +475,42 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                     const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);        // clamp4(raw) + 8
                     const int32_t o = imad(qb, mul, wf >> 11);
                     const int32_t ob = __viaddmin_s32_relu(o, 32768, 65535);   // clamp16(o) + 32768
-                    tmv[s] = tm1; rawv[s] = raw; qbv[s] = qb; obv[s] = ob;
                     r2 = r1;
                     r1 = ob;
+                    if (s & 1) {
+                        rmin = __vimin3_s32(rmin, raw_even, raw);
+                        rmax = __vimax3_s32(rmax, raw_even, raw);
+                    } else {
+                        raw_even = raw;
+                    }
+                    nearmin = min(nearmin, (uint32_t)imad(tm1, lmul, (int32_t)near_k));   // (tm1 << lsh) + near_k
+                    const int32_t miss = imad(ob, -1, x[s] + 32768);
+                    const uint64_t sq = (uint64_t)((int64_t)miss * miss);
+                    if (s & 1) e1s += sq; else e0 += sq;
+                    const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
+                    if (byte < 4) nw0 = (uint32_t)imad(qb, 1 << bit, (int32_t)nw0);
+                    else nw1 = (uint32_t)imad(qb, (int32_t)(1u << bit), (int32_t)nw1);  // disjoint bit fields: add == or
                     // independent work for the NEXT frame rides along (software pipelining), first round only
                     if (round == 0) {
-                        if (s == 1) {
-#pragma unroll
-                            for (int j = 0; j < 14; j++) xn[j] = frame_next[j];  // same address per half: broadcast
-                        }
                         if (s == 4) key_rest_next = key_rest_partial(frame_next);
                         if (s == 10) key_rest_next = max(key_rest_next, __shfl_xor_sync(kFull, key_rest_next, 1));
                     }
                 }
 
-                // ---------------- phase B ----------------
-                int32_t rmin = 0, rmax = 0;
-                uint32_t nearmin = 0xFFFFFFFFu;
-#pragma unroll
-                for (int s = 0; s < 14; s += 2) {
-                    rmin = __vimin3_s32(rmin, rawv[s], rawv[s + 1]);
-                    rmax = __vimax3_s32(rmax, rawv[s], rawv[s + 1]);
-                }
-#pragma unroll
-                for (int s = 0; s < 14; s++) nearmin = __viaddmin_u32((uint32_t)tmv[s] << lsh, near_k, nearmin);
                 // branch-free flags (0/1 integers): a compiled '&&' would put divergent branches on the critical
-                // path.  maxOverflow (:147-151) is max(rmax - 7, -8 - rmin, 0); only its comparisons are needed.
+                // path.  maxOverflow (:147-151) is max(rmax - 7, -8 - rmin, 0); only its comparisons are needed, and
+                // all of them are thresholds of one number, m = max(rmax + 1, -rmin):
+                //   over <= 1  <=>  rmax <= 8 and rmin >= -9    <=>  m <= 9
+                //   over >= 240 <=> rmax >= 247 or rmin <= -248 <=>  m >= 248
+                //   over > 248 <=>  rmax > 255 or rmin < -256   <=>  m >= 257
+                // big / huge (|raw| >= threshold) use m >= threshold, which can only err on the careful side.
+                const int32_t m = __viaddmax_s32(rmax, 1, -rmin);
                 const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
-                const uint32_t big = (uint32_t)(rmax >= big_thr) | (uint32_t)(rmin <= -big_thr);     // |diff| >= 2^24
-                const uint32_t huge = (uint32_t)(rmax >= huge_thr) | (uint32_t)(rmin <= -huge_thr);  // |diff| >= 2^29
-                const uint32_t over_ge_240 = (uint32_t)(rmax >= 247) | (uint32_t)(rmin <= -248);
-                const uint32_t over_gt_248 = (uint32_t)(rmax > 255) | (uint32_t)(rmin < -256);
-                const uint32_t over_le_1 = (uint32_t)(rmax <= 8) & (uint32_t)(rmin >= -9);
+                const uint32_t big = (uint32_t)(m >= big_thr);     // some |diff| >= 2^24 (or one short of it)
+                const uint32_t huge = (uint32_t)(m >= huge_thr);   // some |diff| >= 2^29
+                const uint32_t over_ge_240 = (uint32_t)(m >= 248);
+                const uint32_t over_gt_248 = (uint32_t)(m >= 257);
+                const uint32_t over_le_1 = (uint32_t)(m <= 9);
                 const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | over_ge_240;
                 const bool take = !resolved;  // lanes of resolved predictors keep their round-0 result
                 const uint32_t live_take = valid & (uint32_t)(take && active);
@@ -423,19 +522,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 term_bits = __ballot_sync(kFull, terminal != 0u);
                 trouble_bits |= __ballot_sync(kFull, (inexact | bump) != 0u);
 
-                // squared error (four partial sums) and nibble packing of this pass: fills the ballot latency;
-                // computed unconditionally and kept with selects (a divergent block would cost more than it saves)
-                uint64_t e0 = 0, e1s = 0, e2 = 0, e3 = 0;
-                uint32_t nw0 = 0, nw1 = 0;
-#pragma unroll
-                for (int s = 0; s < 14; s++) {
-                    const int32_t miss = x[s] + 32768 - obv[s];
-                    const uint64_t sq = (uint64_t)((int64_t)miss * miss);  // exact; the sum stays below 2^36
-                    if ((s & 3) == 0) e0 += sq; else if ((s & 3) == 1) e1s += sq; else if ((s & 3) == 2) e2 += sq; else e3 += sq;
-                    const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
-                    if (byte < 4) nw0 += (uint32_t)qbv[s] << bit; else nw1 += (uint32_t)qbv[s] << bit;  // disjoint
-                }
-                const uint64_t nerr = (e0 + e1s) + (e2 + e3);
+                const uint64_t nerr = e0 + e1s;
                 err = take ? nerr : err;
                 w0 = take ? (nw0 ^ 0x88888800u) : w0;  // remove the +8 nibble bias (q & 15 == (q + 8) ^ 8)
                 w1 = take ? (nw1 ^ 0x88888888u) : w1;
@@ -490,18 +577,26 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             if (active) {
                 p1 = (int32_t)(packed & 0xFFFFu);
                 p2 = (int32_t)(packed >> 16);
+                frames_done = i + 1;
+                if (l16 == i) tr = packed;
+            }
+            if (kMode != kGcChain) {
+                // splice test: the pair this frame hands on against the pair recorded after the same frame
+                const uint32_t old = __shfl_sync(kFull, tr_old, half * 16 + i);
+                if (active && packed == old) spliced = true;
+                all_done = __all_sync(kFull, spliced || rc + i + 1 >= len);
+                if (all_done) break;
             }
 
-#pragma unroll
-            for (int j = 0; j < 14; j++) x[j] = xn[j];
             key_rest = key_rest_next;
         }
         staged_wait();
 
-        // write the chunk's bytes; only the channel's last frame can be partial (:38)
-        if (frames_here > 0) {
+        // write the bytes and trace words of the frames encoded in this chunk; only the channel's last frame can be
+        // partial (:38)
+        if (frames_done > 0) {
             const int64_t byte0 = (int64_t)cf * kGcFrameBytes;
-            const int bytes_here = (int)min((int64_t)frames_here * kGcFrameBytes, (int64_t)total_bytes - byte0);
+            const int bytes_here = (int)min((int64_t)frames_done * kGcFrameBytes, (int64_t)total_bytes - byte0);
             if (l16 < 8) {
                 const int b = l16 * 16;
                 if (b + 16 <= bytes_here) {
@@ -510,14 +605,31 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                     for (int j = b; j < bytes_here; j++) dst[byte0 + j] = out_buf[warp][half][j];
                 }
             }
+            if (l16 < frames_done) trace[cf + l16] = tr;
+            done += frames_done;
         }
         __syncwarp();
         buf ^= 1;
+        if (kMode != kGcChain && all_done) break;
+    }
+        // ---- end of the job ----
+        if (kMode != kGcChain) {
+            reencoded += done;
+            if (kMode == kGcCascade && need) truth_upto = seg_lo + done;
+            if (kMode == kGcRunOn && need && !spliced && l16 == 0 && seg_hi < f_end)
+                atomicAdd(&sa.stats[2], 1ull);  // this boundary's segment end changed under its successor
+        }
     }
 
-    if (l16 == 0 && live) {
-        tab.hist[2 * ch] = (int16_t)(p1 - 32768);
-        tab.hist[2 * ch + 1] = (int16_t)(p2 - 32768);
+    if (kMode != kGcChain && l16 == 0 && reencoded > 0) atomicAdd(&sa.stats[kMode == kGcRunOn ? 0 : 1], (unsigned long long)reencoded);
+    // the history the next call continues from (:40-41 carried across launches): the pair the range's last frame hands on
+    if ((kMode == kGcCascade || (kMode == kGcChain && sa.seg_count == 1)) && live && range_frames > 0) {
+        __syncwarp();
+        if (l16 == 0) {
+            const uint32_t last = trace[f_end - 1];
+            tab.hist[2 * ch] = (int16_t)((int32_t)(last & 0xFFFFu) - 32768);
+            tab.hist[2 * ch + 1] = (int16_t)((int32_t)(last >> 16) - 32768);
+        }
     }
 }
 
@@ -573,14 +685,50 @@ gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restr
     }
 }
 
+// How many segments to cut the frame range into.  The chain launch is throughput bound once every SM sub-partition
+// holds its four warps (measured on C2: ~850 cycles per frame pair and sub-partition from 4 warps up, against the
+// 1419-cycle dependent chain of a lone warp), so the aim is (a) several full waves of (channel pair, segment) items -
+// the last, partly filled wave is the only loss - and (b) segments long enough that the run-on work at their
+// boundaries (a few dozen frames each, a long tail) stays small.  Measured on C2 (512 item rows): 75.5 ms with one
+// segment, 48 ms with 3, 39.0 with 17, 38.7 with 24, 38.8 with 34, 45 with 48 (profiles/r02_seg_sweep.md).
+int gc_encode_pick_segments(int n_channels, int max_frames)
+{
+    if (const char *env = std::getenv("VGB_GC_SEGMENTS")) {
+        const int v = std::atoi(env);
+        if (v >= 1) return v > kGcMaxSegments ? kGcMaxSegments : v;
+    }
+    static int slots = 0;
+    if (slots == 0) {
+        int dev = 0, sms = 148, per_sm = kEncChainBlocksPerSm;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_encode_kernel<kGcChain>, kEncWarps * 32, 0) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = kEncChainBlocksPerSm;
+        }
+        slots = sms * per_sm * kEncWarps;  // resident warps of the chain launch
+    }
+    const int rows = (n_channels + 1) / 2;
+    const int max_s = std::min(kGcMaxSegments, std::max(1, max_frames / kGcMinSegFrames));
+    const int want = (int)((5ll * slots + rows - 1) / rows);  // about five waves of items
+    return std::max(1, std::min(want, max_s));
+}
+
 void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16_t *coefs, uint8_t *adpcm,
-                      int max_frames, int frame_begin, int frame_end, cudaStream_t stream)
+                      int max_frames, int frame_begin, int frame_end, GcSegArgs sa, cudaStream_t stream)
 {
     if (tab.n_channels <= 0 || max_frames <= 0) return;
     if (frame_begin >= frame_end || frame_begin >= max_frames) return;
     const int per_block = kEncWarps * 2;  // two channels per warp
-    int blocks = (tab.n_channels + per_block - 1) / per_block;
-    gc_encode_kernel<<<blocks, kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end);
+    const int blocks = (tab.n_channels + per_block - 1) / per_block;
+    if (sa.seg_count < 1) sa.seg_count = 1;
+    if (sa.seg_count > kGcMaxSegments) sa.seg_count = kGcMaxSegments;
+    cudaMemsetAsync(sa.stats, 0, 4 * sizeof(unsigned long long), stream);
+    gc_encode_kernel<kGcChain><<<dim3(blocks, sa.seg_count), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
+    if (sa.seg_count > 1) {
+        gc_encode_kernel<kGcRunOn><<<dim3(blocks, sa.seg_count - 1), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
+        gc_encode_kernel<kGcCascade><<<dim3(blocks, 1), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
+    }
 }
 
 void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs, int n_frames,

@@ -15,8 +15,9 @@ void launch_gc_coef_refine(const GcChannelTable &tab, const double2 *records, co
                            int16_t *coefs_out, cudaStream_t stream);
 
 // gc_encode.cu — GcAdpcmEncoder.Encode / DspEncodeFrame / DspEncodeCoef (Codecs/GcAdpcm/GcAdpcmEncoder.cs:14-171)
+int gc_encode_pick_segments(int n_channels, int max_frames);  // segments per channel for the time-parallel encode
 void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16_t *coefs, uint8_t *adpcm,
-                      int max_frames, int frame_begin, int frame_end, cudaStream_t stream);
+                      int max_frames, int frame_begin, int frame_end, GcSegArgs seg, cudaStream_t stream);
 void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs, int n_frames,
                              uint8_t *adpcm_out, cudaStream_t stream);
 
