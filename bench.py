@@ -289,7 +289,7 @@ def main():
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
     st4 = (C.c_uint64 * 4)()
-    N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(st4))
+    N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(st4, 4))
     splice = {"segments_per_channel": int(st4[0]), "runon_frames": int(st4[1]), "cascade_frames": int(st4[2]),
               "cascade_boundaries": int(st4[3]),
               "fallback_frames_frac": round((int(st4[1]) + int(st4[2])) / max(n_ch * ((n + 13) // 14), 1), 6)}

@@ -190,12 +190,14 @@ int32_t vgb_debug_last_timeline(float *ms_out, int32_t n);
 int32_t vgb_debug_last_coefs_done(float *ms_out, int32_t n);
 
 /* Bookkeeping of the most recent GC-ADPCM encode launch, which runs time-parallel (every channel's frame range is
- * cut into segments encoded concurrently, then spliced at the boundaries; gc_encode.cu): out4[0] segments per channel,
- * out4[1] frames re-encoded by the boundary run-ons, out4[2] frames re-encoded by the serial cascade (the fallback when a
- * boundary does not re-lock inside its segment), out4[3] boundaries the cascade had to repair.  bench.py reports
- * (out4[1] + out4[2]) / frames as `fallback_frames_frac`.  Synchronises the device.
- * VGB_GC_SEGMENTS=<n> in the environment forces the segment count (1 = the plain serial loop of GcAdpcmEncoder.cs:30-43). */
-int32_t vgb_gcadpcm_debug_splice_stats(uint64_t *out4);
+ * cut into segments encoded concurrently, then spliced at the boundaries; gc_encode.cu): out[0] segments per channel,
+ * out[1] frames re-encoded by the boundary run-ons, out[2] frames re-encoded by the serial cascade (the fallback when a
+ * boundary does not re-lock inside its segment), out[3] boundaries the cascade had to repair, out[4] the longest
+ * run-on in frames, out[5 + b] the number of run-ons of 2^b .. 2^(b+1)-1 frames (b = 0..13, the last one open).  n = how
+ * many words to fill (up to 19).  bench.py reports (out[1] + out[2]) / frames as `fallback_frames_frac`.  Synchronises
+ * the device.  VGB_GC_SEGMENTS=<n> in the environment forces the segment count (1 = the plain serial loop of
+ * GcAdpcmEncoder.cs:30-43). */
+int32_t vgb_gcadpcm_debug_splice_stats(uint64_t *out, int32_t n);
 
 /* Debug/test taps (tests/ only): run coefficient phase 1 and return, per frame, the direct-form pair and the
  * accept flag the refinement consumes.  Host buffers; dir_out [frames][2] doubles, accepted_out [frames] bytes. */

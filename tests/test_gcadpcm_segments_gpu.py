@@ -33,7 +33,7 @@ def splice_stats(vg):
     from vgaudio_b200 import _native as N
 
     out = (C.c_uint64 * 4)()
-    N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(out))
+    N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(out, 4))
     return {"segments": int(out[0]), "runon_frames": int(out[1]), "cascade_frames": int(out[2]), "cascade_boundaries": int(out[3])}
 
 

@@ -56,15 +56,16 @@ def main():
             N.check(vg.lib.vgb_last_kernel_ms(buf, 4))
             ms.append(list(buf))
         torch.cuda.synchronize()
-        st = (C.c_uint64 * 4)()
-        N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(st))
+        st = (C.c_uint64 * 19)()
+        N.check(vg.lib.vgb_gcadpcm_debug_splice_stats(st, 19))
         if ref is None:
             ref = adpcm.clone()
         same = bool((adpcm == ref).all().item())
         row = {"segments_forced": s, "segments": int(st[0]), "gc_encode_ms": round(min(m[2] for m in ms), 3),
                "coef_frames_ms": round(min(m[0] for m in ms), 3), "coef_refine_ms": round(min(m[1] for m in ms), 3),
                "runon_frames": int(st[1]), "cascade_frames": int(st[2]), "cascade_boundaries": int(st[3]),
-               "fallback_frac": round((int(st[1]) + int(st[2])) / (n_ch * frames), 6), "same_bytes_as_first": same}
+               "fallback_frac": round((int(st[1]) + int(st[2])) / (n_ch * frames), 6), "longest_runon": int(st[4]),
+               "runon_log2_hist": [int(st[5 + b]) for b in range(14)], "same_bytes_as_first": same}
         rows.append(row)
         print(json.dumps(row), flush=True)
     return 0

@@ -114,7 +114,7 @@ SIGNATURES = {
     "vgb_debug_last_timeline": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_debug_last_coefs_done": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_gcadpcm_debug_records": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
-    "vgb_gcadpcm_debug_splice_stats": (C.c_int32, [C.c_void_p]),
+    "vgb_gcadpcm_debug_splice_stats": (C.c_int32, [C.c_void_p, C.c_int32]),
 }
 
 

@@ -188,7 +188,7 @@ GcWorkspace carve(int64_t rec_total_frames, int32_t n_channels)
     w.off_mask = take((size_t)(rec_total_frames / 32 + 1) * 4);
     w.off_trace = take((size_t)rec_total_frames * 4);
     w.off_used_start = take(n * kGcMaxSegments * 4);
-    w.off_stats = take(64);
+    w.off_stats = take(kGcStatWords * 8);
     w.total = o;
     return w;
 }
@@ -1015,18 +1015,18 @@ int32_t vgb_debug_last_coefs_done(float *ms_out, int32_t n)
     return VGB_OK;
 }
 
-/* Bookkeeping of the most recent time-parallel encode launch: out[0] segments per channel, out[1] frames re-encoded by
- * the boundary run-ons, out[2] by the cascade, out[3] boundaries the cascade had to repair.  Synchronises the device. */
-int32_t vgb_gcadpcm_debug_splice_stats(uint64_t *out4)
+/* Bookkeeping of the most recent time-parallel encode launch (see the header).  Synchronises the device. */
+int32_t vgb_gcadpcm_debug_splice_stats(uint64_t *out, int32_t n)
 {
-    if (!out4) return fail(VGB_E_ARG, "out4 is NULL");
+    if (!out || n < 0) return fail(VGB_E_ARG, "bad arguments");
     std::lock_guard<std::mutex> lock(g_ctx.mu);
-    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (int i = 0; i < n; i++) out[i] = 0;
     if (!g_ctx.ready || !g_ctx.last_seg.stats) return VGB_OK;
-    unsigned long long st[4] = {};
+    unsigned long long st[kGcStatWords] = {};
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(st, g_ctx.last_seg.stats, sizeof st, cudaMemcpyDeviceToHost));
-    out4[0] = (uint64_t)g_ctx.last_seg.seg_count; out4[1] = st[0]; out4[2] = st[1]; out4[3] = st[2];
+    if (n > 0) out[0] = (uint64_t)g_ctx.last_seg.seg_count;
+    for (int i = 1; i < n && i <= kGcStatWords; i++) out[i] = st[i - 1];
     return VGB_OK;
 }
 

@@ -58,10 +58,12 @@ struct GcChannelTable {
 // Time-parallel encoding (gc_encode.cu): segment bookkeeping of one encode launch, all in the caller's workspace.
 constexpr int kGcMinSegFrames = 256;  // no segment shorter than this (run-ons at the boundaries must stay a small share)
 constexpr int kGcMaxSegments = 256;
+constexpr int kGcStatWords = 18;      // GcSegArgs::stats
 struct GcSegArgs {
     uint32_t *trace;             // [rec_off[ch] + frame] the pair (hist1 + 32768) | (hist2 + 32768) << 16 a frame hands on
     uint32_t *used_start;        // [ch][seg_count] the pair a boundary's run-on started from
-    unsigned long long *stats;   // [0] frames re-encoded by run-ons, [1] by the cascade, [2] boundaries left to the cascade
+    unsigned long long *stats;   // [0] frames re-encoded by run-ons, [1] by the cascade, [2] boundaries left to the cascade,
+                                 // [3] longest run-on, [4 + b] run-ons of 2^b .. 2^(b+1)-1 frames (b = 13: longer)
     int32_t seg_count;
 };
 

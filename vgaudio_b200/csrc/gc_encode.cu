@@ -43,6 +43,9 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kEncChunkFrames = 16;                                   // frames staged per chunk
 constexpr int kEncChunkSamples = kEncChunkFrames * kGcFrameSamples;   // 224 samples = 448 B = 28 x 16 B
 constexpr int kEncWarps = 2;                                          // channels per CTA
+#ifndef VGB_ENC_X_SMEM
+#define VGB_ENC_X_SMEM 0
+#endif
 #ifndef VGB_ENC_BLOCKS_PER_SM
 #define VGB_ENC_BLOCKS_PER_SM 8
 #endif
@@ -156,6 +159,30 @@ __device__ __forceinline__ uint32_t gc_peak_key(int32_t older, int32_t newer, in
     const int32_t diff = clamp16(wsub(cur, guess));
     return ((uint32_t)abs(diff) << 5) | ((uint32_t)(15 - s) << 1) | ((uint32_t)diff >> 31);
 }
+
+// The same residual for the channel encoder's hot loop, cheaper on the integer ALU pipe (the busiest unit of that
+// kernel): the distance is NOT clamped per sample and the two signs are tracked as two running maxima of
+// (+-distance * 16 + order), order = 15 - s, so that a larger |distance| wins and then the earlier sample, exactly the
+// reference's strict '>'.  Per sample that is three multiply-adds and the truncating division; the maxima are taken
+// two samples at a time.  gc_peak_pack folds the pair back into the key format above (|distance| << 5 | order << 1 |
+// sign); Clamp16 (:113) is applied to the winner there - clamping commutes with the maximum, and among clamped
+// samples sign and order no longer matter: every |distance| >= 18432 gives scalePower 12 whatever its sign.
+// All three samples carry the +32768 bias of the staged data; neg_bias = -32768 * (c0 + c1) removes it from the sum.
+__device__ __forceinline__ void gc_peak_terms(int32_t older, int32_t newer, int32_t cur, int32_t c0, int32_t c1, int s,
+                                              int32_t neg_bias, int32_t &tp, int32_t &tn)
+{
+    const int32_t g = imad(newer, c0, imad(older, c1, neg_bias));
+    const int32_t q = (int32_t)(g + (int32_t)((uint32_t)(g >> 31) >> 21)) >> 11;  // g / 2048, truncating toward zero (A.6)
+    const int32_t d = imad(q, -1, cur);                                           // distance + 32768; |distance| < 2^21
+    tp = imad(d, 16, 15 - s - 32768 * 16);
+    tn = imad(d, -16, 15 - s + 32768 * 16);
+}
+__device__ __forceinline__ uint32_t gc_peak_pack(int32_t kp, int32_t kn)
+{
+    const int32_t k = max(kp, kn);                    // (|distance| << 4) | order of the first largest sample (0: none)
+    return ((uint32_t)k << 1) | (uint32_t)(kn > kp);  // sign in bit 0
+}
+constexpr uint32_t kPeakKeyMax = (32768u << 5) | 1u;  // Clamp16: -32768 (a positive 32767 gives the same scalePower)
 
 // First value scalePower takes inside the do/while (:118-129), from the max-residual key.  Closed form of
 //   n = 0; while (n <= 12 && (peak > 7 || peak < -8)) { peak /= 2; n++; }   ("/" truncates toward zero)
@@ -281,7 +308,8 @@ __global__ void __launch_bounds__(kEncWarps * 32, kMode == kGcChain ? kEncChainB
 gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int16_t *__restrict__ coefs,
                  uint8_t *__restrict__ adpcm, int frame_begin, int frame_end, GcSegArgs sa)
 {
-    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][2][kEncChunkSamples];   // [warp][half][buffer]
+    __shared__ __align__(16) int16_t in_buf[kEncWarps][2][2][kEncChunkSamples];   // [warp][half][buffer], cp.async target
+    __shared__ __align__(16) int32_t x_buf[kEncWarps][2][2][kEncChunkSamples];    // the same samples widened once per chunk, +32768
     __shared__ __align__(16) uint8_t out_buf[kEncWarps][2][kEncChunkFrames * kGcFrameBytes];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,19 +359,35 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
     };
+    // int16 -> int32 once per chunk (14 samples per lane) instead of a 16-bit load and a sign extension per sample use:
+    // the frame loop then reads whole 64-bit pairs, broadcast to the 16 lanes of a half
+    auto widen_chunk = [&](int b) {
+        const uint32_t *from = reinterpret_cast<const uint32_t *>(&in_buf[warp][half][b][l16 * kGcFrameSamples]);
+        int2 *to = reinterpret_cast<int2 *>(&x_buf[warp][half][b][l16 * kGcFrameSamples]);
+#pragma unroll
+        for (int k = 0; k < kGcFrameSamples / 2; k++) {
+            const uint32_t w = from[k];
+            to[k] = make_int2((int32_t)(int16_t)(w & 0xFFFFu) + 32768, ((int32_t)w >> 16) + 32768);  // stored with the +32768 bias
+        }
+        __syncwarp();
+    };
     // residual keys of samples 2..13 (raw samples only).  The two candidate lanes of a predictor share the work:
     // lane `cand` takes samples 2+6*cand .. 7+6*cand, one shuffle-xor combines them.
-    auto key_rest_partial = [&](const int16_t *frame) -> uint32_t {
+    auto key_rest_partial = [&](const int32_t *frame) -> uint32_t {
         const int s0 = 2 + 6 * cand;
         int32_t v[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = frame[s0 - 2 + j];
-        uint32_t k = 0;
+        int32_t kp = 0, kn = 0;
 #pragma unroll
-        for (int j = 0; j < 6; j += 2)
-            k = __vimax3_u32(k, gc_peak_key(v[j], v[j + 1], v[j + 2], c0, c1, s0 + j),
-                             gc_peak_key(v[j + 1], v[j + 2], v[j + 3], c0, c1, s0 + j + 1));
-        return k;
+        for (int j = 0; j < 6; j += 2) {
+            int32_t tpa, tna, tpb, tnb;
+            gc_peak_terms(v[j], v[j + 1], v[j + 2], c0, c1, s0 + j, -bias_c, tpa, tna);
+            gc_peak_terms(v[j + 1], v[j + 2], v[j + 3], c0, c1, s0 + j + 1, -bias_c, tpb, tnb);
+            kp = __vimax3_s32(kp, tpa, tpb);
+            kn = __vimax3_s32(kn, tna, tnb);
+        }
+        return gc_peak_pack(kp, kn);
     };
 
     // ---- jobs: a chain job is one segment; a run-on job is one segment boundary; the cascade walks the boundaries ----
@@ -386,8 +430,9 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     int buf = 0;
     stage_chunk(seg_lo, 0);
     staged_wait();
+    widen_chunk(0);
     // pipeline prologue: residual keys of the first frame
-    uint32_t key_rest = key_rest_partial(in_buf[warp][half][0]);
+    uint32_t key_rest = key_rest_partial(x_buf[warp][half][0]);
     key_rest = max(key_rest, __shfl_xor_sync(kFull, key_rest, 1));
 
     for (int rc = 0; rc < len_warp; rc += kEncChunkFrames) {
@@ -396,8 +441,8 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         stage_chunk(cf + kEncChunkFrames, buf ^ 1);
         const int frames_warp = min(kEncChunkFrames, len_warp - rc);
         const int frames_here = max(min(kEncChunkFrames, len - rc), 0);    // this half's share
-        const int16_t *chunk = in_buf[warp][half][buf];
-        const int16_t *other = in_buf[warp][half][buf ^ 1];
+        const int32_t *chunk = x_buf[warp][half][buf];
+        const int32_t *other = x_buf[warp][half][buf ^ 1];
         uint32_t tr = 0;           // lane l16 keeps the pair frame cf + l16 hands on
         uint32_t tr_old = 0;       // run-on: the pair recorded there by the chain being met
         if (kMode != kGcChain && l16 < frames_here && !spliced) tr_old = trace[cf + l16];
@@ -405,21 +450,30 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
         bool all_done = false;
 
         for (int i = 0; i < frames_warp; i++) {
-            if (i == kEncChunkFrames - 1) staged_wait();  // this frame reads the next chunk's first samples
+            if (i == kEncChunkFrames - 1) {  // this frame reads the next chunk's first samples
+                staged_wait();
+                widen_chunk(buf ^ 1);
+            }
             const bool active = i < frames_here && !spliced;  // a finished half idles while its warp mate goes on
-            const int16_t *frame = chunk + i * kGcFrameSamples;
-            const int16_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
+            const int32_t *frame = chunk + i * kGcFrameSamples;
+            const int32_t *frame_next = (i + 1 < kEncChunkFrames) ? frame + kGcFrameSamples : other;
             const int32_t p1_in = p1, p2_in = p2;
-            // the frame's samples (same address for the 16 lanes of a half: broadcast).  Not carried in registers from
+            // the frame's samples, biased (same address for the 16 lanes of a half: broadcast).  Not carried in registers from
             // the previous frame: the kernel is issue bound once several warps share a sub-partition, and 14 registers
             // fewer per thread buy another resident warp
+#if VGB_ENC_X_SMEM
+            const int32_t *x = frame;  // read at every use (LSU pipe, nearly idle) instead of 14 live registers
+#else
             int32_t x[14];
 #pragma unroll
             for (int j = 0; j < 14; j++) x[j] = frame[j];
+#endif
 
             // ---------------- head ----------------
-            const uint32_t key = __vimax3_u32(key_rest, gc_peak_key(p2, p1, x[0], c0, c1, 0, -bias_c),
-                                              gc_peak_key(p1, x[0] + 32768, x[1], c0, c1, 1, -bias_c));
+            int32_t tp0, tn0, tp1, tn1;
+            gc_peak_terms(p2, p1, x[0], c0, c1, 0, -bias_c, tp0, tn0);
+            gc_peak_terms(p1, x[0], x[1], c0, c1, 1, -bias_c, tp1, tn1);
+            const uint32_t key = min(max(key_rest, gc_peak_pack(max(tp0, tp1), max(tn0, tn1))), kPeakKeyMax);
             const int sp_first = gc_first_scale_power(key);
 
             // results of this lane's best pass so far (round 1 moves unresolved predictors two powers up)
@@ -441,7 +495,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 const int32_t half_q = (int32_t)(1u << (shift - 1));
                 const int32_t mul = (int32_t)(1u << sp_try);                        // 2^(shift-11)
                 // tm1 = diff + half - 1 = x*2048 + base_m - c0*p1 - c1*p2 ;  e1 = tm1 - half (sign bit = diff <= 0)
-                const int32_t base_m = wadd(bias_c, half_q) - 1;
+                const int32_t base_m = wadd(bias_c, half_q) - 1 - 32768 * 2048;
                 // guess + 1024 - 8*2^shift = c0*p1 + c1*p2 + base_g
                 const int32_t base_g = wsub(wsub(1024, (int32_t)(8u << shift)), bias_c);
                 const int lsh = 32 - shift;
@@ -461,16 +515,14 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 uint32_t nw0 = 0, nw1 = 0;
 #pragma unroll
                 for (int s = 0; s < 14; s++) {
-                    const int32_t wt = imad(x[s], 2048, base_m);
-                    const int32_t wh = imad(x[s], 2048, base_m - half_q);
+                    const int32_t wt = imad(x[s], 2048, base_m);   // x carries +32768: folded into base_m
                     const int32_t an = imad(r2, nc1, wt);          // r2 terms: one step off the chain
-                    const int32_t ah = imad(r2, nc1, wh);          // an - half
                     const int32_t gn = imad(r2, c1, base_g);
                     const int32_t tm1 = imad(r1, nc0, an);         // diff + half - 1          <- chain
-                    const int32_t e1 = imad(r1, nc0, ah);          // diff - 1: negative iff diff <= 0
                     const int32_t wf = imad(r1, c0, gn);           // guess + 1024 - 8*2^shift
-                    // round half toward zero: (diff + half - (diff > 0)) >> shift = (tm1 + (diff <= 0)) >> shift
-                    const int32_t t2 = tm1 + (int32_t)((uint32_t)e1 >> 31);
+                    // round half toward zero: (diff + half - (diff > 0)) >> shift = (tm1 + (diff <= 0)) >> shift.  diff <= 0
+                    // is tm1 < half, and for 0 <= tm1 < half both tm1 and tm1 + 1 shift to 0: only the SIGN of tm1 matters
+                    const int32_t t2 = tm1 + (int32_t)((uint32_t)tm1 >> 31);
                     const int32_t raw = sar(t2, shift);
                     const int32_t qb = __viaddmin_s32_relu(raw, 8, 15);        // clamp4(raw) + 8
                     const int32_t o = imad(qb, mul, wf >> 11);
@@ -484,7 +536,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                         raw_even = raw;
                     }
                     nearmin = min(nearmin, (uint32_t)imad(tm1, lmul, (int32_t)near_k));   // (tm1 << lsh) + near_k
-                    const int32_t miss = imad(ob, -1, x[s] + 32768);
+                    const int32_t miss = imad(ob, -1, x[s]);
                     const uint64_t sq = (uint64_t)((int64_t)miss * miss);
                     if (s & 1) e1s += sq; else e0 += sq;
                     const int byte = 1 + s / 2, bit = (byte & 3) * 8 + ((s & 1) ? 0 : 4);
@@ -505,22 +557,23 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
                 //   over > 248 <=>  rmax > 255 or rmin < -256   <=>  m >= 257
                 // big / huge (|raw| >= threshold) use m >= threshold, which can only err on the careful side.
                 const int32_t m = __viaddmax_s32(rmax, 1, -rmin);
-                const int32_t big_thr = 1 << (24 - shift), huge_thr = 1 << (29 - shift);
-                const uint32_t big = (uint32_t)(m >= big_thr);     // some |diff| >= 2^24 (or one short of it)
-                const uint32_t huge = (uint32_t)(m >= huge_thr);   // some |diff| >= 2^29
-                const uint32_t over_ge_240 = (uint32_t)(m >= 248);
-                const uint32_t over_gt_248 = (uint32_t)(m >= 257);
-                const uint32_t over_le_1 = (uint32_t)(m <= 9);
-                const uint32_t near = (uint32_t)(nearmin <= 2u * near_c) | over_ge_240;
+                const int32_t m_scaled = imad(m, mul, 0);                   // m * 2^(shift-11) <= 2^21
+                // predicates combined with non-short-circuit operators: compare-and-combine is one instruction each
+                const bool big = m_scaled >= (1 << 13);     // some |diff| >= 2^24 (or one short of it)
+                const bool huge = m_scaled >= (1 << 18);    // some |diff| >= 2^29
+                const bool over_ge_240 = m >= 248;
+                const bool over_gt_248 = m >= 257;
+                const bool over_le_1 = m <= 9;
+                const bool near = (nearmin <= 2u * near_c) | over_ge_240;
                 const bool take = !resolved;  // lanes of resolved predictors keep their round-0 result
-                const uint32_t live_take = valid & (uint32_t)(take && active);
-                const uint32_t inexact = live_take & (huge | (big & near));
-                const uint32_t bump = live_take & (uint32_t)(sp_try < 12) & over_gt_248;  // bump loop (:166-168)
+                const bool live_take = (valid != 0u) & take & active;
+                const bool inexact = live_take & (huge | (big & near));
+                const bool bump = live_take & (sp_try < 12) & over_gt_248;  // bump loop (:166-168)
                 // while (:170) fails; an idle half reports "done" so that it never forces a second round
-                const uint32_t term_now = active ? (valid & (over_le_1 | (uint32_t)(sp_try >= 12))) : 1u;
-                terminal = take ? term_now : terminal;
+                const bool term_now = !active | ((valid != 0u) & (over_le_1 | (sp_try >= 12)));
+                terminal = take ? (uint32_t)term_now : terminal;
                 term_bits = __ballot_sync(kFull, terminal != 0u);
-                trouble_bits |= __ballot_sync(kFull, (inexact | bump) != 0u);
+                trouble_bits |= __ballot_sync(kFull, inexact | bump);
 
                 const uint64_t nerr = e0 + e1s;
                 err = take ? nerr : err;
@@ -571,7 +624,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             if (trouble0 || trouble1) {
                 __syncwarp();  // the fast path's frame bytes are overwritten below by another lane of the warp
                 const bool mine = (half ? trouble1 : trouble0) && active;
-                const uint32_t redo = gc_slow_frame(frame, p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane, mine, out8);
+                const uint32_t redo = gc_slow_frame(&in_buf[warp][half][buf][i * kGcFrameSamples], p1_in - 32768, p2_in - 32768, c0, c1, sp_first, lane, mine, out8);
                 if (mine) packed = redo;
             }
             if (active) {
@@ -618,6 +671,10 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
             if (kMode == kGcCascade && need) truth_upto = seg_lo + done;
             if (kMode == kGcRunOn && need && !spliced && l16 == 0 && seg_hi < f_end)
                 atomicAdd(&sa.stats[2], 1ull);  // this boundary's segment end changed under its successor
+            if (kMode == kGcRunOn && need && l16 == 0) {  // run-on length statistics: maximum and a log2 histogram
+                atomicMax(&sa.stats[3], (unsigned long long)done);
+                atomicAdd(&sa.stats[4 + min(31 - __clz(max(done, 1)), 13)], 1ull);
+            }
         }
     }
 
@@ -723,7 +780,7 @@ void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16
     const int blocks = (tab.n_channels + per_block - 1) / per_block;
     if (sa.seg_count < 1) sa.seg_count = 1;
     if (sa.seg_count > kGcMaxSegments) sa.seg_count = kGcMaxSegments;
-    cudaMemsetAsync(sa.stats, 0, 4 * sizeof(unsigned long long), stream);
+    cudaMemsetAsync(sa.stats, 0, kGcStatWords * sizeof(unsigned long long), stream);
     gc_encode_kernel<kGcChain><<<dim3(blocks, sa.seg_count), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
     if (sa.seg_count > 1) {
         gc_encode_kernel<kGcRunOn><<<dim3(blocks, sa.seg_count - 1), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
