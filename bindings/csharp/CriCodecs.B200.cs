@@ -28,6 +28,7 @@ namespace VGAudio.Native
         public int TotalBandCount, BaseBandCount, StereoBandCount, HfrBandCount, BandsPerHfrGroup, HfrGroupCount;
         public int Bitrate;
         public int Looping, LoopStartFrame, LoopEndFrame, PreLoopSamples, PostLoopSamples;  // HcaInfo.cs:29-33
+        public int UseAthCurve;  // HcaInfo.cs:38 (old files: the decoder adds the ATH curve to the noise level)
     }
 
     internal static unsafe class VgAudioB200Cri

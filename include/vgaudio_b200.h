@@ -260,6 +260,10 @@ typedef struct vgb_hca_info {
     int32_t total_band_count, base_band_count, stereo_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
     int32_t bitrate;
     int32_t looping, loop_start_frame, loop_end_frame, pre_loop_samples, post_loop_samples; /* HcaInfo.cs:29-33 */
+    /* HcaInfo.UseAthCurve (HcaInfo.cs:38; set by HcaReader for version < 2.0 files without an ath chunk and for ath
+     * type 1, HcaReader.cs:116,201): the decoder adds ScaleAthCurve(sample_rate) (CriHcaFrame.cs:60-84) to the noise level
+     * when it derives resolutions (CriHcaPacking.cs:79-95).  vgb_hca_query / the encoder always write 0. */
+    int32_t use_ath_curve;
 } vgb_hca_info;
 
 /* CriHcaEncoder.Initialize (CriHcaEncoder.cs:61-114): stream parameters for one configuration, so the caller can

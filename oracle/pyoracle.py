@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.vgo_adx_decode.restype = None
         L.vgo_hca_init.argtypes = [vp, vp]
         L.vgo_hca_encode.argtypes = [vp, vp, vp, vp]
+        L.vgo_hca_encode_ath.argtypes = [vp, vp, vp, vp]
         L.vgo_hca_spectra.argtypes = [vp, vp, vp]
         L.vgo_hca_decode.argtypes = [vp, vp, vp]
         L.vgo_hca_unpack_ok.argtypes = [vp, vp]
@@ -194,7 +195,7 @@ class HcaInfo(C.Structure):
         "header_size", "frame_size", "min_resolution", "max_resolution", "track_count", "channel_config",
         "total_band_count", "base_band_count", "stereo_band_count", "hfr_band_count", "bands_per_hfr_group",
         "hfr_group_count", "bitrate", "looping", "loop_start_frame", "loop_end_frame", "pre_loop_samples",
-        "post_loop_samples")]
+        "post_loop_samples", "use_ath_curve")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -263,13 +264,15 @@ def hca_init(params: HcaParams) -> HcaInfo:
     return info
 
 
-def hca_encode(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None):
-    """CriHcaFormat.EncodeFromPcm16 for one stream -> (HcaInfo, frames[frame_count, frame_size])."""
+def hca_encode(channels, sample_rate=48000, quality=2, bitrate=0, limit_bitrate=False, loop=None, ath=False):
+    """CriHcaFormat.EncodeFromPcm16 for one stream -> (HcaInfo, frames[frame_count, frame_size]).
+    ath=True: the test helper vgo_hca_encode_ath (a stream for the decoder's UseAthCurve path)."""
     arrs, tab = _chan_table(channels)
     p = hca_params(arrs, sample_rate, quality, bitrate, limit_bitrate, loop)
     info = hca_init(p)
     frames = np.zeros((info.frame_count, info.frame_size), dtype=np.uint8)
-    rc = lib().vgo_hca_encode(tab, C.byref(p), C.byref(info), frames.ctypes.data)
+    fn = lib().vgo_hca_encode_ath if ath else lib().vgo_hca_encode
+    rc = fn(tab, C.byref(p), C.byref(info), frames.ctypes.data)
     if rc:
         raise ValueError(f"vgo_hca_encode failed: {rc}")
     return info, frames

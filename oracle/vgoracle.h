@@ -99,9 +99,12 @@ typedef struct vgo_hca_info { /* HcaInfo.cs:5-48, the fields the codec uses */
     int32_t total_band_count, base_band_count, stereo_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
     int32_t bitrate;
     int32_t looping, loop_start_frame, loop_end_frame, pre_loop_samples, post_loop_samples; /* HcaInfo.cs:29-33 */
+    int32_t use_ath_curve; /* HcaInfo.cs:38: decode side only (old files); the encoder always writes 0 */
 } vgo_hca_info;
 int vgo_hca_init(const vgo_hca_params *p, vgo_hca_info *info_out);              /* CriHcaEncoder.Initialize :61-114 */
 int vgo_hca_encode(const int16_t *const *pcm, const vgo_hca_params *p, vgo_hca_info *info_out, uint8_t *frames_out);
+/* test helper (NOT in the reference): a well-formed stream whose resolutions use the ATH curve, for the decoder's ATH path */
+int vgo_hca_encode_ath(const int16_t *const *pcm, const vgo_hca_params *p, vgo_hca_info *info_out, uint8_t *frames_out);
 int vgo_hca_spectra(const int16_t *const *pcm, const vgo_hca_params *p, double *spectra_out);
 int vgo_hca_decode(const vgo_hca_info *h, const uint8_t *frames, int16_t *const *pcm_out); /* CriHcaDecoder.Decode :11-25 */
 int vgo_hca_unpack_ok(const vgo_hca_info *h, const uint8_t *frames);             /* test helper: all frames well-formed */

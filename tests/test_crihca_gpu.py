@@ -96,6 +96,46 @@ def test_decode_bit_exact_with_oracle(vg, oracle, nch, quality):
             assert np.sqrt(((got - ref) ** 2).mean()) < 0.25 * np.sqrt((ref ** 2).mean())
 
 
+@pytest.mark.parametrize("nch,rate,quality", [(1, 48000, 2), (2, 44100, 2), (1, 22050, 5), (2, 32000, 4), (1, 8000, 1)])
+def test_decode_old_streams_with_the_ath_curve(vg, oracle, nch, rate, quality):
+    """HcaInfo.UseAthCurve (version < 2.0 files, HcaReader.cs:116,201): resolutions are derived from
+    athCurve[band] + noise level (CriHcaPacking.cs:79-95, CriHcaFrame.ScaleAthCurve :60-84).  The reference encoder never
+    writes such a stream, so the well-formed input comes from the oracle's test helper; decoding it WITHOUT the flag
+    must not give the same PCM (the curve really is applied), decoding it with the flag must match the oracle."""
+    import copy
+
+    streams = _streams(2, nch, 12000, first=520)
+    pairs = [oracle.hca_encode(st, rate, quality, ath=True) for st in streams]
+    infos = []
+    for o_info, _ in pairs:
+        info = vg.crihca.query(vg.crihca.CriHcaParameters(quality=quality, channel_count=nch, sample_rate=rate, sample_count=12000))
+        assert info.use_ath_curve == 0  # CriHcaEncoder.Initialize never sets it
+        assert info.frame_size == o_info.frame_size and info.frame_count == o_info.frame_count
+        info.use_ath_curve = 1
+        infos.append(info)
+    frames = [f for _, f in pairs]
+    pcm = vg.crihca.decode_batch(infos, frames)
+    for s in range(2):
+        o_info = pairs[s][0]
+        assert o_info.use_ath_curve == 1
+        want = oracle.hca_decode(o_info, frames[s])
+        got = np.stack(pcm[s])
+        assert np.array_equal(got, want), f"stream {s}: {int((got != want).sum())} samples differ"
+        ref = np.stack(streams[s]).astype(np.float64)
+        if quality <= 2:
+            assert np.sqrt(((got - ref) ** 2).mean()) < 0.35 * np.sqrt((ref ** 2).mean())
+    plain = copy.copy(infos[0])
+    plain.use_ath_curve = 0
+    try:
+        other = np.stack(vg.crihca.decode(plain, frames[0]))
+        assert not np.array_equal(other, np.stack(pcm[0]))
+    except vg.VgbError:
+        pass  # parsed with the wrong resolutions the frame may also be malformed
+    # mixed flags in one call are rejected
+    with pytest.raises(vg.VgbError):
+        vg.crihca.decode_batch([infos[0], plain], frames)
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 1023, 1024, 1025, 2047, 5000])
 def test_decode_edge_lengths_and_ragged(vg, oracle, n):
     streams = [[synth.channel(60 + i, max(n + 17 * i, 1))[:n + 17 * i]] for i in range(4)]

@@ -155,3 +155,22 @@ def test_non_looping_streaming_front_end_equals_plain_windows(oracle):
     assert info.frame_count == (5000 + 128 + 1023) // 1024 and info.inserted_samples == 128
     y = oracle.hca_decode(info, frames)[0].astype(np.float64)
     assert np.sqrt(((y - x) ** 2).mean()) < 0.25 * np.sqrt((x.astype(np.float64) ** 2).mean())
+
+
+def test_ath_curve_stream_round_trips(oracle):
+    """HcaInfo.UseAthCurve (HcaInfo.cs:38): with the curve, resolutions come from athCurve[band] + noise level on both
+    sides (CriHcaPacking.cs:79-95).  ScaleAthCurve (CriHcaFrame.cs:60-84) resamples the 41856 Hz table: at that rate the
+    index advances by 5.1 entries per band, above ~43 kHz * 654/... the tail is 0xff.  The helper stream must decode
+    close to its input with the flag and differently without it."""
+    from vgaudio_b200 import synth  # data generation only
+
+    pcm = [synth.channel(41, 9000, degenerate=False)]
+    info, frames = oracle.hca_encode(pcm, 48000, 2, ath=True)
+    assert info.use_ath_curve == 1
+    assert oracle.hca_unpack_ok(info, frames)
+    dec = oracle.hca_decode(info, frames)
+    ref = np.asarray(pcm[0], dtype=np.float64)
+    assert np.sqrt(((dec[0] - ref) ** 2).mean()) < 0.35 * np.sqrt((ref ** 2).mean())
+    plain_info, plain_frames = oracle.hca_encode(pcm, 48000, 2)
+    assert plain_info.use_ath_curve == 0
+    assert not np.array_equal(plain_frames, frames)

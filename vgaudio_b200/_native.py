@@ -48,7 +48,7 @@ class VgbHcaInfo(C.Structure):
         "header_size", "frame_size", "min_resolution", "max_resolution", "track_count", "channel_config",
         "total_band_count", "base_band_count", "stereo_band_count", "hfr_band_count", "bands_per_hfr_group",
         "hfr_group_count", "bitrate", "looping", "loop_start_frame", "loop_end_frame", "pre_loop_samples",
-        "post_loop_samples")]
+        "post_loop_samples", "use_ath_curve")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

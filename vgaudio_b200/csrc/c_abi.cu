@@ -1357,6 +1357,22 @@ int32_t hca_initialize(const vgb_hca_params &p, vgb_hca_info &h, HcaVirtual *vir
 }
 
 // CriHcaFrame.GetChannelTypes (CriHcaFrame.cs:34-52)
+// CriHcaFrame.cs:31 + ScaleAthCurve :60-84: the ATH curve (tabulated for 41856 Hz) resampled to the stream's rate; all
+// zero unless HcaInfo.UseAthCurve (old files only; the encoder never sets it, so the encode entry points leave it zero).
+void hca_fill_ath(const vgb_hca_info &h, uint8_t ath[128])
+{
+    std::memset(ath, 0, 128);
+    if (!h.use_ath_curve) return;
+    int acc = 0, i = 0;
+    for (; i < 128; i++) {
+        acc += h.sample_rate;
+        const int index = acc >> 13;
+        if (index >= (int)sizeof kHcaAthCurve) break;
+        ath[i] = kHcaAthCurve[index];
+    }
+    for (; i < 128; i++) ath[i] = 0xff;
+}
+
 void hca_channel_types(const vgb_hca_info &h, int32_t types[8])
 {
     static const int t2[] = {1, 2}, t3[] = {1, 2, 0}, t4a[] = {1, 2, 0, 0}, t4b[] = {1, 2, 1, 2}, t5a[] = {1, 2, 0, 0, 0},
@@ -1527,6 +1543,7 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     cfg.bands_per_hfr_group = h0.bands_per_hfr_group;
     cfg.hfr_group_count = h0.hfr_group_count;
     hca_channel_types(h0, cfg.channel_type);
+    hca_fill_ath(h0, cfg.ath);
 
     std::vector<HcaStream> streams(n_streams);
     std::vector<int64_t> in_off((size_t)n_streams * nch), in_len((size_t)n_streams * nch), out_off(n_streams), out_len(n_streams);
@@ -1609,6 +1626,8 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
             b.hfr_band_count != h0.hfr_band_count || b.bands_per_hfr_group != h0.bands_per_hfr_group ||
             b.hfr_group_count != h0.hfr_group_count || b.track_count != h0.track_count || b.channel_config != h0.channel_config)
             return fail(VGB_E_ARG, "stream %d: all streams of one call must share the band layout and frame size", s);
+        if ((b.use_ath_curve != 0) != (h0.use_ath_curve != 0) || (b.use_ath_curve && b.sample_rate != h0.sample_rate))
+            return fail(VGB_E_ARG, "stream %d: all streams of one call must share UseAthCurve (and then the sample rate)", s);
         if (b.sample_count < 0 || b.frame_count < 0 || b.inserted_samples < 0) return fail(VGB_E_ARG, "stream %d: negative count", s);
     }
     if (h0.frame_size < 8 || h0.frame_size > 0xffff) return fail(VGB_E_ARG, "frame_size out of range");
@@ -1631,6 +1650,7 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
     cfg.bands_per_hfr_group = h0.bands_per_hfr_group;
     cfg.hfr_group_count = h0.hfr_group_count;
     hca_channel_types(h0, cfg.channel_type);
+    hca_fill_ath(h0, cfg.ath);
 
     std::vector<HcaStream> streams(n_streams);
     std::vector<int64_t> in_off(n_streams), in_len(n_streams), out_off((size_t)n_streams * nch), out_len((size_t)n_streams * nch);
@@ -1705,6 +1725,30 @@ int32_t interleave_check(int32_t n_items, int32_t count, int64_t in_size, int32_
 }
 }  // namespace
 
+// Launches with g_ctx.mu already held (shared by the *_dev entry points and the host-pointer wrappers, which keep the
+// lock across staging, launch and read-back: every entry point may reserve() - free and reallocate - the shared slabs).
+static int32_t interleave_locked(const void *d_in, int64_t in_channel_stride, int64_t in_item_stride, void *d_out, int64_t out_item_stride,
+                                 int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, cudaStream_t st)
+{
+    tick(8, true, st);
+    CUDA_TRY(launch_interleave(d_in, in_channel_stride, in_item_stride, d_out, out_item_stride, n_items, count, in_size, interleave_size,
+                               out_size, st));
+    tick(8, false, st);
+    g_ctx.launches += 1;
+    return VGB_OK;
+}
+
+static int32_t deinterleave_locked(const void *d_in, int64_t in_item_stride, void *d_out, int64_t out_channel_stride, int64_t out_item_stride,
+                                   int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, cudaStream_t st)
+{
+    tick(9, true, st);
+    CUDA_TRY(launch_deinterleave(d_in, in_item_stride, d_out, out_channel_stride, out_item_stride, n_items, count, in_size,
+                                 interleave_size, out_size, st));
+    tick(9, false, st);
+    g_ctx.launches += 1;
+    return VGB_OK;
+}
+
 int32_t vgb_interleave_dev(const void *d_in, int64_t in_channel_stride, int64_t in_item_stride, void *d_out, int64_t out_item_stride,
                            int32_t n_items, int32_t count, int64_t in_size, int32_t interleave_size, int64_t out_size, void *cuda_stream)
 {
@@ -1714,13 +1758,8 @@ int32_t vgb_interleave_dev(const void *d_in, int64_t in_channel_stride, int64_t 
     if (!d_in || !d_out) return fail(VGB_E_ARG, "NULL argument");
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    tick(8, true, st);
-    CUDA_TRY(launch_interleave(d_in, in_channel_stride, in_item_stride, d_out, out_item_stride, n_items, count, in_size, interleave_size,
-                               out_size, st));
-    tick(8, false, st);
-    g_ctx.launches += 1;
-    return VGB_OK;
+    return interleave_locked(d_in, in_channel_stride, in_item_stride, d_out, out_item_stride, n_items, count, in_size, interleave_size,
+                             out_size, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int32_t vgb_deinterleave_dev(const void *d_in, int64_t in_item_stride, void *d_out, int64_t out_channel_stride, int64_t out_item_stride,
@@ -1732,13 +1771,8 @@ int32_t vgb_deinterleave_dev(const void *d_in, int64_t in_item_stride, void *d_o
     if (!d_in || !d_out) return fail(VGB_E_ARG, "NULL argument");
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    tick(9, true, st);
-    CUDA_TRY(launch_deinterleave(d_in, in_item_stride, d_out, out_channel_stride, out_item_stride, n_items, count, in_size,
-                                 interleave_size, out_size, st));
-    tick(9, false, st);
-    g_ctx.launches += 1;
-    return VGB_OK;
+    return deinterleave_locked(d_in, in_item_stride, d_out, out_channel_stride, out_item_stride, n_items, count, in_size, interleave_size,
+                               out_size, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int32_t vgb_interleave(const uint8_t *const *inputs, int32_t count, int32_t in_size, int32_t interleave_size, int32_t out_size,
@@ -1751,17 +1785,14 @@ int32_t vgb_interleave(const uint8_t *const *inputs, int32_t count, int32_t in_s
     for (int c = 0; c < count; c++)
         if (!inputs[c] && in_size > 0) return fail(VGB_E_ARG, "inputs[%d] is NULL", c);
     const int64_t pitch = (int64_t)align_up((size_t)in_size, 16), out_bytes = (int64_t)out_size * count;
-    {
-        std::lock_guard<std::mutex> lock(g_ctx.mu);
-        VGB_TRY(ensure_ready_locked());
-        VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
-        VGB_TRY(g_ctx.adpcm.reserve((size_t)out_bytes + 16));
-        for (int c = 0; c < count; c++)
-            if (in_size > 0)
-                CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(g_ctx.pcm.p) + c * pitch, inputs[c], (size_t)in_size, cudaMemcpyHostToDevice, g_ctx.stream));
-    }
-    VGB_TRY(vgb_interleave_dev(g_ctx.pcm.p, pitch, 0, g_ctx.adpcm.p, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);  // one lock for staging, launch and read-back
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)out_bytes + 16));
+    for (int c = 0; c < count; c++)
+        if (in_size > 0)
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(g_ctx.pcm.p) + c * pitch, inputs[c], (size_t)in_size, cudaMemcpyHostToDevice, g_ctx.stream));
+    VGB_TRY(interleave_locked(g_ctx.pcm.p, pitch, 0, g_ctx.adpcm.p, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
     CUDA_TRY(cudaMemcpyAsync(output, g_ctx.adpcm.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
     CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
     return VGB_OK;
@@ -1781,15 +1812,12 @@ int32_t vgb_deinterleave(const uint8_t *input, int32_t length, int32_t interleav
     for (int c = 0; c < count; c++)
         if (!outputs[c]) return fail(VGB_E_ARG, "outputs[%d] is NULL", c);
     const int64_t pitch = (int64_t)align_up((size_t)out_size, 16);
-    {
-        std::lock_guard<std::mutex> lock(g_ctx.mu);
-        VGB_TRY(ensure_ready_locked());
-        VGB_TRY(g_ctx.adpcm.reserve((size_t)length + 16));
-        VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
-        if (length > 0) CUDA_TRY(cudaMemcpyAsync(g_ctx.adpcm.p, input, (size_t)length, cudaMemcpyHostToDevice, g_ctx.stream));
-    }
-    VGB_TRY(vgb_deinterleave_dev(g_ctx.adpcm.p, 0, g_ctx.pcm.p, pitch, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);  // one lock for staging, launch and read-back
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(g_ctx.adpcm.reserve((size_t)length + 16));
+    VGB_TRY(g_ctx.pcm.reserve((size_t)pitch * count + 16));
+    if (length > 0) CUDA_TRY(cudaMemcpyAsync(g_ctx.adpcm.p, input, (size_t)length, cudaMemcpyHostToDevice, g_ctx.stream));
+    VGB_TRY(deinterleave_locked(g_ctx.adpcm.p, 0, g_ctx.pcm.p, pitch, 0, 1, count, in_size, interleave_size, out_size, g_ctx.stream));
     for (int c = 0; c < count; c++)
         CUDA_TRY(cudaMemcpyAsync(outputs[c], static_cast<char *>(g_ctx.pcm.p) + c * pitch, (size_t)out_size, cudaMemcpyDeviceToHost, g_ctx.stream));
     CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));

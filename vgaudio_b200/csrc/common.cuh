@@ -99,6 +99,7 @@ struct HcaConfig {
     int32_t channel_count, frame_size;
     int32_t base_band_count, stereo_band_count, total_band_count, hfr_band_count, bands_per_hfr_group, hfr_group_count;
     int32_t channel_type[8];  // 0 Discrete, 1 StereoPrimary, 2 StereoSecondary
+    uint8_t ath[128];         // decoder: CriHcaFrame.AthCurve (CriHcaFrame.cs:31), all zero unless HcaInfo.UseAthCurve
 };
 
 struct HcaStream {

@@ -638,7 +638,7 @@ hca_decode_parse_kernel(const uint8_t *__restrict__ frames, const HcaStream *__r
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_lens64[16], s_vals64[16];
-    __shared__ uint8_t s_maxbits[16], s_curve[64];
+    __shared__ uint8_t s_maxbits[16], s_curve[64], s_ath[128];
     uint8_t *sres = smem_raw;  // [nch][128][kParseThreads] resolutions of this thread's frame (thread fastest)
     const int nch = cfg.channel_count, tid = threadIdx.x;
     if (tid < 16) {
@@ -653,6 +653,7 @@ hca_decode_parse_kernel(const uint8_t *__restrict__ frames, const HcaStream *__r
         s_maxbits[tid] = T.quantized_max_bits[tid];
     }
     if (tid < 59) s_curve[tid] = T.scale_to_resolution[tid];
+    for (int b = tid; b < 128; b += kParseThreads) s_ath[b] = cfg.ath[b];
     __syncthreads();
 
     const int64_t fi = (int64_t)blockIdx.x * kParseThreads + tid;
@@ -722,8 +723,8 @@ hca_decode_parse_kernel(const uint8_t *__restrict__ frames, const HcaStream *__r
             }
             prev = sf;
             int res = 0;
-            if (b < coded && sf != 0) {  // CalculateResolution (CriHcaPacking.cs:60-69), ATH curve unused
-                int pos = (b < eval_boundary ? noise_level - 1 : noise_level) - 5 * sf / 2 + 2;
+            if (b < coded && sf != 0) {  // CalculateResolution (CriHcaPacking.cs:60-69) of athCurve[b] + noise (:86-94)
+                int pos = s_ath[b] + (b < eval_boundary ? noise_level - 1 : noise_level) - 5 * sf / 2 + 2;
                 pos = min(max(pos, 0), 58);
                 res = s_curve[pos];
             }
