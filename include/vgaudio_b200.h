@@ -96,7 +96,10 @@ int32_t vgb_gcadpcm_encode_batch(const int16_t *const *pcm, const int32_t *n_sam
 
 /* GcAdpcmFormat.ToPcm16's loop body (GcAdpcmFormat.cs:45-48 -> GcAdpcmChannel.GetPcmAudio, GcAdpcmChannel.cs:57-60
  * -> GcAdpcmDecoder.Decode, GcAdpcmDecoder.cs:10-54).  n_bytes[c] is the length of adpcm[c]; params[c].sample_count
- * == -1 decodes ByteCountToSampleCount(n_bytes[c]) samples.  pcm_out[c] receives sample_count samples. */
+ * == -1 decodes ByteCountToSampleCount(n_bytes[c]) samples.  pcm_out[c] receives sample_count samples.
+ * VGB_E_DATA: a frame header selects a predictor outside 0..7 (IndexOutOfRangeException at GcAdpcmDecoder.cs:31-32);
+ * the message names the lowest such channel.  The device-resident variant below cannot report it without a
+ * synchronisation: there the lookup wraps (predictor & 7). */
 int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
                                  const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out);
 
@@ -236,7 +239,8 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
                              vgb_progress_cb cb, void *user);
 
 /* CriAdxCodec.Decode(byte[] adpcm, int sampleCount, CriAdxParameters config) (CriAdxCodec.cs:9-54).
- * n_bytes[c] = length of adpcm[c]; pcm_out[c] receives sample_count[c] samples. */
+ * n_bytes[c] = length of adpcm[c]; pcm_out[c] receives sample_count[c] samples.
+ * VGB_E_DATA: a Fixed-type frame selects a filter outside 0..3 (IndexOutOfRangeException at CriAdxCodec.Coefs, :186-191). */
 int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
                              const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out);
 

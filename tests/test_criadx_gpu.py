@@ -72,6 +72,25 @@ def test_decode_hostile_streams(vg, oracle):
             assert np.array_equal(dec[c], want), (typ, c)
 
 
+def test_fixed_type_rejects_filter_numbers_past_the_table(vg, oracle):
+    """Fixed-type frames carry their filter number in the top three bits; CriAdxCodec.Coefs has four rows (:186-191), so
+    4..7 is an IndexOutOfRangeException in the reference: VGB_E_DATA here.  0..3 decode like the oracle."""
+    rng = np.random.default_rng(19)
+    n_ch, frames = 12, 40
+    adpcm = rng.integers(0, 256, (n_ch, frames * 18), dtype=np.uint8)
+    adpcm[:, 0::18] &= 0x7F   # filter numbers 0..3
+    cfgs = [_cfg(vg, type=2, history=0, version=3 + (c % 2)) for c in range(n_ch)]
+    dec = vg.criadx.decode_batch(adpcm, frames * 32, cfgs)
+    for c in range(n_ch):
+        assert np.array_equal(dec[c], oracle.adx_decode(adpcm[c], frames * 32, 48000, 500, 18, cfgs[c].version, 0, 0, 2)), c
+    for ch, frame in [(0, 0), (11, 39), (6, 20)]:
+        bad = adpcm.copy()
+        bad[ch, frame * 18] |= 0x80
+        with pytest.raises(vg.VgbError) as e:
+            vg.criadx.decode_batch(bad, frames * 32, cfgs)
+        assert e.value.code == -2 and f"channel {ch}:" in str(e.value)
+
+
 def test_errors(vg):
     with pytest.raises(vg.VgbError):   # empty v4 channel: the reference throws IndexOutOfRangeException (CriAdxCodec.cs:71)
         vg.criadx.encode_batch([np.zeros(0, dtype=np.int16)], [_cfg(vg)])

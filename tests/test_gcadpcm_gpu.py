@@ -135,6 +135,28 @@ def test_decode_hostile_streams(vg, oracle):
         assert np.array_equal(dec[c], want), c
 
 
+def test_decode_rejects_predictor_indices_past_the_table(vg):
+    """coefs[predictor * 2] with predictor 8..15 is an IndexOutOfRangeException in GcAdpcmDecoder.Decode (:31-32): the
+    batch call reports VGB_E_DATA (and names the lowest such channel) instead of decoding garbage."""
+    rng = np.random.default_rng(4)
+    adpcm = rng.integers(0, 256, (40, 64 * 8), dtype=np.uint8)
+    adpcm[:, ::8] &= 0x7F
+    coefs = rng.integers(-2048, 2048, (40, 16)).astype(np.int16)
+    cfgs = [vg.gcadpcm.GcAdpcmParameters(64 * 14)] * 40
+    vg.gcadpcm.decode_batch(adpcm, coefs, cfgs)  # clean
+    for ch, frame in [(33, 63), (7, 0), (39, 17)]:
+        bad = adpcm.copy()
+        bad[ch, frame * 8] |= 0x80
+        with pytest.raises(vg.VgbError) as e:
+            vg.gcadpcm.decode_batch(bad, coefs, cfgs)
+        assert e.value.code == -2 and f"channel {ch}:" in str(e.value)
+    bad = adpcm.copy()
+    bad[5, 8] |= 0x80
+    with pytest.raises(vg.VgbError) as e:  # the seek-table rebuild decodes the same stream
+        vg.gcadpcm.seek_table_and_loop_context(list(bad), coefs, [64 * 14] * 40, 100, [10] * 40)
+    assert e.value.code == -2
+
+
 def test_dsp_encode_frame_independent_frames(vg, oracle):
     rng = np.random.default_rng(9)
     n = 300

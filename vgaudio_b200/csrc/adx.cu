@@ -222,7 +222,7 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
 }
 
 __global__ void __launch_bounds__(kAdxThreads)
-adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restrict__ tab, int n_channels,
+adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restrict__ tab, int n_channels, int32_t *__restrict__ status,
                   int16_t *__restrict__ pcm)
 {
     __shared__ __align__(16) uint4 dec_ring[kAdxStages][9][kAdxThreads];  // [stage][16-byte chunk of the group][thread]
@@ -236,6 +236,7 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
     const int frame_count = div_round_up(sample_count, spf);
     const bool v4 = c.version == 4;
     int32_t hist1 = c.history, hist2 = c.history;  // :16-17
+    uint32_t bad_filter = 0;                       // OR of the header bytes of Fixed-type frames
     int current = 0;
     int start_sample = c.padding > 0 ? c.padding % spf : 0;       // :21
     int64_t in = (int64_t)(c.padding / spf) * c.frame_size;      // :22
@@ -271,6 +272,7 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
                 int32_t c0 = c.coef0, c1 = c.coef1;
                 if (c.type == 2) {
                     const int k = ((int)((b0 >> 4) & 0xF) >> 1) & 3;
+                    bad_filter |= b0;  // bit 7: filter number 4..7
                     c0 = k == 0 ? 0 : (k == 1 ? 0x0F00 : (k == 2 ? 0x1CC0 : 0x1880));
                     c1 = k == 0 ? 0 : (k == 1 ? 0 : (k == 2 ? (int16_t)0xF300 : (int16_t)0xF240));
                 }
@@ -327,6 +329,7 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
         int32_t c0 = c.coef0, c1 = c.coef1;
         if (c.type == 2) {  // CriAdxCodec.Coefs (:186-191); the reference throws for filter numbers 4..7
             const int k = filter_num & 3;
+            bad_filter |= b0;
             c0 = k == 0 ? 0 : (k == 1 ? 0x0F00 : (k == 2 ? 0x1CC0 : 0x1880));
             c1 = k == 0 ? 0 : (k == 1 ? 0 : (k == 2 ? (int16_t)0xF300 : (int16_t)0xF240));
         }
@@ -347,6 +350,8 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
         }
         start_sample = 0;
     }
+    // CriAdxCodec.Coefs[filterNum] (:186-191) has four rows: the reference throws IndexOutOfRangeException for 4..7
+    if ((bad_filter & 0x80u) && status) atomicMin(status, ch);
     // `new short[sampleCount]` is zero-initialised: samples the padding logic never produces stay 0 (:14,:31-33)
     for (; current < sample_count; current++) dst[current] = 0;
 }
@@ -358,10 +363,10 @@ void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels
     adx_encode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out);
 }
 
-void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream)
+void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, int32_t *status, cudaStream_t stream)
 {
     if (n_channels <= 0) return;
-    adx_decode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(adpcm, tab, n_channels, pcm);
+    adx_decode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(adpcm, tab, n_channels, status, pcm);
 }
 
 }  // namespace vgb

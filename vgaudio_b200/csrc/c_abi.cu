@@ -167,6 +167,7 @@ struct GcLayout {
 struct GcWorkspace {
     size_t off_pcm_off, off_adpcm_off, off_rec_off, off_n_samples, off_enc_count, off_hist, off_records, off_mask;
     size_t off_trace, off_used_start, off_stats;  // time-parallel encode bookkeeping (GcSegArgs)
+    size_t off_status;                            // decode: first channel with an out-of-range predictor index
     size_t table_bytes;
     size_t total;
 };
@@ -189,6 +190,7 @@ GcWorkspace carve(int64_t rec_total_frames, int32_t n_channels)
     w.off_trace = take((size_t)rec_total_frames * 4);
     w.off_used_start = take(n * kGcMaxSegments * 4);
     w.off_stats = take(kGcStatWords * 8);
+    w.off_status = take(16);
     w.total = o;
     return w;
 }
@@ -206,6 +208,7 @@ GcChannelTable table_view(void *ws, const GcWorkspace &w, int32_t n_channels)
     t.n_samples = reinterpret_cast<const int32_t *>(b + w.off_n_samples);
     t.enc_count = reinterpret_cast<const int32_t *>(b + w.off_enc_count);
     t.hist = reinterpret_cast<int16_t *>(b + w.off_hist);
+    t.status = reinterpret_cast<int32_t *>(b + w.off_status);
     t.n_channels = n_channels;
     return t;
 }
@@ -345,6 +348,7 @@ int32_t run_gc_decode(const uint8_t *d_adpcm, const GcLayout &lay, const int16_t
     VGB_TRY(upload_tables(lay, w, d_ws, stream));
     if (lay.n_channels == 0) return VGB_OK;
     GcChannelTable tab = table_view(d_ws, w, lay.n_channels);
+    CUDA_TRY(cudaMemsetAsync(tab.status, 0x7f, 4, stream));  // "no channel": any index is smaller
     tick(3, true, stream);
     launch_gc_decode(d_adpcm, tab, d_coefs, d_pcm, lay.max_frames, 0, INT_MAX, stream);
     tick(3, false, stream);
@@ -754,7 +758,12 @@ int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_b
                           static_cast<int16_t *>(g_ctx.pcm.p), g_ctx.ws.p, w, st));
     for (int c = 0; c < n_channels; c++) { off_b[c] = lay.pcm_off[c] * 2; len_b[c] = (int64_t)counts[c] * 2; }
     VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), off_b, len_b, st));
+    int32_t bad_channel = INT_MAX;
+    CUDA_TRY(cudaMemcpyAsync(&bad_channel, static_cast<char *>(g_ctx.ws.p) + w.off_status, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    // coefs[predictor * 2] with predictor 8..15 is an IndexOutOfRangeException in GcAdpcmDecoder.Decode (:31-32)
+    if (bad_channel >= 0 && bad_channel < n_channels)
+        return fail(VGB_E_DATA, "channel %d: a frame header selects a predictor outside 0..7", bad_channel);
     return VGB_OK;
 }
 
@@ -819,6 +828,7 @@ int32_t vgb_gcadpcm_seek_context_batch(const uint8_t *const *adpcm, const int32_
     CUDA_TRY(cudaMemsetAsync(misc, 0, (size_t)slab * 2, st));  // entry 0 and absent history samples are zero
     VGB_TRY(upload_tables(lay, w, g_ctx.ws.p, st));
     GcChannelTable tab = table_view(g_ctx.ws.p, w, lay.n_channels);
+    CUDA_TRY(cudaMemsetAsync(tab.status, 0x7f, 4, st));
     launch_gc_taps(static_cast<const uint8_t *>(g_ctx.adpcm.p), tab, static_cast<const int16_t *>(g_ctx.coefs.p),
                    reinterpret_cast<const GcTapChannel *>(misc + o_taps), reinterpret_cast<int16_t *>(misc), lay.max_frames, st);
     g_ctx.launches += lay.max_frames > 0 ? 1 : 0;
@@ -829,7 +839,11 @@ int32_t vgb_gcadpcm_seek_context_batch(const uint8_t *const *adpcm, const int32_
         host_slab.resize((size_t)slab);
         CUDA_TRY(cudaMemcpyAsync(host_slab.data(), misc, (size_t)slab * 2, cudaMemcpyDeviceToHost, st));
     }
+    int32_t bad_channel = INT_MAX;
+    CUDA_TRY(cudaMemcpyAsync(&bad_channel, tab.status, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad_channel >= 0 && bad_channel < n_channels)  // the reference's EnsurePcmDecoded would throw inside Decode
+        return fail(VGB_E_DATA, "channel %d: a frame header selects a predictor outside 0..7", bad_channel);
     if (loop_context_out)
         for (int c = 0; c < n_channels; c++) {
             int16_t *ctx = loop_context_out + (size_t)c * 3;
@@ -1200,17 +1214,25 @@ int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes
     cudaStream_t st = g_ctx.stream;
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
-    VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
+    const size_t o_status = align_up(tab.size() * sizeof(AdxChannel), 256);
+    VGB_TRY(g_ctx.misc.reserve(o_status + 16));
+    int32_t *d_status = reinterpret_cast<int32_t *>(static_cast<char *>(g_ctx.misc.p) + o_status);
     VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, adpcm, in_len, st));
     CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0x7f, 4, st));
     tick(5, true, st);
     launch_adx_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
-                      static_cast<int16_t *>(g_ctx.pcm.p), st);
+                      static_cast<int16_t *>(g_ctx.pcm.p), d_status, st);
     tick(5, false, st);
     g_ctx.launches += 1;
     CUDA_TRY(cudaGetLastError());
     VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
+    int32_t bad_channel = INT_MAX;
+    CUDA_TRY(cudaMemcpyAsync(&bad_channel, d_status, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    // CriAdxCodec.Coefs[filterNum] (:186-191) has four rows: IndexOutOfRangeException in the reference
+    if (bad_channel >= 0 && bad_channel < n_channels)
+        return fail(VGB_E_DATA, "channel %d: a Fixed-type frame selects a filter outside 0..3", bad_channel);
     return VGB_OK;
 }
 

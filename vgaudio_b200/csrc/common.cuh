@@ -52,6 +52,7 @@ struct GcChannelTable {
     const int32_t *n_samples;  // [ch] PCM length (coefficient analysis length / decode sample count)
     const int32_t *enc_count;  // [ch] samples to encode (<= n_samples)
     int16_t *hist;             // [ch][2] running history: [0] = hist1 (newest), [1] = hist2
+    int32_t *status;           // decode: lowest channel index whose stream selects a predictor 8..15 (INT_MAX: none); may be null
     int32_t n_channels;
 };
 

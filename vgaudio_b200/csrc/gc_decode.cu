@@ -41,14 +41,17 @@ __device__ __forceinline__ int32_t dec_imad(int32_t a, int32_t b, int32_t c)
 
 struct DecState {
     int32_t hb1, hb2;  // biased history (+32768): newest, older
+    uint32_t heads;    // OR of the frame headers seen: bit 7 set = some frame selected a predictor 8..15
 };
 
 // 14 samples of one frame (8 bytes in w0,w1; byte 0 = header).  out[0..6] = the 14 samples, two per word.
 __device__ __forceinline__ void gc_decode_frame(uint32_t w0, uint32_t w1, const uint32_t *coef_pairs, DecState &st, uint32_t *out)
 {
     const uint32_t head = w0 & 0xFFu;
+    st.heads |= w0;
     const int sp = (int)(head & 0xFu);  // scale = (1 << sp) * 2048 (GcAdpcmDecoder.cs:28)
-    // a hostile header may select pairs 8..15: the reference would throw; we wrap to stay in bounds
+    // a hostile header may select pairs 8..15: the reference throws IndexOutOfRangeException; the lookup wraps to stay
+    // in bounds and the channel is reported through tab.status (the batch call then returns VGB_E_DATA)
     const uint32_t pair = coef_pairs[(head >> 4) & 7u];
     const int32_t c1 = (int32_t)(int16_t)(pair & 0xFFFFu), c2 = (int32_t)pair >> 16;
     int32_t k = wsub(1024, wmul(32768, wadd(c1, c2)));  // rounding constant minus the bias of both histories
@@ -129,7 +132,7 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
         const uint32_t c1 = (uint16_t)coefs[(int64_t)ch * 16 + 2 * p], c2 = (uint16_t)coefs[(int64_t)ch * 16 + 2 * p + 1];
         pairs[p] = c1 | (c2 << 16);
     }
-    DecState st{tab.hist[2 * ch] + 32768, tab.hist[2 * ch + 1] + 32768};
+    DecState st{tab.hist[2 * ch] + 32768, tab.hist[2 * ch + 1] + 32768, 0u};
 
     // groups of 4 whole frames whose 56 samples all exist go through the vector path
     const int full_frames = min(f_hi, n / kGcFrameSamples);  // frames with all 14 samples
@@ -197,6 +200,7 @@ gc_decode_kernel(const uint8_t *__restrict__ adpcm, GcChannelTable tab, const in
         }
     }
 
+    if ((st.heads & 0x80u) && tab.status) atomicMin(tab.status, ch);
     tab.hist[2 * ch] = (int16_t)(st.hb1 - 32768);  // carried into the next time slice of the same call
     tab.hist[2 * ch + 1] = (int16_t)(st.hb2 - 32768);
 }

@@ -32,7 +32,8 @@ void launch_gc_taps(const uint8_t *adpcm, const GcChannelTable &tab, const int16
 // adx.cu — CriAdxCodec.Encode / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171)
 void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
                        cudaStream_t stream);
-void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, cudaStream_t stream);
+void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, int32_t *status,
+                       cudaStream_t stream);  // status: lowest channel with a fixed-filter number 4..7 (atomicMin), may be null
 
 // hca.cu — CriHcaEncoder.EncodeFrame + CriHcaPacking.PackFrame (Codecs/CriHca/CriHcaEncoder.cs:271-286)
 size_t hca_encode_smem_bytes(const HcaConfig &cfg);
