@@ -14,7 +14,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def segments():
-    saved = os.environ.get("VGB_GC_SEGMENTS")
+    """force(n) sets the segment count (None: the library's own choice); the shortest segment is lowered to 256 frames
+    for the whole test so that short inputs are really cut (the default of 4096 is sized for the run-on tail)."""
+    saved = {k: os.environ.get(k) for k in ("VGB_GC_SEGMENTS", "VGB_GC_MIN_SEG_FRAMES")}
+    os.environ["VGB_GC_MIN_SEG_FRAMES"] = "256"
 
     def force(n):
         if n is None:
@@ -23,10 +26,11 @@ def segments():
             os.environ["VGB_GC_SEGMENTS"] = str(n)
 
     yield force
-    if saved is None:
-        os.environ.pop("VGB_GC_SEGMENTS", None)
-    else:
-        os.environ["VGB_GC_SEGMENTS"] = saved
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def splice_stats(vg):

@@ -221,6 +221,7 @@ GcSegArgs seg_view(void *ws, const GcWorkspace &w, int32_t seg_count)
     a.used_start = reinterpret_cast<uint32_t *>(b + w.off_used_start);
     a.stats = reinterpret_cast<unsigned long long *>(b + w.off_stats);
     a.seg_count = seg_count;
+    a.min_seg_frames = kGcMinSegFrames;  // launch_gc_encode sets the effective value
     return a;
 }
 
@@ -480,6 +481,79 @@ GcLayout sub_layout(const GcLayout &full, int c0, int c1)
     return g;
 }
 
+// ---- host-call pipeline over groups of independent units (channels / streams) ------------------------------------------
+// Every host-pointer entry point moves bytes over PCIe on both sides of its kernels.  Units are independent, so the
+// call is cut into groups: the H2D copy of group g+1, the kernels of group g and the D2H copy of group g-1 overlap on
+// three kinds of streams.  `h2d(g)` enqueues on g_ctx.s_in, `kern(g, stream)` on one of the kernel streams,
+// `d2h(g)` on g_ctx.s_out; the helper adds the events, the timeline taps and the final synchronisation.  Returns with
+// nothing in flight, also on error (caller memory may be unpinned / freed right after).
+struct PipelineDrain {
+    ~PipelineDrain()
+    {
+        cudaStreamSynchronize(g_ctx.s_in);
+        for (auto st : g_ctx.s_comp) cudaStreamSynchronize(st);
+        cudaStreamSynchronize(g_ctx.s_out);
+        (void)cudaGetLastError();
+    }
+};
+
+// how many groups for `units` units carrying `bytes` bytes over PCIe in total (both directions)
+int pipeline_group_count(int64_t units, int64_t bytes, int min_units_per_group)
+{
+    int64_t n = std::min<int64_t>(kMaxGroups / 2, std::min<int64_t>(bytes / (32 << 20), units / std::max(min_units_per_group, 1)));
+    if (const char *env = std::getenv("VGB_PIPELINE_GROUPS")) {  // tuning knob: 1..kMaxGroups
+        const int want = std::atoi(env);
+        if (want >= 1 && want <= kMaxGroups && units >= want) n = want;
+    }
+    return (int)std::max<int64_t>(n, 1);
+}
+
+// group boundaries over units with the given weights (roughly equal weight per group, order preserved)
+std::vector<int> pipeline_bounds(const std::vector<int64_t> &weight, int n_groups)
+{
+    const int n = (int)weight.size();
+    std::vector<int> bound(n_groups + 1, n);
+    bound[0] = 0;
+    int64_t total = 0, run = 0;
+    for (int64_t w : weight) total += w;
+    int g = 1;
+    for (int u = 0; u < n && g < n_groups; u++) {
+        run += weight[u];
+        if (run * n_groups >= total * g) bound[g++] = u + 1;
+    }
+    return bound;
+}
+
+template <class H2D, class Kern, class D2H, class Done>
+int32_t run_group_pipeline(int n_groups, H2D h2d, Kern kern, D2H d2h, Done done)
+{
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));  // nothing of a previous call still uses the shared slabs
+    PipelineDrain drain;
+    CUDA_TRY(cudaEventRecord(g_ctx.ev_t0, g_ctx.s_in));
+    g_ctx.last_groups = n_groups;
+    for (int g = 0; g < n_groups; g++) {
+        VGB_TRY(h2d(g));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_in[g], g_ctx.s_in));
+    }
+    for (int g = 0; g < n_groups; g++) {
+        cudaStream_t st = g_ctx.s_comp[g % kCompStreams];
+        CUDA_TRY(cudaStreamWaitEvent(st, g_ctx.ev_in[g], 0));
+        VGB_TRY(kern(g, st));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_mid[g], st));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_done[g], st));
+    }
+    for (int g = 0; g < n_groups; g++) {
+        CUDA_TRY(cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev_done[g], 0));
+        VGB_TRY(d2h(g));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_out[g], g_ctx.s_out));
+    }
+    for (int g = 0; g < n_groups; g++) {
+        CUDA_TRY(cudaEventSynchronize(g_ctx.ev_out[g]));
+        VGB_TRY(done(g));
+    }
+    return VGB_OK;
+}
+
 // One host call, pipelined over three kinds of streams (input copies, kernels, output copies) in up to kMaxGroups
 // channel groups: the H2D copy of group g+1, the kernels of group g and the D2H copy of group g-1 overlap (channels
 // are independent; a channel's coefficients need all of its samples).
@@ -533,15 +607,7 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     VGB_TRY(ensure_ready_locked());
     // every exit, including the error returns below, leaves no copy in flight on caller memory (pins are released
     // and the buffers may be freed as soon as this function returns)
-    struct PipelineDrain {
-        ~PipelineDrain()
-        {
-            cudaStreamSynchronize(g_ctx.s_in);
-            for (auto st : g_ctx.s_comp) cudaStreamSynchronize(st);
-            cudaStreamSynchronize(g_ctx.s_out);
-            (void)cudaGetLastError();
-        }
-    } drain;
+    PipelineDrain drain;
     std::vector<GcLayout> glay(n_groups);
     std::vector<GcWorkspace> gws(n_groups);
     std::vector<size_t> ws_at(n_groups);
@@ -741,29 +807,71 @@ int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_b
     VGB_TRY(layout_common(lay, counts.data(), params, n_channels, true));
     layout_pack_offsets(lay);
 
+    // channel groups: H2D of the ADPCM of group g+1 || decode of group g || D2H of the PCM of group g-1
+    std::vector<int64_t> weight(n_channels);
+    int64_t pcie_bytes = 0;
+    for (int c = 0; c < n_channels; c++) {
+        weight[c] = (int64_t)counts[c] + 64;
+        pcie_bytes += (int64_t)counts[c] * 2 + gc_sample_count_to_byte_count(counts[c]);
+    }
+    const int n_groups = pipeline_group_count(n_channels, pcie_bytes, 32);
+    const std::vector<int> bound = pipeline_bounds(weight, n_groups);
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = g_ctx.stream;
-    const GcWorkspace w = carve(32, n_channels);
+    std::vector<GcLayout> glay(n_groups);
+    std::vector<GcWorkspace> gws(n_groups);
+    std::vector<size_t> ws_at(n_groups);
+    size_t ws_total = 0;
+    for (int g = 0; g < n_groups; g++) {
+        glay[g] = sub_layout(lay, bound[g], bound[g + 1]);
+        gws[g] = carve(32, glay[g].n_channels);
+        ws_at[g] = ws_total;
+        ws_total += align_up(gws[g].total, 256);
+    }
     VGB_TRY(g_ctx.pcm.reserve((size_t)lay.pcm_total * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)lay.adpcm_total));
     VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 32 * 2));
-    VGB_TRY(g_ctx.ws.reserve(w.total));
+    VGB_TRY(g_ctx.ws.reserve(ws_total));
+    char *ws_base = static_cast<char *>(g_ctx.ws.p);
+    int16_t *d_coefs = static_cast<int16_t *>(g_ctx.coefs.p);
+    std::vector<int32_t> bad(n_groups, INT_MAX);
 
-    std::vector<int64_t> off_b(n_channels), len_b(n_channels);
-    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.adpcm_off[c]; len_b[c] = gc_sample_count_to_byte_count(counts[c]); }
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), off_b, adpcm, len_b, st));
-    CUDA_TRY(cudaMemcpyAsync(g_ctx.coefs.p, coefs, (size_t)n_channels * 32, cudaMemcpyHostToDevice, st));
-    VGB_TRY(run_gc_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), lay, static_cast<const int16_t *>(g_ctx.coefs.p),
-                          static_cast<int16_t *>(g_ctx.pcm.p), g_ctx.ws.p, w, st));
-    for (int c = 0; c < n_channels; c++) { off_b[c] = lay.pcm_off[c] * 2; len_b[c] = (int64_t)counts[c] * 2; }
-    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), off_b, len_b, st));
-    int32_t bad_channel = INT_MAX;
-    CUDA_TRY(cudaMemcpyAsync(&bad_channel, static_cast<char *>(g_ctx.ws.p) + w.off_status, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    auto h2d = [&](int g) -> int32_t {
+        const int c0 = bound[g], n = bound[g + 1] - c0;
+        if (g == 0) {  // the small tables first, while the copy stream is idle
+            for (int k = 0; k < n_groups; k++) VGB_TRY(upload_tables(glay[k], gws[k], ws_base + ws_at[k], g_ctx.s_in));
+            CUDA_TRY(cudaMemcpyAsync(d_coefs, coefs, (size_t)n_channels * 32, cudaMemcpyHostToDevice, g_ctx.s_in));
+        }
+        std::vector<int64_t> off_b(n), len_b(n);
+        for (int c = 0; c < n; c++) { off_b[c] = lay.adpcm_off[c0 + c]; len_b[c] = gc_sample_count_to_byte_count(counts[c0 + c]); }
+        return copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), off_b, adpcm + c0, len_b, g_ctx.s_in);
+    };
+    auto kern = [&](int g, cudaStream_t st) -> int32_t {
+        if (glay[g].n_channels == 0) return VGB_OK;
+        GcChannelTable tab = table_view(ws_base + ws_at[g], gws[g], glay[g].n_channels);
+        CUDA_TRY(cudaMemsetAsync(tab.status, 0x7f, 4, st));  // "no channel": any index is smaller
+        if (n_groups == 1) tick(3, true, st);  // the kernel timers describe unpipelined calls only
+        launch_gc_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), tab, d_coefs + (size_t)bound[g] * 16,
+                         static_cast<int16_t *>(g_ctx.pcm.p), glay[g].max_frames, 0, INT_MAX, st);
+        if (n_groups == 1) tick(3, false, st);
+        g_ctx.launches += glay[g].max_frames > 0 ? 1 : 0;
+        CUDA_TRY(cudaGetLastError());
+        return VGB_OK;
+    };
+    auto d2h = [&](int g) -> int32_t {
+        const int c0 = bound[g], n = bound[g + 1] - c0;
+        std::vector<int64_t> off_b(n), len_b(n);
+        for (int c = 0; c < n; c++) { off_b[c] = lay.pcm_off[c0 + c] * 2; len_b[c] = (int64_t)counts[c0 + c] * 2; }
+        VGB_TRY(copy_channels_out(pcm_out + c0, static_cast<const char *>(g_ctx.pcm.p), off_b, len_b, g_ctx.s_out));
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(&bad[g], ws_base + ws_at[g] + gws[g].off_status, 4, cudaMemcpyDeviceToHost, g_ctx.s_out));
+        return VGB_OK;
+    };
+    VGB_TRY(run_group_pipeline(n_groups, h2d, kern, d2h, [](int) { return VGB_OK; }));
     // coefs[predictor * 2] with predictor 8..15 is an IndexOutOfRangeException in GcAdpcmDecoder.Decode (:31-32)
-    if (bad_channel >= 0 && bad_channel < n_channels)
-        return fail(VGB_E_DATA, "channel %d: a frame header selects a predictor outside 0..7", bad_channel);
+    for (int g = 0; g < n_groups; g++)
+        if (bad[g] >= 0 && bad[g] < glay[g].n_channels)
+            return fail(VGB_E_DATA, "channel %d: a frame header selects a predictor outside 0..7", bound[g] + bad[g]);
     return VGB_OK;
 }
 
@@ -1155,26 +1263,49 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
         ab += (int64_t)align_up((size_t)bytes, 16);
         frames_total += bytes / p.frame_size;
     }
+    // channel groups: H2D of group g+1 || encode of group g || D2H of group g-1
+    std::vector<int64_t> weight(n_channels);
+    int64_t pcie_bytes = 0;
+    for (int c = 0; c < n_channels; c++) { weight[c] = in_len[c] + 64; pcie_bytes += in_len[c] + out_len[c]; }
+    const int n_groups = pipeline_group_count(n_channels, pcie_bytes, 32);
+    const std::vector<int> bound = pipeline_bounds(weight, n_groups);
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = g_ctx.stream;
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
     VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
     VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 2));
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
-    CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
-    tick(4, true, st);
-    launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
-                      static_cast<uint8_t *>(g_ctx.adpcm.p), static_cast<int16_t *>(g_ctx.coefs.p), st);
-    tick(4, false, st);
-    g_ctx.launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    if (history_out) CUDA_TRY(cudaMemcpyAsync(history_out, g_ctx.coefs.p, (size_t)n_channels * 2, cudaMemcpyDeviceToHost, st));
-    VGB_TRY(copy_channels_out(adpcm_out, static_cast<const char *>(g_ctx.adpcm.p), out_off, out_len, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (cb) cb(user, frames_total);
-    return VGB_OK;
+    const AdxChannel *d_tab = static_cast<const AdxChannel *>(g_ctx.misc.p);
+    int16_t *d_hist = static_cast<int16_t *>(g_ctx.coefs.p);
+    auto sub = [&](const std::vector<int64_t> &v, int g) { return std::vector<int64_t>(v.begin() + bound[g], v.begin() + bound[g + 1]); };
+    auto h2d = [&](int g) -> int32_t {
+        if (g == 0) CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, g_ctx.s_in));
+        return copy_channels_in(static_cast<char *>(g_ctx.pcm.p), sub(in_off, g), pcm + bound[g], sub(in_len, g), g_ctx.s_in);
+    };
+    auto kern = [&](int g, cudaStream_t st) -> int32_t {
+        const int c0 = bound[g], n = bound[g + 1] - c0;
+        if (n == 0) return VGB_OK;
+        if (n_groups == 1) tick(4, true, st);
+        launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), d_tab + c0, n, static_cast<uint8_t *>(g_ctx.adpcm.p), d_hist + c0, st);
+        if (n_groups == 1) tick(4, false, st);
+        g_ctx.launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return VGB_OK;
+    };
+    auto d2h = [&](int g) -> int32_t {
+        const int c0 = bound[g], n = bound[g + 1] - c0;
+        if (history_out && n > 0) CUDA_TRY(cudaMemcpyAsync(history_out + c0, d_hist + c0, (size_t)n * 2, cudaMemcpyDeviceToHost, g_ctx.s_out));
+        return copy_channels_out(adpcm_out + c0, static_cast<const char *>(g_ctx.adpcm.p), sub(out_off, g), sub(out_len, g), g_ctx.s_out);
+    };
+    auto done = [&](int g) -> int32_t {  // IProgressReport: one delta per finished group, summing to the frame total
+        int64_t frames = 0;
+        for (int c = bound[g]; c < bound[g + 1]; c++) frames += out_len[c] / params[c].frame_size;
+        if (cb && frames > 0) cb(user, frames);
+        return VGB_OK;
+    };
+    (void)frames_total;
+    return run_group_pipeline(n_groups, h2d, kern, d2h, done);
 }
 
 int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
@@ -1209,30 +1340,49 @@ int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes
         ps += (int64_t)align_up((size_t)sample_count[c], 8);
         ab += (int64_t)align_up((size_t)n_bytes[c], 16);
     }
+    std::vector<int64_t> weight(n_channels);
+    int64_t pcie_bytes = 0;
+    for (int c = 0; c < n_channels; c++) { weight[c] = out_len[c] + 64; pcie_bytes += in_len[c] + out_len[c]; }
+    const int n_groups = pipeline_group_count(n_channels, pcie_bytes, 32);
+    const std::vector<int> bound = pipeline_bounds(weight, n_groups);
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
-    cudaStream_t st = g_ctx.stream;
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
     const size_t o_status = align_up(tab.size() * sizeof(AdxChannel), 256);
-    VGB_TRY(g_ctx.misc.reserve(o_status + 16));
-    int32_t *d_status = reinterpret_cast<int32_t *>(static_cast<char *>(g_ctx.misc.p) + o_status);
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, adpcm, in_len, st));
-    CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d_status, 0x7f, 4, st));
-    tick(5, true, st);
-    launch_adx_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), static_cast<const AdxChannel *>(g_ctx.misc.p), n_channels,
-                      static_cast<int16_t *>(g_ctx.pcm.p), d_status, st);
-    tick(5, false, st);
-    g_ctx.launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
-    int32_t bad_channel = INT_MAX;
-    CUDA_TRY(cudaMemcpyAsync(&bad_channel, d_status, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    VGB_TRY(g_ctx.misc.reserve(o_status + 16 * (size_t)n_groups));
+    const AdxChannel *d_tab = static_cast<const AdxChannel *>(g_ctx.misc.p);
+    int32_t *d_status = reinterpret_cast<int32_t *>(static_cast<char *>(g_ctx.misc.p) + o_status);  // [group * 4]
+    std::vector<int32_t> bad(n_groups, INT_MAX);
+    auto sub = [&](const std::vector<int64_t> &v, int g) { return std::vector<int64_t>(v.begin() + bound[g], v.begin() + bound[g + 1]); };
+    auto h2d = [&](int g) -> int32_t {
+        if (g == 0) {
+            CUDA_TRY(cudaMemcpyAsync(g_ctx.misc.p, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, g_ctx.s_in));
+            CUDA_TRY(cudaMemsetAsync(d_status, 0x7f, 16 * (size_t)n_groups, g_ctx.s_in));
+        }
+        return copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), sub(in_off, g), adpcm + bound[g], sub(in_len, g), g_ctx.s_in);
+    };
+    auto kern = [&](int g, cudaStream_t st) -> int32_t {
+        const int c0 = bound[g], n = bound[g + 1] - c0;
+        if (n == 0) return VGB_OK;
+        if (n_groups == 1) tick(5, true, st);
+        launch_adx_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), d_tab + c0, n, static_cast<int16_t *>(g_ctx.pcm.p), d_status + 4 * g, st);
+        if (n_groups == 1) tick(5, false, st);
+        g_ctx.launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return VGB_OK;
+    };
+    auto d2h = [&](int g) -> int32_t {
+        VGB_TRY(copy_channels_out(pcm_out + bound[g], static_cast<const char *>(g_ctx.pcm.p), sub(out_off, g), sub(out_len, g), g_ctx.s_out));
+        CUDA_TRY(cudaMemcpyAsync(&bad[g], d_status + 4 * g, 4, cudaMemcpyDeviceToHost, g_ctx.s_out));
+        return VGB_OK;
+    };
+    VGB_TRY(run_group_pipeline(n_groups, h2d, kern, d2h, [](int) { return VGB_OK; }));
     // CriAdxCodec.Coefs[filterNum] (:186-191) has four rows: IndexOutOfRangeException in the reference
-    if (bad_channel >= 0 && bad_channel < n_channels)
-        return fail(VGB_E_DATA, "channel %d: a Fixed-type frame selects a filter outside 0..3", bad_channel);
+    for (int g = 0; g < n_groups; g++)
+        if (bad[g] >= 0 && bad[g] < bound[g + 1] - bound[g])
+            return fail(VGB_E_DATA, "channel %d: a Fixed-type frame selects a filter outside 0..3", bound[g] + bad[g]);
     return VGB_OK;
 }
 
@@ -1599,28 +1749,56 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
         frames_total += infos[s].frame_count;
     }
 
+    // stream groups: H2D of group g+1 || encode of group g || D2H of group g-1
+    std::vector<int64_t> weight(n_streams);
+    int64_t pcie_bytes = 0;
+    for (int s = 0; s < n_streams; s++) {
+        weight[s] = (int64_t)infos[s].frame_count + 1;
+        pcie_bytes += (int64_t)params[s].sample_count * 2 * nch + out_len[s];
+    }
+    const int n_groups = pipeline_group_count(n_streams, pcie_bytes, 16);
+    const std::vector<int> bound = pipeline_bounds(weight, n_groups);
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
     VGB_TRY(hca_tables_ready_locked());
-    cudaStream_t st = g_ctx.stream;
     const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)fb + 16));
     VGB_TRY(g_ctx.misc.reserve(o_status + (size_t)n_streams * 4));
     char *misc = static_cast<char *>(g_ctx.misc.p);
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.pcm.p), in_off, pcm, in_len, st));
-    CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
-    tick(6, true, st);
-    CUDA_TRY(launch_hca_encode(static_cast<const int16_t *>(g_ctx.pcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
-                               max_frames, cfg, g_hca_tables.view, static_cast<uint8_t *>(g_ctx.adpcm.p),
-                               reinterpret_cast<int32_t *>(misc + o_status), st));
-    tick(6, false, st);
-    g_ctx.launches += 1;
+    const HcaStream *d_streams = reinterpret_cast<const HcaStream *>(misc);
+    int32_t *d_status = reinterpret_cast<int32_t *>(misc + o_status);
     std::vector<int32_t> status(n_streams, 0);
-    CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
-    VGB_TRY(copy_channels_out(frames_out, static_cast<const char *>(g_ctx.adpcm.p), out_off, out_len, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    auto h2d = [&](int g) -> int32_t {
+        if (g == 0) {
+            CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, g_ctx.s_in));
+            CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, g_ctx.s_in));
+        }
+        const size_t c0 = (size_t)bound[g] * nch, c1 = (size_t)bound[g + 1] * nch;
+        return copy_channels_in(static_cast<char *>(g_ctx.pcm.p), std::vector<int64_t>(in_off.begin() + c0, in_off.begin() + c1), pcm + c0,
+                                std::vector<int64_t>(in_len.begin() + c0, in_len.begin() + c1), g_ctx.s_in);
+    };
+    auto kern = [&](int g, cudaStream_t st) -> int32_t {
+        const int s0 = bound[g], n = bound[g + 1] - s0;
+        if (n == 0) return VGB_OK;
+        int group_max = 0;
+        for (int s = s0; s < s0 + n; s++) group_max = std::max(group_max, infos[s].frame_count);
+        if (n_groups == 1) tick(6, true, st);
+        CUDA_TRY(launch_hca_encode(static_cast<const int16_t *>(g_ctx.pcm.p), d_streams + s0, n, group_max, cfg, g_hca_tables.view,
+                                   static_cast<uint8_t *>(g_ctx.adpcm.p), d_status + s0, st));
+        if (n_groups == 1) tick(6, false, st);
+        g_ctx.launches += 1;
+        return VGB_OK;
+    };
+    auto d2h = [&](int g) -> int32_t {
+        const int s0 = bound[g], n = bound[g + 1] - s0;
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(status.data() + s0, d_status + s0, (size_t)n * 4, cudaMemcpyDeviceToHost, g_ctx.s_out));
+        return copy_channels_out(frames_out + s0, static_cast<const char *>(g_ctx.adpcm.p), std::vector<int64_t>(out_off.begin() + s0, out_off.begin() + s0 + n),
+                                 std::vector<int64_t>(out_len.begin() + s0, out_len.begin() + s0 + n), g_ctx.s_out);
+    };
+    (void)max_frames;
+    VGB_TRY(run_group_pipeline(n_groups, h2d, kern, d2h, [](int) { return VGB_OK; }));
     for (int s = 0; s < n_streams; s++) {
         if (status[s] == VGB_HCA_BITRATE_TOO_LOW) return fail(VGB_E_DATA, "stream %d: Bitrate is set too low.", s);
         if (status[s] == VGB_HCA_NOT_IMPLEMENTED) return fail(VGB_E_STATE, "stream %d: evaluation boundary search failed (NotImplementedException in the reference)", s);
@@ -1701,33 +1879,77 @@ int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *i
         frames_total += info[s].frame_count;
     }
 
+    // stream groups: H2D of the frames of group g+1 || decode of group g || D2H of the PCM of group g-1
+    std::vector<int64_t> weight(n_streams);
+    int64_t pcie_bytes = 0;
+    for (int s = 0; s < n_streams; s++) {
+        weight[s] = (int64_t)info[s].frame_count + 1;
+        pcie_bytes += in_len[s] + (int64_t)info[s].sample_count * 2 * nch;
+    }
+    const int n_groups = pipeline_group_count(n_streams, pcie_bytes, 16);
+    const std::vector<int> bound = pipeline_bounds(weight, n_groups);
+    // per-group scratch: the seam addends (2 x 128 doubles per channel-frame) and the parse records; the kernels index
+    // both by the group-relative frame number, so dct_off restarts at every group
+    std::vector<int64_t> g_frames(n_groups, 0);
+    std::vector<int> g_max(n_groups, 0);
+    std::vector<size_t> edge_at(n_groups), parsed_at(n_groups);
+    size_t edge_total = 0, parsed_total = 0;
+    for (int g = 0; g < n_groups; g++) {
+        for (int s = bound[g]; s < bound[g + 1]; s++) {
+            streams[s].dct_off = g_frames[g];
+            g_frames[g] += info[s].frame_count;
+            g_max[g] = std::max(g_max[g], info[s].frame_count);
+        }
+        edge_at[g] = edge_total;
+        edge_total += align_up((size_t)g_frames[g] * nch * 2 * 128 * sizeof(double), 256);
+        parsed_at[g] = parsed_total;
+        parsed_total += align_up(hca_decode_parsed_bytes(cfg, g_frames[g]), 256);
+    }
+    (void)max_frames;
+
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     VGB_TRY(ensure_ready_locked());
     VGB_TRY(hca_tables_ready_locked());
-    cudaStream_t st = g_ctx.stream;
     const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
     const size_t o_edge = align_up(o_status + (size_t)n_streams * 4, 256);
-    const size_t o_parsed = align_up(o_edge + (size_t)frames_total * nch * 2 * 128 * sizeof(double), 256);
+    const size_t o_parsed = align_up(o_edge + edge_total, 256);
     VGB_TRY(g_ctx.pcm.reserve((size_t)(ps + 8) * 2));
     VGB_TRY(g_ctx.adpcm.reserve((size_t)fb + 16));
-    VGB_TRY(g_ctx.misc.reserve(o_parsed + hca_decode_parsed_bytes(cfg, frames_total)));
+    VGB_TRY(g_ctx.misc.reserve(o_parsed + parsed_total + 256));
     char *misc = static_cast<char *>(g_ctx.misc.p);
-    VGB_TRY(copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), in_off, frames, in_len, st));
-    CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, st));
-    // samples past the last frame (sample_count > frame_count * 1024 - inserted) stay zero, like a fresh short[]
-    CUDA_TRY(cudaMemsetAsync(g_ctx.pcm.p, 0, (size_t)ps * 2, st));
-    tick(7, true, st);
-    CUDA_TRY(launch_hca_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), reinterpret_cast<const HcaStream *>(misc), n_streams,
-                               max_frames, frames_total, cfg, g_hca_tables.view, reinterpret_cast<uint8_t *>(misc + o_parsed),
-                               reinterpret_cast<double *>(misc + o_edge),
-                               static_cast<int16_t *>(g_ctx.pcm.p), reinterpret_cast<int32_t *>(misc + o_status), st));
-    tick(7, false, st);
-    g_ctx.launches += 3;
+    const HcaStream *d_streams = reinterpret_cast<const HcaStream *>(misc);
+    int32_t *d_status = reinterpret_cast<int32_t *>(misc + o_status);
     std::vector<int32_t> status(n_streams, 0);
-    CUDA_TRY(cudaMemcpyAsync(status.data(), misc + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
-    VGB_TRY(copy_channels_out(pcm_out, static_cast<const char *>(g_ctx.pcm.p), out_off, out_len, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    auto h2d = [&](int g) -> int32_t {
+        if (g == 0) {
+            CUDA_TRY(cudaMemcpyAsync(misc, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, g_ctx.s_in));
+            CUDA_TRY(cudaMemsetAsync(misc + o_status, 0, (size_t)n_streams * 4, g_ctx.s_in));
+            // samples past the last frame (sample_count > frame_count * 1024 - inserted) stay zero, like a fresh short[]
+            CUDA_TRY(cudaMemsetAsync(g_ctx.pcm.p, 0, (size_t)ps * 2, g_ctx.s_in));
+        }
+        const int s0 = bound[g], n = bound[g + 1] - s0;
+        return copy_channels_in(static_cast<char *>(g_ctx.adpcm.p), std::vector<int64_t>(in_off.begin() + s0, in_off.begin() + s0 + n), frames + s0,
+                                std::vector<int64_t>(in_len.begin() + s0, in_len.begin() + s0 + n), g_ctx.s_in);
+    };
+    auto kern = [&](int g, cudaStream_t st) -> int32_t {
+        const int s0 = bound[g], n = bound[g + 1] - s0;
+        if (n == 0 || g_frames[g] == 0) return VGB_OK;
+        if (n_groups == 1) tick(7, true, st);
+        CUDA_TRY(launch_hca_decode(static_cast<const uint8_t *>(g_ctx.adpcm.p), d_streams + s0, n, g_max[g], g_frames[g], cfg, g_hca_tables.view,
+                                   reinterpret_cast<uint8_t *>(misc + o_parsed + parsed_at[g]), reinterpret_cast<double *>(misc + o_edge + edge_at[g]),
+                                   static_cast<int16_t *>(g_ctx.pcm.p), d_status + s0, st));
+        if (n_groups == 1) tick(7, false, st);
+        g_ctx.launches += 3;
+        return VGB_OK;
+    };
+    auto d2h = [&](int g) -> int32_t {
+        const int s0 = bound[g], n = bound[g + 1] - s0;
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(status.data() + s0, d_status + s0, (size_t)n * 4, cudaMemcpyDeviceToHost, g_ctx.s_out));
+        const size_t c0 = (size_t)s0 * nch, c1 = (size_t)(s0 + n) * nch;
+        return copy_channels_out(pcm_out + c0, static_cast<const char *>(g_ctx.pcm.p), std::vector<int64_t>(out_off.begin() + c0, out_off.begin() + c1),
+                                 std::vector<int64_t>(out_len.begin() + c0, out_len.begin() + c1), g_ctx.s_out);
+    };
+    VGB_TRY(run_group_pipeline(n_groups, h2d, kern, d2h, [](int) { return VGB_OK; }));
     for (int s = 0; s < n_streams; s++) {
         if (status[s] == VGB_HCA_BAD_SYNC) return fail(VGB_E_DATA, "stream %d: Invalid frame header", s);
         if (status[s] == VGB_HCA_BAD_DELTA) return fail(VGB_E_DATA, "stream %d: scale factor delta out of range", s);

@@ -57,7 +57,7 @@ struct GcChannelTable {
 };
 
 // Time-parallel encoding (gc_encode.cu): segment bookkeeping of one encode launch, all in the caller's workspace.
-constexpr int kGcMinSegFrames = 256;  // no segment shorter than this (run-ons at the boundaries must stay a small share)
+constexpr int kGcMinSegFrames = 4096; // default shortest segment (gc_encode_min_segment_frames): longer than the run-on tail
 constexpr int kGcMaxSegments = 256;
 constexpr int kGcStatWords = 18;      // GcSegArgs::stats
 struct GcSegArgs {
@@ -66,6 +66,7 @@ struct GcSegArgs {
     unsigned long long *stats;   // [0] frames re-encoded by run-ons, [1] by the cascade, [2] boundaries left to the cascade,
                                  // [3] longest run-on, [4 + b] run-ons of 2^b .. 2^(b+1)-1 frames (b = 13: longer)
     int32_t seg_count;
+    int32_t min_seg_frames;      // no segment shorter than this
 };
 
 // One channel of a seek-table / loop-context request (gc_decode_kernel<true>).

@@ -269,10 +269,10 @@ __device__ __noinline__ uint32_t gc_slow_frame(const int16_t *frame, int32_t h1,
 constexpr int kGcChain = 0, kGcRunOn = 1, kGcCascade = 2;
 
 // frames per segment of a channel with `range_frames` frames to encode (device and host agree on this)
-__host__ __device__ __forceinline__ int gc_seg_len(int range_frames, int seg_count)
+__host__ __device__ __forceinline__ int gc_seg_len(int range_frames, int seg_count, int min_seg_frames)
 {
     const int per = (div_round_up(range_frames, seg_count > 0 ? seg_count : 1) + kEncChunkFrames - 1) / kEncChunkFrames * kEncChunkFrames;
-    return per < kGcMinSegFrames ? kGcMinSegFrames : per;
+    return per < min_seg_frames ? min_seg_frames : per;
 }
 
 // grid.x: one HALF-WARP per channel (two channels per warp); encodes frames [frame_begin, frame_end) of every channel,
@@ -324,7 +324,7 @@ gc_encode_kernel(const int16_t *__restrict__ pcm, GcChannelTable tab, const int1
     const int n_frames = div_round_up(n_enc, kGcFrameSamples);
     const int f_end = min(frame_end, n_frames);                         // this channel's end of the frame range
     const int range_frames = max(f_end - frame_begin, 0);
-    const int seg_len = gc_seg_len(range_frames, sa.seg_count);         // this channel's frames per segment
+    const int seg_len = gc_seg_len(range_frames, sa.seg_count, sa.min_seg_frames);         // this channel's frames per segment
     const int total_bytes = gc_sample_count_to_byte_count(n_enc);
 
     const int16_t *src = pcm + tab.pcm_off[ch];
@@ -742,14 +742,31 @@ gc_encode_frames_kernel(int16_t *__restrict__ pcm_in_out, const int32_t *__restr
     }
 }
 
+// Shortest segment, in frames (a multiple of 16).  A boundary costs a run-on of a few dozen frames as a rule, but the
+// distribution has a long tail: loud, tonal material (predictor poles next to the unit circle) forgets a wrong history
+// only over thousands of frames (measured on C2: 23 552 boundaries, median 8-16 frames, 20 above 1024, longest 3809).
+// A run-on that does not splice inside its segment leaves the rest of the channel to the serial cascade, so segments
+// stay longer than that tail; VGB_GC_MIN_SEG_FRAMES overrides (the tests use 256 to exercise many segments on short
+// inputs).
+int gc_encode_min_segment_frames()
+{
+    if (const char *env = std::getenv("VGB_GC_MIN_SEG_FRAMES")) {
+        const int v = std::atoi(env);
+        if (v >= kEncChunkFrames) return (v + kEncChunkFrames - 1) / kEncChunkFrames * kEncChunkFrames;
+    }
+    return kGcMinSegFrames;
+}
+
 // How many segments to cut the frame range into.  The chain launch is throughput bound once every SM sub-partition
-// holds its four warps (measured on C2: ~850 cycles per frame pair and sub-partition from 4 warps up, against the
+// holds its four warps (measured on C2: ~800 cycles per frame pair and sub-partition from 4 warps up, against the
 // 1419-cycle dependent chain of a lone warp), so the aim is (a) several full waves of (channel pair, segment) items -
-// the last, partly filled wave is the only loss - and (b) segments long enough that the run-on work at their
-// boundaries (a few dozen frames each, a long tail) stays small.  Measured on C2 (512 item rows): 75.5 ms with one
-// segment, 48 ms with 3, 39.0 with 17, 38.7 with 24, 38.8 with 34, 45 with 48 (profiles/r02_seg_sweep.md).
+// the last, partly filled wave is the only loss - and (b) segments longer than the run-on tail (above).  Measured on C2
+// (512 item rows): 75.5 ms with one segment, 48 ms with 3, 39.0 with 17, 38.7 with 24, 38.8 with 34, 45 with 48
+// (profiles/r02_seg_sweep.md; the last two already lose boundaries to the cascade).
 int gc_encode_pick_segments(int n_channels, int max_frames)
 {
+    const int min_seg = gc_encode_min_segment_frames();
+    const int max_s = std::min(kGcMaxSegments, std::max(1, max_frames / min_seg));
     if (const char *env = std::getenv("VGB_GC_SEGMENTS")) {
         const int v = std::atoi(env);
         if (v >= 1) return v > kGcMaxSegments ? kGcMaxSegments : v;
@@ -766,7 +783,6 @@ int gc_encode_pick_segments(int n_channels, int max_frames)
         slots = sms * per_sm * kEncWarps;  // resident warps of the chain launch
     }
     const int rows = (n_channels + 1) / 2;
-    const int max_s = std::min(kGcMaxSegments, std::max(1, max_frames / kGcMinSegFrames));
     const int want = (int)((5ll * slots + rows - 1) / rows);  // about five waves of items
     return std::max(1, std::min(want, max_s));
 }
@@ -780,6 +796,7 @@ void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16
     const int blocks = (tab.n_channels + per_block - 1) / per_block;
     if (sa.seg_count < 1) sa.seg_count = 1;
     if (sa.seg_count > kGcMaxSegments) sa.seg_count = kGcMaxSegments;
+    sa.min_seg_frames = gc_encode_min_segment_frames();
     cudaMemsetAsync(sa.stats, 0, kGcStatWords * sizeof(unsigned long long), stream);
     gc_encode_kernel<kGcChain><<<dim3(blocks, sa.seg_count), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
     if (sa.seg_count > 1) {
