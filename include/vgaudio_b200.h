@@ -31,7 +31,7 @@ extern "C" {
 #define VGB_E_DATA   -2  /* InvalidDataException */
 #define VGB_E_STATE  -3  /* InvalidOperationException */
 #define VGB_E_CUDA   -4  /* no device / CUDA runtime failure */
-#define VGB_E_NCCL   -5  /* reserved for the multi-GPU gather */
+#define VGB_E_NCCL   -5  /* NCCL missing or a collective failed (vgb_nccl_*, vgb_scatterv_dev, vgb_gatherv_dev) */
 #define VGB_E_NOMEM  -6  /* OutOfMemoryException */
 
 #define VGB_ABI_VERSION 1
@@ -43,6 +43,39 @@ int32_t vgb_abi_version(void);
 /* Bind the calling process to CUDA device `device` (>= 0) and create the workspace.  Idempotent. */
 int32_t vgb_init(int32_t device, uint32_t flags);
 int32_t vgb_shutdown(void);
+/* Bind several devices (SURVEY §8b's vgb_init(n_devices, flags); the reference's counterpart is Parallel.ForEach over
+ * files, src/VGAudio.Cli/Batch.cs:24-25).  devices[0] becomes the primary device (the one the *_dev entry points, timers
+ * and debug taps use); every host-pointer *_batch call is then sharded over all bound devices by greedy longest-first bin
+ * packing of the units' sample counts - one worker thread and one H2D / kernel / D2H pipeline per device, each over its
+ * own PCIe link, results written straight into the caller's arrays (no collective: host data reaches a GPU fastest over
+ * that GPU's own link).  A device may be listed more than once. */
+int32_t vgb_init_devices(const int32_t *devices, int32_t n_devices, uint32_t flags);
+int32_t vgb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The one exchange step of a multi-GPU job whose data is already resident in HBM: scatterv of PCM from a
+ * root rank, gatherv of bitstreams back.  One rank per GPU (one process per GPU under torchrun, or one thread per device);
+ * grouped ncclSend / ncclRecv with per-rank byte counts - no padding to the longest shard, no host round trip.  NCCL is
+ * bound at run time (dlopen of libnccl.so.2, preferring the copy the process already loaded); every failure is
+ * VGB_E_NCCL.  The reference has no counterpart: its Parallel.ForEach over files (src/VGAudio.Cli/Batch.cs:24-25) shares
+ * one address space.
+ *   vgb_nccl_unique_id   rank 0 creates the 128-byte id and hands it to the others (any out-of-band channel)
+ *   vgb_nccl_init        every rank, with its CUDA device current (after vgb_init): joins the communicator
+ *   vgb_scatterv_dev     root: bytes [send_offset[r], +counts[r]) of d_send go to rank r's d_recv; asynchronous on stream
+ *   vgb_gatherv_dev      rank r's counts[r] bytes at d_send land at d_recv + recv_offset[r] on the root
+ *   vgb_partition_lpt    greedy longest-first bin packing of units (files / channels) onto parts by weight (samples):
+ *                        part_out[u] = part of unit u, load_out[p] = summed weight (may be NULL)
+ * ------------------------------------------------------------------------------------------------------- */
+#define VGB_NCCL_ID_BYTES 128
+int32_t vgb_nccl_unique_id(uint8_t *id_out /* [VGB_NCCL_ID_BYTES] */);
+int32_t vgb_nccl_init(const uint8_t *id, int32_t n_ranks, int32_t rank);
+int32_t vgb_nccl_shutdown(void);
+int32_t vgb_nccl_version(void); /* e.g. 22809; 0 when NCCL cannot be loaded */
+int32_t vgb_scatterv_dev(const void *d_send, const int64_t *send_offset, const int64_t *counts /* [n_ranks] bytes */,
+                         void *d_recv, int32_t root, void *cuda_stream);
+int32_t vgb_gatherv_dev(const void *d_send, void *d_recv, const int64_t *recv_offset, const int64_t *counts /* [n_ranks] bytes */,
+                        int32_t root, void *cuda_stream);
+int32_t vgb_partition_lpt(const int64_t *weight, int32_t n_units, int32_t n_parts, int32_t *part_out, int64_t *load_out);
 const char *vgb_last_error(void);
 /* Pinned host memory, so the host entry points can DMA straight from/to the caller's buffers. */
 int32_t vgb_host_alloc(void **ptr_out, uint64_t bytes);
@@ -238,6 +271,15 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
                              int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out,
                              vgb_progress_cb cb, void *user);
 
+/* Device-resident variant of vgb_adx_encode_batch (same semantics, asynchronous on `cuda_stream`): d_pcm / d_adpcm are HBM
+ * slabs, channel c at pcm_offset[c] samples (a multiple of 8) / adpcm_offset[c] bytes (even); d_history_out ([n] shorts)
+ * may be NULL; d_workspace holds the channel table (vgb_adx_workspace_bytes).  The multi-GPU batch path and bench.py's
+ * device-resident figures use it. */
+uint64_t vgb_adx_workspace_bytes(int32_t n_channels);
+int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples, const vgb_adx_params *params,
+                           int32_t n_channels, int16_t *d_history_out, uint8_t *d_adpcm, const int64_t *adpcm_offset,
+                           void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+
 /* CriAdxCodec.Decode(byte[] adpcm, int sampleCount, CriAdxParameters config) (CriAdxCodec.cs:9-54).
  * n_bytes[c] = length of adpcm[c]; pcm_out[c] receives sample_count[c] samples.
  * VGB_E_DATA: a Fixed-type frame selects a filter outside 0..3 (IndexOutOfRangeException at CriAdxCodec.Coefs, :186-191). */
@@ -283,6 +325,16 @@ int32_t vgb_hca_query(const vgb_hca_params *params, vgb_hca_info *info_out);
  * low.", CriHcaEncoder.cs:469-472), VGB_E_STATE (bit writer overflow). */
 int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
                              vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user);
+
+/* Device-resident variant of vgb_hca_encode_batch (asynchronous on `cuda_stream`): channel c of stream s starts at
+ * pcm_offset[s] + c * channel_stride[s] samples of d_pcm; its frames go to d_frames + frames_offset[s]
+ * (info.frame_count * info.frame_size bytes, from vgb_hca_query).  The per-stream status of the encoder (the reference's
+ * "Bitrate is set too low." ...) stays in the workspace: vgb_hca_encode_dev_status synchronises the stream and maps it. */
+uint64_t vgb_hca_workspace_bytes(int32_t n_streams);
+int32_t vgb_hca_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int64_t *channel_stride, const vgb_hca_params *params,
+                           int32_t n_streams, vgb_hca_info *info_out, uint8_t *d_frames, const int64_t *frames_offset,
+                           void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+int32_t vgb_hca_encode_dev_status(const void *d_workspace, int32_t n_streams, void *cuda_stream);
 
 /* CRI HCA decode: replaces CriHcaDecoder.Decode (Codecs/CriHca/CriHcaDecoder.cs:11-25) for a batch of streams.
  * info[s] is what the caller's container reader parsed (HcaReader -> HcaInfo); the codec reads channel_count,

@@ -145,3 +145,25 @@ def test_gc_math_helpers_equal_the_oracle_on_a_dense_range(vg, oracle):
         f, g = getattr(vg.lib, ours), getattr(L, theirs)
         for v in values:
             assert f(v) == g(v), (ours, v)
+
+
+def test_partition_lpt_and_collective_errors_without_a_communicator(vg):
+    """vgb_partition_lpt is host logic (greedy longest-first, the file -> GPU assignment of the multi-GPU batch path);
+    the collectives refuse to run before vgb_nccl_init (VGB_E_STATE), and a missing NCCL is VGB_E_NCCL, never a crash."""
+    import ctypes as C
+
+    from vgaudio_b200 import _native as N
+
+    w = np.array([10, 1, 9, 2, 8, 3, 7, 4, 6, 5, 0, 11], dtype=np.int64)
+    part = np.zeros(len(w), dtype=np.int32)
+    load = np.zeros(3, dtype=np.int64)
+    N.check(vg.lib.vgb_partition_lpt(w.ctypes.data, len(w), 3, part.ctypes.data, load.ctypes.data))
+    assert load.sum() == w.sum() and load.max() - load.min() <= 1          # 66 over 3 parts: 22 each
+    assert [int(w[part == p].sum()) for p in range(3)] == load.tolist()
+    N.check(vg.lib.vgb_partition_lpt(w.ctypes.data, 0, 4, None, None))
+    assert vg.lib.vgb_partition_lpt(w.ctypes.data, 3, 0, part.ctypes.data, None) == N.VGB_E_ARG
+    counts = np.zeros(8, dtype=np.int64)
+    assert vg.lib.vgb_scatterv_dev(None, counts.ctypes.data, counts.ctypes.data, None, 0, None) == N.VGB_E_STATE
+    assert vg.lib.vgb_gatherv_dev(None, None, counts.ctypes.data, counts.ctypes.data, 0, None) == N.VGB_E_STATE
+    assert vg.lib.vgb_nccl_version() >= 0
+    assert vg.lib.vgb_device_count() in (0, 1)  # nothing bound on a CPU box, one device after another test's vgb_init

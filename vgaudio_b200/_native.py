@@ -61,6 +61,15 @@ SIGNATURES = {
     "vgb_abi_version": (C.c_int32, []),
     "vgb_init": (C.c_int32, [C.c_int32, C.c_uint32]),
     "vgb_shutdown": (C.c_int32, []),
+    "vgb_init_devices": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32]),
+    "vgb_device_count": (C.c_int32, []),
+    "vgb_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "vgb_nccl_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "vgb_nccl_shutdown": (C.c_int32, []),
+    "vgb_nccl_version": (C.c_int32, []),
+    "vgb_scatterv_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_gatherv_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_partition_lpt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vgb_last_error": (C.c_char_p, []),
     "vgb_host_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_uint64]),
     "vgb_host_free": (C.c_int32, [C.c_void_p]),
@@ -98,6 +107,13 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "vgb_adx_calculate_coefficients": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p]),
     "vgb_adx_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_adx_workspace_bytes": (C.c_uint64, [C.c_int32]),
+    "vgb_adx_encode_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.c_void_p]),
+    "vgb_hca_workspace_bytes": (C.c_uint64, [C.c_int32]),
+    "vgb_hca_encode_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.c_void_p]),
+    "vgb_hca_encode_dev_status": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_hca_query": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "vgb_hca_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_hca_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -37,6 +39,21 @@ int32_t fail(int32_t code, const char *fmt, ...)
     g_err = buf;
     return code;
 }
+
+}  // namespace
+namespace vgb {
+int32_t abi_fail(int32_t code, const char *fmt, ...)  // for the other translation units of the boundary (collective.cu)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace vgb
+namespace {
 
 #define CUDA_TRY(expr)                                                                                      \
     do {                                                                                                    \
@@ -90,6 +107,15 @@ constexpr int kTimers = 10;  // 0 coef phase 1, 1 coef refine, 2 gc encode, 3 gc
 constexpr int kMaxGroups = 16;   // channel groups of one host call, pipelined: H2D(g+1) || kernels(g) || D2H(g-1)
 constexpr int kCompStreams = 4;  // kernel streams the groups rotate over
 
+// One upload of the HCA codec tables per device
+struct HcaTableStore {
+    bool ready = false;
+    void *blob = nullptr;
+    HcaTables view{};
+};
+
+// Everything the library keeps per bound device.  The entry points reach "their" context through g_ctx: the primary
+// device's for a caller thread, a worker's own when a host-pointer batch call is sharded over several devices.
 struct Context {
     std::mutex mu;
     bool ready = false;
@@ -104,9 +130,14 @@ struct Context {
     bool ev_used[kTimers] = {};
     std::atomic<int64_t> launches{0};
     GcSegArgs last_seg{};            // bookkeeping of the most recent encode launch (vgb_gcadpcm_debug_splice_stats)
+    HcaTableStore hca_tables;
 };
 
-Context g_ctx;
+Context g_primary;                               // the device vgb_init / vgb_init_devices binds first
+std::vector<std::unique_ptr<Context>> g_extra;   // further devices of vgb_init_devices
+thread_local Context *t_ctx = &g_primary;        // the context this thread works on
+#define g_ctx (*t_ctx)
+#define g_hca_tables (g_ctx.hca_tables)
 
 void hca_tables_release_locked();  // defined next to the HCA table store
 
@@ -680,6 +711,130 @@ int32_t host_encode_impl(const int16_t *const *pcm, const int32_t *n_samples, co
     return VGB_OK;
 }
 
+// ---- several devices in one process (vgb_init_devices) ----------------------------------------------------------------
+// The reference's counterpart is Parallel.ForEach over files (src/VGAudio.Cli/Batch.cs:24-25) on top of Parallel.For over
+// channels: independent units.  A host-pointer batch call is sharded over the bound devices by greedy longest-first
+// bin packing of the units' sample counts; every device gets a worker thread that runs the ordinary single-device call
+// (its own H2D / kernels / D2H pipeline over its own PCIe link) on its share, results land directly in the caller's
+// arrays.  No collective is involved: host data reaches each GPU fastest over that GPU's own link; the NCCL
+// scatterv / gatherv below serve data that is already resident on one device.
+std::vector<Context *> bound_contexts()
+{
+    std::vector<Context *> v{&g_primary};
+    for (auto &c : g_extra) v.push_back(c.get());
+    return v;
+}
+
+// greedy LPT: heaviest unit first onto the least loaded device; a device's units keep ascending order
+std::vector<std::vector<int>> shard_units(const std::vector<int64_t> &weight, int n_dev)
+{
+    const int n = (int)weight.size();
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<int64_t> load(n_dev, 0);
+    std::vector<std::vector<int>> shards(n_dev);
+    for (int u : order) {
+        int best = 0;
+        for (int d = 1; d < n_dev; d++) if (load[d] < load[best]) best = d;
+        shards[best].push_back(u);
+        load[best] += weight[u];
+    }
+    for (auto &sh : shards) std::sort(sh.begin(), sh.end());
+    return shards;
+}
+
+bool sharding_active(int n_units) { return !g_extra.empty() && n_units >= 2 && t_ctx == &g_primary; }
+
+struct SharedProgress {  // IProgressReport.ReportAdd from several worker threads, one at a time
+    vgb_progress_cb cb;
+    void *user;
+    std::mutex mu;
+    static void relay(void *self, int64_t delta)
+    {
+        auto *p = static_cast<SharedProgress *>(self);
+        std::lock_guard<std::mutex> lock(p->mu);
+        if (p->cb) p->cb(p->user, delta);
+    }
+};
+
+// fn(device index, units) runs on a worker thread bound to that device's context; the first failure wins and its
+// message is re-addressed from the shard-local unit index to the caller's.
+template <class Fn>
+int32_t run_sharded(const std::vector<std::vector<int>> &shards, Fn fn)
+{
+    const std::vector<Context *> ctxs = bound_contexts();
+    const int n = (int)shards.size();
+    std::vector<int32_t> rc(n, VGB_OK);
+    std::vector<std::string> err(n);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n; d++) {
+        if (shards[d].empty()) continue;
+        workers.emplace_back([&, d]() {
+            t_ctx = ctxs[d];
+            rc[d] = fn(d, shards[d]);
+            err[d] = g_err;
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int d = 0; d < n; d++)
+        if (rc[d] != VGB_OK) {
+            std::string m = err[d];
+            for (const char *word : {"channel ", "stream "}) {
+                const size_t len = std::strlen(word);
+                if (m.compare(0, len, word) == 0) {
+                    size_t end = len;
+                    while (end < m.size() && m[end] >= '0' && m[end] <= '9') end++;
+                    if (end > len) {
+                        const int local = std::atoi(m.substr(len, end - len).c_str());
+                        if (local >= 0 && local < (int)shards[d].size()) m = word + std::to_string(shards[d][local]) + m.substr(end);
+                    }
+                }
+            }
+            g_err = m + " (device " + std::to_string(ctxs[d]->device) + ")";
+            return rc[d];
+        }
+    return VGB_OK;
+}
+
+template <class T>
+std::vector<T> pick(const T *src, const std::vector<int> &units)
+{
+    std::vector<T> v(units.size());
+    for (size_t i = 0; i < units.size(); i++) v[i] = src[units[i]];
+    return v;
+}
+
+int32_t host_encode_sharded(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
+                            const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out, uint8_t *const *adpcm_out,
+                            vgb_progress_cb cb, void *user, bool do_encode)
+{
+    if (!sharding_active(n_channels) || !pcm || !n_samples || !coefs_out || (do_encode && !adpcm_out))
+        return host_encode_impl(pcm, n_samples, params, coefs_in, n_channels, coefs_out, adpcm_out, cb, user, do_encode);
+    std::vector<int64_t> weight(n_channels);
+    for (int c = 0; c < n_channels; c++) weight[c] = (int64_t)std::max(n_samples[c], 0) + 64;
+    const auto shards = shard_units(weight, 1 + (int)g_extra.size());
+    SharedProgress prog{cb, user, {}};
+    return run_sharded(shards, [&](int, const std::vector<int> &u) -> int32_t {
+        const int m = (int)u.size();
+        auto s_pcm = pick(pcm, u);
+        auto s_n = pick(n_samples, u);
+        std::vector<vgb_gc_params> s_par;
+        if (params) s_par = pick(params, u);
+        std::vector<int16_t> s_cin, s_cout((size_t)m * 16);
+        if (coefs_in) {
+            s_cin.resize((size_t)m * 16);
+            for (int i = 0; i < m; i++) std::memcpy(&s_cin[(size_t)i * 16], coefs_in + (size_t)u[i] * 16, 32);
+        }
+        std::vector<uint8_t *> s_out;
+        if (do_encode) s_out = pick(adpcm_out, u);
+        VGB_TRY(host_encode_impl(s_pcm.data(), s_n.data(), params ? s_par.data() : nullptr, coefs_in ? s_cin.data() : nullptr, m,
+                                 s_cout.data(), do_encode ? s_out.data() : nullptr, cb ? SharedProgress::relay : nullptr, &prog, do_encode));
+        for (int i = 0; i < m; i++) std::memcpy(coefs_out + (size_t)u[i] * 16, &s_cout[(size_t)i * 16], 32);
+        return VGB_OK;
+    });
+}
+
 }  // namespace
 
 // ==========================================================================================================
@@ -702,7 +857,7 @@ int32_t vgb_init(int32_t device, uint32_t flags)
     return ensure_ready_locked();
 }
 
-int32_t vgb_shutdown(void)
+static int32_t shutdown_current(void)  // releases the context this thread points at
 {
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     if (!g_ctx.ready) return VGB_OK;
@@ -738,6 +893,56 @@ int32_t vgb_shutdown(void)
     return VGB_OK;
 }
 
+int32_t vgb_shutdown(void)
+{
+    for (auto &c : g_extra) {
+        t_ctx = c.get();
+        shutdown_current();
+    }
+    g_extra.clear();
+    t_ctx = &g_primary;
+    return shutdown_current();
+}
+
+/* Bind several devices (vgb_init(n_devices, flags)).  devices[0] becomes the primary device - the one the
+ * *_dev entry points, the timers and the debug taps refer to; every host-pointer *_batch call is then sharded over all
+ * of them (greedy longest-first over the units' sample counts, one worker thread and one H2D / kernel / D2H pipeline per
+ * device, results written straight into the caller's arrays).  A device may be listed more than once (two pipelines on
+ * one GPU; also how the sharding logic is tested on a single-GPU machine). */
+int32_t vgb_init_devices(const int32_t *devices, int32_t n_devices, uint32_t flags)
+{
+    (void)flags;
+    if (!devices || n_devices < 1) return fail(VGB_E_ARG, "at least one device is required");
+    if (n_devices > 64) return fail(VGB_E_ARG, "too many devices (%d)", n_devices);
+    for (int i = 0; i < n_devices; i++)
+        if (devices[i] < 0) return fail(VGB_E_ARG, "device must be >= 0 (got %d)", devices[i]);
+    if (t_ctx != &g_primary) return fail(VGB_E_STATE, "vgb_init_devices called from a worker thread");
+    if (!g_extra.empty() || (g_primary.ready && g_primary.device != devices[0]))
+        return fail(VGB_E_STATE, "already bound; call vgb_shutdown first");
+    VGB_TRY(vgb_init(devices[0], flags));
+    for (int i = 1; i < n_devices; i++) {
+        g_extra.emplace_back(new Context());
+        g_extra.back()->device = devices[i];
+        t_ctx = g_extra.back().get();
+        int32_t rc;
+        {
+            std::lock_guard<std::mutex> lock(g_ctx.mu);
+            rc = ensure_ready_locked();
+        }
+        t_ctx = &g_primary;
+        if (rc != VGB_OK) {
+            const std::string keep = g_err;
+            vgb_shutdown();
+            g_err = keep;
+            return rc;
+        }
+    }
+    cudaSetDevice(g_primary.device);
+    return VGB_OK;
+}
+
+int32_t vgb_device_count(void) { return g_primary.ready ? 1 + (int32_t)g_extra.size() : 0; }
+
 int32_t vgb_host_alloc(void **ptr_out, uint64_t bytes)
 {
     if (!ptr_out) return fail(VGB_E_ARG, "ptr_out is NULL");
@@ -756,7 +961,12 @@ int32_t vgb_host_free(void *ptr)
     return VGB_OK;
 }
 
-int64_t vgb_kernel_launch_count(void) { return g_ctx.launches.load(); }
+int64_t vgb_kernel_launch_count(void)
+{
+    int64_t n = g_primary.launches.load();
+    for (auto &c : g_extra) n += c->launches.load();
+    return n;
+}
 
 int32_t vgb_gcadpcm_sample_count_to_byte_count(int32_t n) { return gc_sample_count_to_byte_count(n); }
 int32_t vgb_gcadpcm_byte_count_to_sample_count(int32_t b) { return gc_nibble_count_to_sample_count(b * 2); }
@@ -774,18 +984,18 @@ int32_t vgb_gcadpcm_nibble_to_sample(int32_t nib)
 int32_t vgb_gcadpcm_coefs_batch(const int16_t *const *pcm, const int32_t *n_samples, int32_t n_channels,
                                 int16_t *coefs_out)
 {
-    return host_encode_impl(pcm, n_samples, nullptr, nullptr, n_channels, coefs_out, nullptr, nullptr, nullptr, false);
+    return host_encode_sharded(pcm, n_samples, nullptr, nullptr, n_channels, coefs_out, nullptr, nullptr, nullptr, false);
 }
 
 int32_t vgb_gcadpcm_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_gc_params *params,
                                  const int16_t *coefs_in, int32_t n_channels, int16_t *coefs_out,
                                  uint8_t *const *adpcm_out, vgb_progress_cb cb, void *user)
 {
-    return host_encode_impl(pcm, n_samples, params, coefs_in, n_channels, coefs_out, adpcm_out, cb, user, true);
+    return host_encode_sharded(pcm, n_samples, params, coefs_in, n_channels, coefs_out, adpcm_out, cb, user, true);
 }
 
-int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
-                                 const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out)
+static int32_t gcadpcm_decode_one(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                  const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out)
 {
     PinScope pins;
     if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative (%d)", n_channels);
@@ -1231,9 +1441,9 @@ int32_t vgb_adx_calculate_coefficients(int32_t highpass_frequency, int32_t sampl
     return VGB_OK;
 }
 
-int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
-                             int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out, vgb_progress_cb cb,
-                             void *user)
+static int32_t adx_encode_one(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
+                              int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out, vgb_progress_cb cb,
+                              void *user)
 {
     PinScope pins;
     if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
@@ -1308,8 +1518,54 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
     return run_group_pipeline(n_groups, h2d, kern, d2h, done);
 }
 
-int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
-                             const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out)
+/* ---- device-resident ADX encode (see the header) ---- */
+uint64_t vgb_adx_workspace_bytes(int32_t n_channels)
+{
+    if (n_channels < 0) return 0;
+    return align_up((size_t)std::max(n_channels, 1) * sizeof(AdxChannel), 256) + align_up((size_t)std::max(n_channels, 1) * 2, 256);
+}
+
+int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples, const vgb_adx_params *params,
+                           int32_t n_channels, int16_t *d_history_out, uint8_t *d_adpcm, const int64_t *adpcm_offset,
+                           void *d_workspace, uint64_t workspace_bytes, void *cuda_stream)
+{
+    if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
+    if (n_channels == 0) return VGB_OK;
+    if (!d_pcm || !pcm_offset || !n_samples || !params || !d_adpcm || !adpcm_offset || !d_workspace) return fail(VGB_E_ARG, "NULL argument");
+    if (vgb_adx_workspace_bytes(n_channels) > workspace_bytes)
+        return fail(VGB_E_ARG, "workspace too small: need %llu bytes", (unsigned long long)vgb_adx_workspace_bytes(n_channels));
+    std::vector<AdxChannel> tab(n_channels);
+    for (int c = 0; c < n_channels; c++) {
+        const vgb_adx_params &p = params[c];
+        VGB_TRY(adx_validate(p, c));
+        if (n_samples[c] < 0) return fail(VGB_E_ARG, "channel %d: negative sample count", c);
+        if (p.version == 4 && p.padding == 0 && n_samples[c] == 0)
+            return fail(VGB_E_ARG, "channel %d: version 4 without padding needs at least one sample", c);
+        if (pcm_offset[c] < 0 || (pcm_offset[c] & 7) || adpcm_offset[c] < 0 || (adpcm_offset[c] & 1))
+            return fail(VGB_E_ARG, "channel %d: pcm_offset must be a multiple of 8 samples, adpcm_offset even", c);
+        AdxChannel &t = tab[c];
+        t.pcm_off = pcm_offset[c]; t.adpcm_off = adpcm_offset[c]; t.n_samples = n_samples[c];
+        t.frame_size = p.frame_size; t.version = p.version; t.padding = p.padding; t.type = p.type; t.filter = p.filter;
+        t.history = 0;
+        if (p.type == 2) { t.coef0 = kAdxFixed[p.filter][0]; t.coef1 = kAdxFixed[p.filter][1]; }
+        else adx_calc_coefs(500, p.sample_rate, t.coef0, t.coef1);  // Encode hard-codes 500 (:63)
+    }
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    char *ws = static_cast<char *>(d_workspace);
+    int16_t *d_hist = d_history_out ? d_history_out : reinterpret_cast<int16_t *>(ws + align_up(tab.size() * sizeof(AdxChannel), 256));
+    CUDA_TRY(cudaMemcpyAsync(ws, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));  // pageable: staged before return
+    tick(4, true, st);
+    launch_adx_encode(d_pcm, reinterpret_cast<const AdxChannel *>(ws), n_channels, d_adpcm, d_hist, st);
+    tick(4, false, st);
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return VGB_OK;
+}
+
+static int32_t adx_decode_one(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
+                              const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out)
 {
     PinScope pins;
     if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
@@ -1569,11 +1825,7 @@ void hca_channel_types(const vgb_hca_info &h, int32_t types[8])
 
 // One-time upload of the codec tables (per process/device).  Trig tables: Mdct.GenerateTrigTables (Mdct.cs:183-195)
 // with the host libm, exactly as the oracle builds them; dead zones: CriHcaTables.QuantizerDeadZoneFunction (:68-78).
-struct HcaTableStore {
-    bool ready = false;
-    void *blob = nullptr;
-    HcaTables view{};
-} g_hca_tables;
+// (HcaTableStore is a member of the per-device Context: g_hca_tables below is the current device's store)
 
 void hca_tables_release_locked()
 {
@@ -1687,8 +1939,8 @@ int32_t vgb_hca_query(const vgb_hca_params *params, vgb_hca_info *info_out)
     return hca_initialize(*params, *info_out);
 }
 
-int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
-                             vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user)
+static int32_t hca_encode_one(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
+                              vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user)
 {
     PinScope pins;
     if (n_streams < 0) return fail(VGB_E_ARG, "n_streams is negative");
@@ -1809,8 +2061,99 @@ int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *pa
     return VGB_OK;
 }
 
-int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
-                             int16_t *const *pcm_out)
+/* ---- device-resident HCA encode (see the header) ---- */
+uint64_t vgb_hca_workspace_bytes(int32_t n_streams)
+{
+    if (n_streams < 0) return 0;
+    return align_up((size_t)std::max(n_streams, 1) * sizeof(HcaStream), 256) + align_up((size_t)std::max(n_streams, 1) * 4, 256);
+}
+
+int32_t vgb_hca_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int64_t *channel_stride, const vgb_hca_params *params,
+                           int32_t n_streams, vgb_hca_info *info_out, uint8_t *d_frames, const int64_t *frames_offset,
+                           void *d_workspace, uint64_t workspace_bytes, void *cuda_stream)
+{
+    if (n_streams < 0) return fail(VGB_E_ARG, "n_streams is negative");
+    if (n_streams == 0) return VGB_OK;
+    if (!d_pcm || !pcm_offset || !channel_stride || !params || !d_frames || !frames_offset || !d_workspace) return fail(VGB_E_ARG, "NULL argument");
+    if (vgb_hca_workspace_bytes(n_streams) > workspace_bytes)
+        return fail(VGB_E_ARG, "workspace too small: need %llu bytes", (unsigned long long)vgb_hca_workspace_bytes(n_streams));
+    std::vector<vgb_hca_info> infos(n_streams);
+    std::vector<HcaVirtual> virt(n_streams);
+    for (int s = 0; s < n_streams; s++) {
+        VGB_TRY(hca_initialize(params[s], infos[s], &virt[s]));
+        const vgb_hca_params &a = params[0], &b = params[s];
+        if (a.channel_count != b.channel_count || a.sample_rate != b.sample_rate || a.quality != b.quality ||
+            a.bitrate != b.bitrate || a.limit_bitrate != b.limit_bitrate)
+            return fail(VGB_E_ARG, "stream %d: all streams of one call must share channel count, sample rate, quality and bitrate", s);
+    }
+    const vgb_hca_info &h0 = infos[0];
+    const int nch = h0.channel_count;
+    HcaConfig cfg{};
+    cfg.channel_count = nch;
+    cfg.frame_size = h0.frame_size;
+    cfg.base_band_count = h0.base_band_count;
+    cfg.stereo_band_count = h0.stereo_band_count;
+    cfg.total_band_count = h0.total_band_count;
+    cfg.hfr_band_count = h0.hfr_band_count;
+    cfg.bands_per_hfr_group = h0.bands_per_hfr_group;
+    cfg.hfr_group_count = h0.hfr_group_count;
+    hca_channel_types(h0, cfg.channel_type);
+    std::vector<HcaStream> streams(n_streams);
+    int max_frames = 0;
+    for (int s = 0; s < n_streams; s++) {
+        if (pcm_offset[s] < 0 || channel_stride[s] < params[s].sample_count || frames_offset[s] < 0)
+            return fail(VGB_E_ARG, "stream %d: bad offsets (channel_stride must cover sample_count)", s);
+        streams[s].pcm_off = pcm_offset[s];
+        streams[s].channel_stride = channel_stride[s];
+        streams[s].frames_off = frames_offset[s];
+        streams[s].sample_count = infos[s].sample_count;
+        streams[s].frame_count = infos[s].frame_count;
+        streams[s].pre_zero = virt[s].pre_zero;
+        streams[s].pre_fill = virt[s].pre_fill;
+        streams[s].post_count = virt[s].post_count;
+        streams[s].loop_start = virt[s].loop_start;
+        streams[s].src_count = virt[s].src_count;
+        streams[s].last_chunk = virt[s].last_chunk;
+        max_frames = std::max(max_frames, infos[s].frame_count);
+    }
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(hca_tables_ready_locked());
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    char *ws = static_cast<char *>(d_workspace);
+    const size_t o_status = align_up(streams.size() * sizeof(HcaStream), 256);
+    CUDA_TRY(cudaMemcpyAsync(ws, streams.data(), streams.size() * sizeof(HcaStream), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(ws + o_status, 0, (size_t)n_streams * 4, st));
+    tick(6, true, st);
+    CUDA_TRY(launch_hca_encode(d_pcm, reinterpret_cast<const HcaStream *>(ws), n_streams, max_frames, cfg, g_hca_tables.view, d_frames,
+                               reinterpret_cast<int32_t *>(ws + o_status), st));
+    tick(6, false, st);
+    g_ctx.launches += 1;
+    if (info_out) for (int s = 0; s < n_streams; s++) info_out[s] = infos[s];
+    return VGB_OK;
+}
+
+/* Synchronises `cuda_stream` and maps the per-stream status words the last vgb_hca_encode_dev on this workspace left
+ * (the reference's exceptions: Bitrate is set too low, ...). */
+int32_t vgb_hca_encode_dev_status(const void *d_workspace, int32_t n_streams, void *cuda_stream)
+{
+    if (n_streams <= 0) return VGB_OK;
+    if (!d_workspace) return fail(VGB_E_ARG, "NULL argument");
+    std::vector<int32_t> status(n_streams, 0);
+    const size_t o_status = align_up((size_t)n_streams * sizeof(HcaStream), 256);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CUDA_TRY(cudaMemcpyAsync(status.data(), static_cast<const char *>(d_workspace) + o_status, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_streams; s++) {
+        if (status[s] == VGB_HCA_BITRATE_TOO_LOW) return fail(VGB_E_DATA, "stream %d: Bitrate is set too low.", s);
+        if (status[s] == VGB_HCA_NOT_IMPLEMENTED) return fail(VGB_E_STATE, "stream %d: evaluation boundary search failed (NotImplementedException in the reference)", s);
+        if (status[s] == VGB_HCA_BIT_OVERFLOW) return fail(VGB_E_STATE, "stream %d: Not enough bits left in output buffer", s);
+    }
+    return VGB_OK;
+}
+
+static int32_t hca_decode_one(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
+                              int16_t *const *pcm_out)
 {
     PinScope pins;
     if (n_streams < 0) return fail(VGB_E_ARG, "n_streams is negative");
@@ -2066,6 +2409,111 @@ int32_t vgb_deinterleave(const uint8_t *input, int32_t length, int32_t interleav
         CUDA_TRY(cudaMemcpyAsync(outputs[c], static_cast<char *>(g_ctx.pcm.p) + c * pitch, (size_t)out_size, cudaMemcpyDeviceToHost, g_ctx.stream));
     CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
     return VGB_OK;
+}
+
+}  // extern "C"
+
+// ---- public host-pointer entry points: shard over the bound devices, or run on the one device --------------------------
+extern "C" {
+
+int32_t vgb_gcadpcm_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int16_t *coefs,
+                                 const vgb_gc_params *params, int32_t n_channels, int16_t *const *pcm_out)
+{
+    if (!sharding_active(n_channels) || !adpcm || !n_bytes || !coefs || !pcm_out)
+        return gcadpcm_decode_one(adpcm, n_bytes, coefs, params, n_channels, pcm_out);
+    std::vector<int64_t> weight(n_channels);
+    for (int c = 0; c < n_channels; c++) weight[c] = (int64_t)std::max(n_bytes[c], 0) + 64;
+    return run_sharded(shard_units(weight, 1 + (int)g_extra.size()), [&](int, const std::vector<int> &u) -> int32_t {
+        const int m = (int)u.size();
+        auto s_in = pick(adpcm, u);
+        auto s_nb = pick(n_bytes, u);
+        auto s_out = pick(pcm_out, u);
+        std::vector<vgb_gc_params> s_par;
+        if (params) s_par = pick(params, u);
+        std::vector<int16_t> s_co((size_t)m * 16);
+        for (int i = 0; i < m; i++) std::memcpy(&s_co[(size_t)i * 16], coefs + (size_t)u[i] * 16, 32);
+        return gcadpcm_decode_one(s_in.data(), s_nb.data(), s_co.data(), params ? s_par.data() : nullptr, m, s_out.data());
+    });
+}
+
+int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples, const vgb_adx_params *params,
+                             int32_t n_channels, int16_t *history_out, uint8_t *const *adpcm_out, vgb_progress_cb cb, void *user)
+{
+    if (!sharding_active(n_channels) || !pcm || !n_samples || !params || !adpcm_out)
+        return adx_encode_one(pcm, n_samples, params, n_channels, history_out, adpcm_out, cb, user);
+    std::vector<int64_t> weight(n_channels);
+    for (int c = 0; c < n_channels; c++) weight[c] = (int64_t)std::max(n_samples[c], 0) + 64;
+    SharedProgress prog{cb, user, {}};
+    return run_sharded(shard_units(weight, 1 + (int)g_extra.size()), [&](int, const std::vector<int> &u) -> int32_t {
+        const int m = (int)u.size();
+        auto s_pcm = pick(pcm, u);
+        auto s_n = pick(n_samples, u);
+        auto s_par = pick(params, u);
+        auto s_out = pick(adpcm_out, u);
+        std::vector<int16_t> s_hist(m);
+        VGB_TRY(adx_encode_one(s_pcm.data(), s_n.data(), s_par.data(), m, s_hist.data(), s_out.data(), cb ? SharedProgress::relay : nullptr, &prog));
+        if (history_out) for (int i = 0; i < m; i++) history_out[u[i]] = s_hist[i];
+        return VGB_OK;
+    });
+}
+
+int32_t vgb_adx_decode_batch(const uint8_t *const *adpcm, const int32_t *n_bytes, const int32_t *sample_count,
+                             const vgb_adx_params *params, int32_t n_channels, int16_t *const *pcm_out)
+{
+    if (!sharding_active(n_channels) || !adpcm || !n_bytes || !sample_count || !params || !pcm_out)
+        return adx_decode_one(adpcm, n_bytes, sample_count, params, n_channels, pcm_out);
+    std::vector<int64_t> weight(n_channels);
+    for (int c = 0; c < n_channels; c++) weight[c] = (int64_t)std::max(sample_count[c], 0) + 64;
+    return run_sharded(shard_units(weight, 1 + (int)g_extra.size()), [&](int, const std::vector<int> &u) -> int32_t {
+        auto s_in = pick(adpcm, u);
+        auto s_nb = pick(n_bytes, u);
+        auto s_sc = pick(sample_count, u);
+        auto s_par = pick(params, u);
+        auto s_out = pick(pcm_out, u);
+        return adx_decode_one(s_in.data(), s_nb.data(), s_sc.data(), s_par.data(), (int)u.size(), s_out.data());
+    });
+}
+
+int32_t vgb_hca_encode_batch(const int16_t *const *pcm, const vgb_hca_params *params, int32_t n_streams,
+                             vgb_hca_info *info_out, uint8_t *const *frames_out, vgb_progress_cb cb, void *user)
+{
+    if (!sharding_active(n_streams) || !pcm || !params || !frames_out)
+        return hca_encode_one(pcm, params, n_streams, info_out, frames_out, cb, user);
+    const int nch = params[0].channel_count;
+    if (nch < 1 || nch > 8) return hca_encode_one(pcm, params, n_streams, info_out, frames_out, cb, user);
+    std::vector<int64_t> weight(n_streams);
+    for (int s = 0; s < n_streams; s++) weight[s] = (int64_t)std::max(params[s].sample_count, 0) + 1024;
+    SharedProgress prog{cb, user, {}};
+    return run_sharded(shard_units(weight, 1 + (int)g_extra.size()), [&](int, const std::vector<int> &u) -> int32_t {
+        const int m = (int)u.size();
+        std::vector<const int16_t *> s_pcm((size_t)m * nch);
+        for (int i = 0; i < m; i++)
+            for (int c = 0; c < nch; c++) s_pcm[(size_t)i * nch + c] = pcm[(size_t)u[i] * nch + c];
+        auto s_par = pick(params, u);
+        auto s_out = pick(frames_out, u);
+        std::vector<vgb_hca_info> s_info(m);
+        VGB_TRY(hca_encode_one(s_pcm.data(), s_par.data(), m, s_info.data(), s_out.data(), cb ? SharedProgress::relay : nullptr, &prog));
+        if (info_out) for (int i = 0; i < m; i++) info_out[u[i]] = s_info[i];
+        return VGB_OK;
+    });
+}
+
+int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams, int16_t *const *pcm_out)
+{
+    if (!sharding_active(n_streams) || !frames || !info || !pcm_out) return hca_decode_one(frames, info, n_streams, pcm_out);
+    const int nch = info[0].channel_count;
+    if (nch < 1 || nch > 8) return hca_decode_one(frames, info, n_streams, pcm_out);
+    std::vector<int64_t> weight(n_streams);
+    for (int s = 0; s < n_streams; s++) weight[s] = (int64_t)std::max(info[s].frame_count, 0) + 1;
+    return run_sharded(shard_units(weight, 1 + (int)g_extra.size()), [&](int, const std::vector<int> &u) -> int32_t {
+        const int m = (int)u.size();
+        auto s_in = pick(frames, u);
+        auto s_info = pick(info, u);
+        std::vector<int16_t *> s_out((size_t)m * nch);
+        for (int i = 0; i < m; i++)
+            for (int c = 0; c < nch; c++) s_out[(size_t)i * nch + c] = pcm_out[(size_t)u[i] * nch + c];
+        return hca_decode_one(s_in.data(), s_info.data(), m, s_out.data());
+    });
 }
 
 }  // extern "C"
