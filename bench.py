@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--channels", type=int, default=1024, help="channels per GPU")
     ap.add_argument("--seconds", type=float, default=30.0, help="audio seconds per channel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration: c2 GC-ADPCM encode (default, the headline), c3 GC-ADPCM decode of 8192 channels, "
+                         "c4 HCA encode of 512 streams, c5 65 536-file mixed batch with NCCL scatter/gather (strong scaling)")
+    ap.add_argument("--files", type=int, default=65536, help="c5: number of files in the whole job")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -59,7 +63,7 @@ def env_rank():
 # ------------------------------------------------------------------------------------------------------------
 # synthetic data (same recipe as vgaudio_b200/synth.py, generated on the GPU because the batch is 1.5e9 samples)
 # ------------------------------------------------------------------------------------------------------------
-def make_batch_gpu(torch, n_channels: int, n: int, rank: int, device):
+def make_batch_gpu(torch, n_channels: int, n: int, rank: int, device, degenerate: bool = True):
     g = torch.Generator(device=device)
     g.manual_seed(0x5647415544494F + 7919 * rank)
     out = torch.empty((n_channels, n), dtype=torch.int16, device=device)
@@ -91,7 +95,7 @@ def make_batch_gpu(torch, n_channels: int, n: int, rank: int, device):
         out[c0:c0 + m] = torch.clamp(torch.round(x), -32768, 32767).to(torch.int16)
         del x, in_burst, sign, full, within
     # degenerate channels (all-zero, Nyquist/4 square) as in the test generator
-    if n_channels >= 4:
+    if n_channels >= 4 and degenerate:
         out[0].zero_()
         out[1] = torch.where((torch.arange(n, device=device) // 4) % 2 == 0, 32767, -32768).to(torch.int16)
     return out
@@ -234,6 +238,17 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     N.check(vg.lib.vgb_init(local_rank, 0))
+
+    if args.config != "c2":
+        import bench_configs
+
+        ctx = {"torch": torch, "dist": dist, "vg": vg, "N": N, "bench": sys.modules[__name__]}
+        line = getattr(bench_configs, "run_" + args.config)(args, (rank, local_rank, world), ctx)
+        if rank == 0 and line is not None:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- data + HBM layout -----------------------------------------------------------------------------------
     pcm = make_batch_gpu(torch, n_ch, n, rank, device)
