@@ -426,7 +426,7 @@ def run_c5(args, env, ctx):
     gc_frames = int(((gc_lens.astype(np.int64) + 13) // 14).sum())
     gws_bytes = int(vg.lib.vgb_gcadpcm_workspace_bytes(gc_frames, max(n_gc, 1)))
     gws = torch.empty(gws_bytes, dtype=torch.uint8, device=device)
-    aws_bytes = int(vg.lib.vgb_adx_workspace_bytes(max(n_adx, 1)))
+    aws_bytes = int(vg.lib.vgb_adx_workspace_bytes(int(adx_lens.astype(np.int64).sum()), max(n_adx, 1)))
     aws = torch.empty(aws_bytes, dtype=torch.uint8, device=device)
     adx_params = (N.VgbAdxParams * max(n_adx, 1))()
     for i in range(n_adx):

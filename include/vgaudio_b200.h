@@ -273,9 +273,10 @@ int32_t vgb_adx_encode_batch(const int16_t *const *pcm, const int32_t *n_samples
 
 /* Device-resident variant of vgb_adx_encode_batch (same semantics, asynchronous on `cuda_stream`): d_pcm / d_adpcm are HBM
  * slabs, channel c at pcm_offset[c] samples (a multiple of 8) / adpcm_offset[c] bytes (even); d_history_out ([n] shorts)
- * may be NULL; d_workspace holds the channel table (vgb_adx_workspace_bytes).  The multi-GPU batch path and bench.py's
+ * may be NULL; d_workspace holds the channel table and the bookkeeping of the time-parallel encoder (one word per
+ * 32-sample frame; vgb_adx_workspace_bytes(total samples, channels)).  The multi-GPU batch path and bench.py's
  * device-resident figures use it. */
-uint64_t vgb_adx_workspace_bytes(int32_t n_channels);
+uint64_t vgb_adx_workspace_bytes(int64_t total_samples, int32_t n_channels);
 int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples, const vgb_adx_params *params,
                            int32_t n_channels, int16_t *d_history_out, uint8_t *d_adpcm, const int64_t *adpcm_offset,
                            void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);

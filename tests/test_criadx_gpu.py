@@ -98,3 +98,40 @@ def test_errors(vg):
         vg.criadx.decode(np.zeros(18, dtype=np.uint8), 100, _cfg(vg))
     with pytest.raises(vg.VgbError):
         vg.criadx.encode_batch([np.zeros(10, dtype=np.int16)], [_cfg(vg, type=7)])
+
+
+@pytest.mark.parametrize("seg", [1, 2, 7, 64, None])
+def test_time_parallel_encode_is_bit_exact(vg, oracle, seg):
+    """The ADX encoder cuts a channel's whole frames into segments encoded concurrently from raw history and splices them
+    at the boundaries (adx.cu); VGB_ADX_SEGMENTS forces the count.  Mixed batch: every type / version, ragged lengths with
+    partial last frames, full-scale noise and squares (slow to re-lock), and channels the segmentation must leave to the
+    serial loop (another frame size, padding)."""
+    import os
+
+    rng = np.random.default_rng(31)
+    lens = [32 * 2000, 32 * 2000 + 17, 32 * 3000 + 1, 32 * 700, 32 * 256 * 3, 32 * 5000 + 31, 40, 32 * 2500, 32 * 2200 + 9, 32 * 2100]
+    chans = [synth.channel(40 + i, L) for i, L in enumerate(lens)]
+    chans[3] = rng.integers(-32768, 32768, lens[3]).astype(np.int16)                       # white, full scale
+    chans[7] = np.where((np.arange(lens[7]) // 2) % 2 == 0, 32767, -32768).astype(np.int16)  # Nyquist/2 square
+    cfgs = [_cfg(vg, sample_rate=48000, version=4 - (i % 2), type=2 + (i % 3), filter=i % 4) for i in range(len(chans))]
+    cfgs[8] = _cfg(vg, sample_rate=44100, frame_size=34, version=4, type=3)   # not the standard layout
+    cfgs[9] = _cfg(vg, sample_rate=48000, padding=45, version=4, type=3)      # padded stream
+    saved = os.environ.get("VGB_ADX_SEGMENTS")
+    if seg is None:
+        os.environ.pop("VGB_ADX_SEGMENTS", None)
+    else:
+        os.environ["VGB_ADX_SEGMENTS"] = str(seg)
+    try:
+        adpcm, hist = vg.criadx.encode_batch(chans, cfgs)
+    finally:
+        if saved is None:
+            os.environ.pop("VGB_ADX_SEGMENTS", None)
+        else:
+            os.environ["VGB_ADX_SEGMENTS"] = saved
+    for c, pcm in enumerate(chans):
+        p = cfgs[c]
+        want, want_hist = oracle.adx_encode(pcm, p.sample_rate, p.frame_size, p.version, p.padding, p.type, p.filter)
+        got = np.frombuffer(adpcm[c].tobytes(), np.uint8)
+        first = np.flatnonzero(got != want)
+        assert first.size == 0, f"seg {seg} channel {c}: first differing byte {first[0]} (frame {first[0] // p.frame_size})"
+        assert int(hist[c]) == want_hist, c

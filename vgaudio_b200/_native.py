@@ -107,7 +107,7 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "vgb_adx_calculate_coefficients": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p]),
     "vgb_adx_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
-    "vgb_adx_workspace_bytes": (C.c_uint64, [C.c_int32]),
+    "vgb_adx_workspace_bytes": (C.c_uint64, [C.c_int64, C.c_int32]),
     "vgb_adx_encode_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_void_p]),
     "vgb_hca_workspace_bytes": (C.c_uint64, [C.c_int32]),

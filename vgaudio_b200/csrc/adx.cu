@@ -11,6 +11,8 @@
 // (encoder, four 16-byte chunks) or 8 frames' 144 bytes (decoder, nine chunks) into the thread's own shared-memory ring
 // two steps ahead, results leave as halfword / 16-byte stores straight from registers (partial sectors merge in L2), so
 // DRAM latency never reaches the recurrence.  Other frame sizes / padded streams / a partial last frame take the general loop.
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -49,112 +51,128 @@ __device__ __forceinline__ int32_t adx_imad(int32_t a, int32_t b, int32_t c)
     return d;
 }
 
-__global__ void __launch_bounds__(kAdxThreads)
-adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict__ tab, int n_channels,
-                  uint8_t *__restrict__ adpcm, int16_t *__restrict__ history_out)
+// ---------------------------------------------------------------------------------------------------------
+// The quantiser of pass 2 (:126,:167-171) in integers.  Reference:
+//     scaled = Clamp16((int)(raw * gain)),  gain = 32767.0 / maxDistance (double);   q = Clamp4((scaled +- 2340) / 4681)
+// q only counts how many of the thresholds T_k = 4681 k - 2340 (k = 1..7) |scaled| reaches, and truncation / Clamp16 do
+// not move a value across an integer threshold, so with a = |raw|:
+//     q = sign(raw) * #{ k : a * 32767 >= T_k * maxDistance }
+// (the two fp64 roundings move the product by < 1e-11 while a * 32767 / maxDistance is at least 1 / maxDistance away
+// from T_k unless equal, which the factorisation 32767 = 7 * 31 * 151 restricts to maxDistance = 4681 j).  Two corner
+// cases: maxDistance == 0 gives gain 0 and q = 0; a * 32767 >= 2^31 * maxDistance overflows the (int) cast, which is
+// INT_MIN on x64, hence q = -7 whatever the sign.  tools/adx_quantiser_check.c enumerates the identity for every
+// maxDistance (0..32768) around every threshold and over the full raw range for small maxDistance: 0 mismatches.
+// Per frame: the seven products M_k = T_k * maxDistance (< 2^30) and the overflow bound; per sample a three-step
+// binary search over them instead of int->double, fp64 multiply, double->int, a division by 4681 and two clamps.
+// ---------------------------------------------------------------------------------------------------------
+struct AdxQuant {
+    uint32_t m[8];     // m[k] = T_k * maxDistance for k = 1..7 (m[0] unused)
+    uint32_t ovf;      // smallest |raw| whose product leaves int32 (0xFFFFFFFF: none below 2^18)
+    bool zero;         // maxDistance == 0
+};
+__device__ __forceinline__ AdxQuant adx_quant_setup(int32_t max_distance)
 {
-    __shared__ __align__(16) uint4 enc_ring[kAdxStages][4][kAdxThreads];  // [stage][16-byte chunk of the frame][thread]
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= n_channels) return;
-    const AdxChannel c = tab[ch];
-    const int16_t *src = pcm + c.pcm_off;
-    uint8_t *dst = adpcm + c.adpcm_off;
+    AdxQuant qz;
+#pragma unroll
+    for (int k = 1; k < 8; k++) qz.m[k] = (uint32_t)(4681 * k - 2340) * (uint32_t)max_distance;
+    qz.m[0] = 0;
+    qz.zero = max_distance == 0;
+    // a * 32767 >= 2^31 * md  <=>  a >= ceil(2^31 * md / 32767); only md <= 3 can be reached by |raw| < 2^18
+    qz.ovf = (max_distance >= 1 && max_distance <= 3) ? (uint32_t)((((uint64_t)max_distance << 31) + 32766u) / 32767u) : 0xFFFFFFFFu;
+    return qz;
+}
+__device__ __forceinline__ int32_t adx_quantise(int32_t raw, const AdxQuant &qz)
+{
+    const uint32_t a = (uint32_t)abs(raw);
+    const uint32_t v = min(a, 65535u) * 32767u;  // |raw| >= 30428 already reaches T_7 for every maxDistance <= 32768
+    const bool c4 = v >= qz.m[4];
+    const bool c2 = v >= (c4 ? qz.m[6] : qz.m[2]);
+    const bool c1 = v >= (c4 ? (c2 ? qz.m[7] : qz.m[5]) : (c2 ? qz.m[3] : qz.m[1]));
+    const int32_t k = (c4 ? 4 : 0) + (c2 ? 2 : 0) + (c1 ? 1 : 0);
+    int32_t q = raw < 0 ? -k : k;
+    q = a >= qz.ovf ? -7 : q;
+    return qz.zero ? 0 : q;
+}
+
+// EncodeFrame (:107-147) for one whole frame of the standard layout (32 samples in x[], history h2 = pcm[0],
+// h1 = pcm[1]); writes the 18 bytes at out16 and leaves the reconstructed pair in (h1, h2).
+template <bool kV4>
+__device__ __forceinline__ void adx_encode_frame_std(const int32_t (&x)[32], int32_t c0, int32_t c1, bool exponential, int type, int filter,
+                                                     int32_t &h1, int32_t &h2, uint16_t *out16)
+{
+    int32_t max_distance = 0;  // pass 1 (:112-118): neighbours are RAW samples except for the two history slots
+    {
+        int32_t p0 = h2, p1 = h1;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const int32_t predicted = (wmul(p1, c0) >> 12) + (wmul(p0, c1) >> 12);
+            max_distance = max(max_distance, abs(clamp16(x[i] - predicted)));
+            p0 = p1;
+            p1 = x[i];
+        }
+    }
+    int32_t scale = (max_distance - 1) / 7 + 1;  // CalculateScale (:149-165)
+    if (scale > 0x1000) scale = 0x1000;
+    int32_t scale_out = scale - 1;
+    if (exponential) {
+        const int power = scale_out == 0 ? 0 : (31 - __clz(scale_out)) + 1;
+        scale = 1 << power;
+        scale_out = 12 - power;
+        max_distance = 8 * scale - 1;
+    }
+    const AdxQuant qz = adx_quant_setup(max_distance);  // gain = 32767.0 / maxDistance, in integers
+    const uint32_t hdr0 = ((uint32_t)(scale_out >> 8) & 0x1fu) | (type == 2 ? (uint32_t)(filter << 5) : 0u);
+    out16[0] = (uint16_t)((hdr0 & 0xFFu) | (((uint32_t)scale_out & 0xFFu) << 8));  // :140-141
+    // pass 2 (:122-138).  Clamp16(scale * q) (:131) is the identity here: scale <= 0x1000 (:151-163) and q in [-8, 7]
+    // give a product in [-32768, 28672], so it is left out of the dependent chain.
+    uint32_t hw = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
+        const int32_t q = adx_quantise(x[i] - predicted, qz);
+        if (kV4) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
+        const int32_t recon = clamp16(wmul(scale, q) + predicted);
+        h2 = h1;
+        h1 = recon;
+        // byte = (q_even << 4) | q_odd; halfword = byte0 | byte1 << 8
+        const int sh = ((i & 1) ? 0 : 4) + ((i & 2) ? 8 : 0);
+        hw |= ((uint32_t)q & 0xFu) << sh;
+        if ((i & 3) == 3) { out16[1 + (i >> 2)] = (uint16_t)hw; hw = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TIME-PARALLEL ENCODING, as for GC-ADPCM (gc_encode.cu): a frame depends on its predecessors only through the two
+// reconstructed samples it starts from (:98-99,:137), and the fixed high-pass predictor (pole radius ~0.9) forgets a
+// wrong pair within a handful of frames.  The whole frames of a standard-layout channel are cut into seg_count segments:
+//   kAdxChain    thread = (channel, segment): segment 0 from the true history, the others from the raw samples in
+//                front of them; bytes and, per frame, the pair handed on (`trace`) are written
+//   kAdxRunOn    thread = (channel, boundary): the chain of segment s-1 runs on into segment s until its pair equals the
+//                recorded one (from there the recorded chain is the true one), inside its segment, noting its start pair
+//   kAdxCascade  thread = channel: repairs a boundary whose predecessor's end pair changed afterwards (serially, across
+//                segment ends if need be), then encodes the partial last frame from the true pair
+// Exact by construction: the only test is equality of two int16 pairs.  Channels with another frame size or padding
+// keep the plain serial loop (segment 0's thread).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAdxChain = 0, kAdxRunOn = 1, kAdxCascade = 2;
+__host__ __device__ __forceinline__ int adx_seg_len(int whole_frames, int seg_count, int min_seg)
+{
+    const int per = (whole_frames + (seg_count > 0 ? seg_count : 1) - 1) / (seg_count > 0 ? seg_count : 1);
+    return per < min_seg ? min_seg : per;
+}
+
+// General loop of Encode (:76-101): any frame size, padding, partial frames; frames [f_first, frame_count).
+__device__ void adx_encode_general(const AdxChannel &c, const int16_t *__restrict__ src, uint8_t *__restrict__ dst, int f_first,
+                                   int32_t &h1, int32_t &h2)
+{
     const int spf = (c.frame_size - 2) * 2;
     const int sample_count = c.n_samples + c.padding;            // :59
     const int frame_count = div_round_up(sample_count, spf);     // :61
     const int32_t c0 = c.coef0, c1 = c.coef1;
     const bool v4 = c.version == 4;
     const bool exponential = c.type == 4;
-
-    int32_t h2 = 0, h1 = 0;  // pcmBuffer[0], pcmBuffer[1]
-    int16_t hist_cfg = 0;
-    if (v4 && c.padding == 0 && c.n_samples > 0) {  // :69-74
-        h2 = h1 = src[0];
-        hist_cfg = src[0];
-    }
-    if (history_out) history_out[ch] = hist_cfg;
-
-    int f_first = 0;
-    if (c.frame_size == 18 && c.padding == 0) {
-        // ---- standard layout: whole frames of 32 samples straight from registers
-        const int whole = c.n_samples / 32;
-        const uint4 *vin = reinterpret_cast<const uint4 *>(src);  // pcm_off is a multiple of 8 samples
-        auto issue = [&](int f) {  // frame f -> ring stage f % kAdxStages (cp.async: no register scoreboard to wait on)
-            if (f < whole) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) cp_async16(&enc_ring[f % kAdxStages][j][threadIdx.x], vin + (int64_t)f * 4 + j);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-#pragma unroll
-        for (int a = 0; a < kAdxStages - 1; a++) issue(a);
-        for (int f = 0; f < whole; f++) {
-            issue(f + kAdxStages - 1);
-            asm volatile("cp.async.wait_group %0;" ::"n"(kAdxStages - 1) : "memory");
-            int32_t x[32];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint4 v = enc_ring[f % kAdxStages][j][threadIdx.x];
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    x[8 * j + 2 * k] = (int32_t)(int16_t)(w[k] & 0xFFFFu);
-                    x[8 * j + 2 * k + 1] = (int32_t)w[k] >> 16;
-                }
-            }
-            int32_t max_distance = 0;  // pass 1 (:112-118)
-            {
-                int32_t p0 = h2, p1 = h1;
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const int32_t predicted = (wmul(p1, c0) >> 12) + (wmul(p0, c1) >> 12);
-                    max_distance = max(max_distance, abs(clamp16(x[i] - predicted)));
-                    p0 = p1;
-                    p1 = x[i];
-                }
-            }
-            int32_t scale = (max_distance - 1) / 7 + 1;  // CalculateScale (:149-165)
-            if (scale > 0x1000) scale = 0x1000;
-            int32_t scale_out = scale - 1;
-            if (exponential) {
-                const int power = scale_out == 0 ? 0 : (31 - __clz(scale_out)) + 1;
-                scale = 1 << power;
-                scale_out = 12 - power;
-                max_distance = 8 * scale - 1;
-            }
-            const double gain = max_distance == 0 ? 0.0 : __ddiv_rn(32767.0, (double)max_distance);
-            uint16_t *out16 = reinterpret_cast<uint16_t *>(dst + (int64_t)f * 18);  // adpcm_off is even
-            const uint32_t hdr0 = ((uint32_t)(scale_out >> 8) & 0x1fu) | (c.type == 2 ? (uint32_t)(c.filter << 5) : 0u);
-            out16[0] = (uint16_t)((hdr0 & 0xFFu) | (((uint32_t)scale_out & 0xFFu) << 8));  // :140-141
-            // pass 2 (:122-138); the version test is hoisted (two copies of the loop instead of predicating both).
-            // Clamp16(scale * q) (:131) is the identity here: scale <= 0x1000 (:151-163) and q in [-8, 7] give a product
-            // in [-32768, 28672], so it is left out of the dependent chain.
-            auto pass2 = [&](auto is_v4) {
-                uint32_t hw = 0;
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
-                    const int32_t raw = x[i] - predicted;
-                    const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
-                    const int32_t q = adx_short_to_nibble(scaled);
-                    const int32_t decoded_distance = wmul(scale, q);
-                    if (decltype(is_v4)::value) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
-                    const int32_t recon = clamp16(decoded_distance + predicted);
-                    h2 = h1;
-                    h1 = recon;
-                    // byte = (q_even << 4) | q_odd; halfword = byte0 | byte1 << 8
-                    const int sh = ((i & 1) ? 0 : 4) + ((i & 2) ? 8 : 0);
-                    hw |= ((uint32_t)q & 0xFu) << sh;
-                    if ((i & 3) == 3) { out16[1 + (i >> 2)] = (uint16_t)hw; hw = 0; }
-                }
-            };
-            if (v4) pass2(std::true_type{}); else pass2(std::false_type{});
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        f_first = whole;
-    }
-
     int padding_remaining = c.padding;
+    for (int f = 0; f < f_first && padding_remaining != 0; f++) padding_remaining -= min(padding_remaining, min(sample_count - f * spf, spf));
     for (int f = f_first; f < frame_count; f++) {
         int to_copy = min(sample_count - f * spf, spf);  // :78
         int lead = 0;                                    // zero samples in front (pcmBufferStart - 2)
@@ -174,7 +192,6 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
             const int k = i - lead;
             return (k >= 0 && k < to_copy) ? (int32_t)__ldg(src + first + k) : 0;
         };
-
         // pass 1 (:112-118): neighbours are the RAW samples except for the two history slots
         int32_t max_distance = 0;
         {
@@ -182,14 +199,12 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
             for (int i = 0; i < spf; i++) {
                 const int32_t cur = sample_at(i);
                 const int32_t predicted = (wmul(p1, c0) >> 12) + (wmul(p0, c1) >> 12);
-                const int32_t distance = abs(clamp16(cur - predicted));
-                max_distance = max(max_distance, distance);
+                max_distance = max(max_distance, abs(clamp16(cur - predicted)));
                 p0 = p1;
                 p1 = cur;
             }
         }
-        // CalculateScale (:149-165)
-        int32_t scale = (max_distance - 1) / 7 + 1;
+        int32_t scale = (max_distance - 1) / 7 + 1;  // CalculateScale (:149-165)
         if (scale > 0x1000) scale = 0x1000;
         int32_t scale_out = scale - 1;
         if (exponential) {
@@ -198,8 +213,7 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
             scale_out = 12 - power;
             max_distance = 8 * scale - 1;
         }
-        const double gain = max_distance == 0 ? 0.0 : __ddiv_rn(32767.0, (double)max_distance);
-
+        const AdxQuant qz = adx_quant_setup(max_distance);
         // pass 2 (:122-138): quantise + reconstruct, feeding the reconstruction back
         uint32_t pair = 0;
         out[0] = (uint8_t)(((scale_out >> 8) & 0x1f) | (c.type == 2 ? (c.filter << 5) : 0));  // :140, :95
@@ -207,9 +221,7 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
         for (int i = 0; i < spf; i++) {
             const int32_t cur = sample_at(i);
             int32_t predicted = (wmul(h1, c0) >> 12) + (wmul(h2, c1) >> 12);
-            const int32_t raw = cur - predicted;
-            const int32_t scaled = clamp16(cast_double_to_int_x64(__dmul_rn((double)raw, gain)));
-            const int32_t q = adx_short_to_nibble(scaled);
+            const int32_t q = adx_quantise(cur - predicted, qz);
             const int32_t decoded_distance = clamp16(wmul(scale, q));
             if (v4) predicted = wadd(wmul(h1, c0), wmul(h2, c1)) >> 12;
             const int32_t recon = clamp16(decoded_distance + predicted);
@@ -218,6 +230,132 @@ adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict_
             if (i & 1) out[2 + (i >> 1)] = (uint8_t)(pair | (uint32_t)(q & 0xF));  // CombineNibbles (:145)
             else pair = (uint32_t)(q << 4) & 0xF0u;
         }
+    }
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kAdxThreads)
+adx_encode_kernel(const int16_t *__restrict__ pcm, const AdxChannel *__restrict__ tab, int n_channels,
+                  uint8_t *__restrict__ adpcm, int16_t *__restrict__ history_out, AdxSegArgs sa)
+{
+    __shared__ __align__(16) uint4 enc_ring[kAdxStages][4][kAdxThreads];  // [stage][16-byte chunk of the frame][thread]
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_channels) return;
+    const AdxChannel c = tab[ch];
+    const int16_t *src = pcm + c.pcm_off;
+    uint8_t *dst = adpcm + c.adpcm_off;
+    const int32_t c0 = c.coef0, c1 = c.coef1;
+    const bool v4 = c.version == 4;
+    const bool exponential = c.type == 4;
+    const bool standard = c.frame_size == 18 && c.padding == 0;
+    const int whole = standard ? c.n_samples / 32 : 0;            // frames of the standard layout with all 32 samples
+    const int seg_len = adx_seg_len(whole, sa.seg_count, sa.min_seg_frames);
+    uint32_t *trace = sa.trace + c.trace_off;                     // [frame] recon pair handed on: (h1 & 0xFFFF) | h2 << 16
+    uint32_t *used_start = sa.used_start + (int64_t)ch * sa.seg_count;
+
+    // frames [f_lo, f_hi) of the standard layout from the pair (h1, h2); kSplice: stop once the pair after a frame equals
+    // the recorded one.  Returns the number of frames encoded.
+    auto run = [&](int f_lo, int f_hi, int32_t &h1, int32_t &h2, bool splice) -> int {
+        const uint4 *vin = reinterpret_cast<const uint4 *>(src);  // pcm_off is a multiple of 8 samples
+        auto issue = [&](int f) {  // frame f -> ring stage (cp.async: no register scoreboard to wait on)
+            if (f < f_hi) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) cp_async16(&enc_ring[(f - f_lo) % kAdxStages][j][threadIdx.x], vin + (int64_t)f * 4 + j);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int a = 0; a < kAdxStages - 1; a++) issue(f_lo + a);
+        int done = 0;
+        for (int f = f_lo; f < f_hi; f++) {
+            issue(f + kAdxStages - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kAdxStages - 1) : "memory");
+            int32_t x[32];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = enc_ring[(f - f_lo) % kAdxStages][j][threadIdx.x];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    x[8 * j + 2 * k] = (int32_t)(int16_t)(w[k] & 0xFFFFu);
+                    x[8 * j + 2 * k + 1] = (int32_t)w[k] >> 16;
+                }
+            }
+            uint16_t *out16 = reinterpret_cast<uint16_t *>(dst + (int64_t)f * 18);  // adpcm_off is even
+            if (v4) adx_encode_frame_std<true>(x, c0, c1, exponential, c.type, c.filter, h1, h2, out16);
+            else adx_encode_frame_std<false>(x, c0, c1, exponential, c.type, c.filter, h1, h2, out16);
+            const uint32_t pair = ((uint32_t)h1 & 0xFFFFu) | ((uint32_t)h2 << 16);
+            done++;
+            if (splice && trace[f] == pair) break;  // the recorded chain continues from exactly this pair
+            trace[f] = pair;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return done;
+    };
+
+    if (kMode == kAdxChain) {
+        const int s = blockIdx.y;
+        int32_t h2 = 0, h1 = 0;  // pcmBuffer[0], pcmBuffer[1]
+        if (s == 0) {
+            int16_t hist_cfg = 0;
+            if (v4 && c.padding == 0 && c.n_samples > 0) {  // :69-74
+                h2 = h1 = src[0];
+                hist_cfg = src[0];
+            }
+            if (history_out) history_out[ch] = hist_cfg;
+        }
+        if (!standard) {
+            if (s == 0) adx_encode_general(c, src, dst, 0, h1, h2);
+            return;
+        }
+        const int f_lo = s * seg_len, f_hi = min(f_lo + seg_len, whole);
+        if (f_lo < f_hi) {
+            if (s > 0) {  // speculative start: the raw samples in front of the segment
+                h1 = src[(int64_t)f_lo * 32 - 1];
+                h2 = src[(int64_t)f_lo * 32 - 2];
+            }
+            run(f_lo, f_hi, h1, h2, false);
+        }
+        // a single-segment launch has no cascade: the partial last frame follows right here
+        if (sa.seg_count == 1 && s == 0) adx_encode_general(c, src, dst, whole, h1, h2);
+        return;
+    }
+    if (!standard) return;
+    if (kMode == kAdxRunOn) {
+        const int s = blockIdx.y + 1;
+        const int f_lo = s * seg_len, f_hi = min(f_lo + seg_len, whole);
+        if (f_lo >= f_hi) return;
+        const uint32_t start = trace[f_lo - 1];
+        used_start[s] = start;
+        int32_t h1 = (int32_t)(int16_t)(start & 0xFFFFu), h2 = (int32_t)(int16_t)(start >> 16);
+        const int done = run(f_lo, f_hi, h1, h2, true);
+        atomicAdd(&sa.stats[0], (unsigned long long)done);
+        return;
+    }
+    // cascade: one thread per channel walks the boundaries in order
+    int truth_upto = 0;
+    for (int s = 1; s < sa.seg_count; s++) {
+        const int f_lo = s * seg_len;
+        if (f_lo >= whole) break;
+        if (f_lo < truth_upto) continue;
+        const uint32_t start = trace[f_lo - 1];
+        if (start == used_start[s]) continue;
+        int32_t h1 = (int32_t)(int16_t)(start & 0xFFFFu), h2 = (int32_t)(int16_t)(start >> 16);
+        const int done = run(f_lo, whole, h1, h2, true);
+        truth_upto = f_lo + done;
+        atomicAdd(&sa.stats[1], (unsigned long long)done);
+        atomicAdd(&sa.stats[2], 1ull);
+    }
+    {   // the partial last frame (and nothing else) from the true pair
+        int32_t h1 = 0, h2 = 0;
+        if (whole > 0) {
+            const uint32_t last = trace[whole - 1];
+            h1 = (int32_t)(int16_t)(last & 0xFFFFu);
+            h2 = (int32_t)(int16_t)(last >> 16);
+        } else if (v4 && c.n_samples > 0) {
+            h2 = h1 = src[0];
+        }
+        adx_encode_general(c, src, dst, whole, h1, h2);
     }
 }
 
@@ -356,11 +494,33 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
     for (; current < sample_count; current++) dst[current] = 0;
 }
 
+// Segments per channel of the time-parallel ADX encode: thread-per-item kernels want every SM full of threads
+// (~512 resident per SM at this register count), the run-on at a boundary is a handful of frames.
+int adx_encode_pick_segments(int n_channels, int max_whole_frames)
+{
+    if (const char *env = std::getenv("VGB_ADX_SEGMENTS")) {
+        const int v = std::atoi(env);
+        if (v >= 1) return v > kAdxMaxSegments ? kAdxMaxSegments : v;
+    }
+    const int max_s = std::max(1, std::min(kAdxMaxSegments, max_whole_frames / kAdxMinSegFrames));
+    const long long want = (4ll * 148 * 512 + n_channels - 1) / std::max(n_channels, 1);  // about four waves of threads
+    return (int)std::max<long long>(1, std::min<long long>(want, max_s));
+}
+
 void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
-                       cudaStream_t stream)
+                       AdxSegArgs sa, cudaStream_t stream)
 {
     if (n_channels <= 0) return;
-    adx_encode_kernel<<<(n_channels + kAdxThreads - 1) / kAdxThreads, kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out);
+    if (sa.seg_count < 1 || !sa.trace) sa.seg_count = 1;
+    if (sa.seg_count > kAdxMaxSegments) sa.seg_count = kAdxMaxSegments;
+    sa.min_seg_frames = kAdxMinSegFrames;
+    const int blocks = (n_channels + kAdxThreads - 1) / kAdxThreads;
+    if (sa.stats) cudaMemsetAsync(sa.stats, 0, 4 * sizeof(unsigned long long), stream);
+    adx_encode_kernel<kAdxChain><<<dim3(blocks, sa.seg_count), kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out, sa);
+    if (sa.seg_count > 1) {
+        adx_encode_kernel<kAdxRunOn><<<dim3(blocks, sa.seg_count - 1), kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out, sa);
+        adx_encode_kernel<kAdxCascade><<<dim3(blocks, 1), kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out, sa);
+    }
 }
 
 void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, int32_t *status, cudaStream_t stream)

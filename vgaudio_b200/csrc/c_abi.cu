@@ -433,6 +433,28 @@ void try_pin(const void *p, size_t bytes)
         (void)cudaGetLastError();  // stay pageable
 }
 
+// Many small copies in one driver call (cudaMemcpyBatchAsync, CUDA 12.8+): a ragged batch of tens of thousands of short
+// files otherwise spends more host time in cudaMemcpyAsync calls (~5 us each) than the copies take on the link.  Falls
+// back to one call per copy when the batched call is refused.
+int32_t copy_many(std::vector<void *> &dsts, std::vector<void *> &srcs, std::vector<size_t> &sizes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    const size_t n = sizes.size();
+    if (n == 0) return VGB_OK;
+    static bool batch_ok = std::getenv("VGB_NO_MEMCPY_BATCH") == nullptr;
+    if (batch_ok && n >= 16) {
+        cudaMemcpyAttributes attr{};
+        attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;  // sources stay valid until the call returns (we synchronise)
+        attr.flags = 0;
+        size_t attr_idx = 0, fail_idx = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), n, &attr, &attr_idx, 1, &fail_idx, stream);
+        if (e == cudaSuccess) return VGB_OK;
+        (void)cudaGetLastError();
+        batch_ok = false;  // e.g. an older driver: stay on the per-copy path for the rest of the process
+    }
+    for (size_t i = 0; i < n; i++) CUDA_TRY(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], kind, stream));
+    return VGB_OK;
+}
+
 // Host -> device copy of every channel's bytes: one strided 2D copy when the caller's buffers form a slab,
 // else one copy per channel.
 template <typename T>
@@ -455,12 +477,16 @@ int32_t copy_channels_in(char *d_base, const std::vector<int64_t> &d_off_bytes, 
             return VGB_OK;
         }
     }
+    std::vector<void *> dsts, srcs;
+    std::vector<size_t> sizes;
     for (int c = 0; c < n; c++)
         if (bytes[c] > 0) {
             try_pin(h_ptr[c], (size_t)bytes[c]);
-            CUDA_TRY(cudaMemcpyAsync(d_base + d_off_bytes[c], h_ptr[c], (size_t)bytes[c], cudaMemcpyHostToDevice, stream));
+            dsts.push_back(d_base + d_off_bytes[c]);
+            srcs.push_back(const_cast<void *>(static_cast<const void *>(h_ptr[c])));
+            sizes.push_back((size_t)bytes[c]);
         }
-    return VGB_OK;
+    return copy_many(dsts, srcs, sizes, cudaMemcpyHostToDevice, stream);
 }
 
 template <typename T>
@@ -482,10 +508,15 @@ int32_t copy_channels_out(T *const *h_ptr, const char *d_base, const std::vector
             return VGB_OK;
         }
     }
+    std::vector<void *> dsts, srcs;
+    std::vector<size_t> sizes;
     for (int c = 0; c < n; c++)
-        if (bytes[c] > 0)
-            CUDA_TRY(cudaMemcpyAsync(h_ptr[c], d_base + d_off_bytes[c], (size_t)bytes[c], cudaMemcpyDeviceToHost, stream));
-    return VGB_OK;
+        if (bytes[c] > 0) {
+            dsts.push_back(static_cast<void *>(h_ptr[c]));
+            srcs.push_back(const_cast<char *>(d_base + d_off_bytes[c]));
+            sizes.push_back((size_t)bytes[c]);
+        }
+    return copy_many(dsts, srcs, sizes, cudaMemcpyDeviceToHost, stream);
 }
 
 // Sub-batch of channels [c0, c1) of a validated full layout; offsets stay absolute into the shared slabs, the record
@@ -1427,6 +1458,31 @@ int32_t adx_validate(const vgb_adx_params &p, int c)
     return VGB_OK;
 }
 
+// Workspace of the time-parallel ADX encoder behind `base`: [trace: one word per whole standard-layout frame][used_start:
+// n x kAdxMaxSegments][stats].  Fills trace_off of every row and returns the view; `bytes_out` = bytes needed.
+AdxSegArgs adx_seg_carve(std::vector<AdxChannel> &tab, int first, int n, char *base, size_t &bytes_out)
+{
+    int64_t frames = 0;
+    int max_whole = 0;
+    for (int c = first; c < first + n; c++) {
+        const bool standard = tab[c].frame_size == 18 && tab[c].padding == 0;
+        const int whole = standard ? tab[c].n_samples / 32 : 0;
+        tab[c].trace_off = frames;
+        frames += whole;
+        max_whole = std::max(max_whole, whole);
+    }
+    const size_t o_used = align_up((size_t)(frames + 1) * 4, 256);
+    const size_t o_stats = o_used + align_up((size_t)std::max(n, 1) * kAdxMaxSegments * 4, 256);
+    bytes_out = o_stats + 256;
+    AdxSegArgs a{};
+    a.trace = reinterpret_cast<uint32_t *>(base);
+    a.used_start = reinterpret_cast<uint32_t *>(base + o_used);
+    a.stats = reinterpret_cast<unsigned long long *>(base + o_stats);
+    a.seg_count = adx_encode_pick_segments(n, max_whole);
+    a.min_seg_frames = kAdxMinSegFrames;
+    return a;
+}
+
 const int16_t kAdxFixed[4][2] = {{0, 0}, {0x0F00, 0}, {0x1CC0, (int16_t)0xF300}, {0x1880, (int16_t)0xF240}};
 
 }  // namespace
@@ -1486,6 +1542,23 @@ static int32_t adx_encode_one(const int16_t *const *pcm, const int32_t *n_sample
     VGB_TRY(g_ctx.adpcm.reserve((size_t)ab + 16));
     VGB_TRY(g_ctx.misc.reserve(tab.size() * sizeof(AdxChannel)));
     VGB_TRY(g_ctx.coefs.reserve((size_t)n_channels * 2));
+    // bookkeeping of the time-parallel encoder, one region per group (trace offsets are group relative)
+    std::vector<size_t> seg_at(n_groups), seg_bytes(n_groups);
+    std::vector<AdxSegArgs> seg(n_groups);
+    size_t seg_total = 0;
+    for (int g = 0; g < n_groups; g++) {
+        seg[g] = adx_seg_carve(tab, bound[g], bound[g + 1] - bound[g], nullptr, seg_bytes[g]);
+        seg_at[g] = seg_total;
+        seg_total += align_up(seg_bytes[g], 256);
+    }
+    VGB_TRY(g_ctx.ws.reserve(seg_total + 256));
+    for (int g = 0; g < n_groups; g++) {
+        char *base = static_cast<char *>(g_ctx.ws.p) + seg_at[g];
+        const AdxSegArgs rel = seg[g];
+        seg[g].trace = reinterpret_cast<uint32_t *>(base + (reinterpret_cast<char *>(rel.trace) - static_cast<char *>(nullptr)));
+        seg[g].used_start = reinterpret_cast<uint32_t *>(base + (reinterpret_cast<char *>(rel.used_start) - static_cast<char *>(nullptr)));
+        seg[g].stats = reinterpret_cast<unsigned long long *>(base + (reinterpret_cast<char *>(rel.stats) - static_cast<char *>(nullptr)));
+    }
     const AdxChannel *d_tab = static_cast<const AdxChannel *>(g_ctx.misc.p);
     int16_t *d_hist = static_cast<int16_t *>(g_ctx.coefs.p);
     auto sub = [&](const std::vector<int64_t> &v, int g) { return std::vector<int64_t>(v.begin() + bound[g], v.begin() + bound[g + 1]); };
@@ -1497,9 +1570,9 @@ static int32_t adx_encode_one(const int16_t *const *pcm, const int32_t *n_sample
         const int c0 = bound[g], n = bound[g + 1] - c0;
         if (n == 0) return VGB_OK;
         if (n_groups == 1) tick(4, true, st);
-        launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), d_tab + c0, n, static_cast<uint8_t *>(g_ctx.adpcm.p), d_hist + c0, st);
+        launch_adx_encode(static_cast<const int16_t *>(g_ctx.pcm.p), d_tab + c0, n, static_cast<uint8_t *>(g_ctx.adpcm.p), d_hist + c0, seg[g], st);
         if (n_groups == 1) tick(4, false, st);
-        g_ctx.launches += 1;
+        g_ctx.launches += seg[g].seg_count > 1 ? 3 : 1;
         CUDA_TRY(cudaGetLastError());
         return VGB_OK;
     };
@@ -1519,10 +1592,12 @@ static int32_t adx_encode_one(const int16_t *const *pcm, const int32_t *n_sample
 }
 
 /* ---- device-resident ADX encode (see the header) ---- */
-uint64_t vgb_adx_workspace_bytes(int32_t n_channels)
+uint64_t vgb_adx_workspace_bytes(int64_t total_samples, int32_t n_channels)
 {
-    if (n_channels < 0) return 0;
-    return align_up((size_t)std::max(n_channels, 1) * sizeof(AdxChannel), 256) + align_up((size_t)std::max(n_channels, 1) * 2, 256);
+    if (n_channels < 0 || total_samples < 0) return 0;
+    const size_t n = (size_t)std::max(n_channels, 1);
+    return align_up(n * sizeof(AdxChannel), 256) + align_up(n * 2, 256) + align_up((size_t)(total_samples / 32 + 1) * 4, 256) +
+           align_up(n * kAdxMaxSegments * 4, 256) + 512;
 }
 
 int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, const int32_t *n_samples, const vgb_adx_params *params,
@@ -1532,8 +1607,12 @@ int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, cons
     if (n_channels < 0) return fail(VGB_E_ARG, "n_channels is negative");
     if (n_channels == 0) return VGB_OK;
     if (!d_pcm || !pcm_offset || !n_samples || !params || !d_adpcm || !adpcm_offset || !d_workspace) return fail(VGB_E_ARG, "NULL argument");
-    if (vgb_adx_workspace_bytes(n_channels) > workspace_bytes)
-        return fail(VGB_E_ARG, "workspace too small: need %llu bytes", (unsigned long long)vgb_adx_workspace_bytes(n_channels));
+    {
+        int64_t total = 0;
+        for (int c = 0; c < n_channels; c++) total += n_samples[c] > 0 ? n_samples[c] : 0;
+        if (vgb_adx_workspace_bytes(total, n_channels) > workspace_bytes)
+            return fail(VGB_E_ARG, "workspace too small: need %llu bytes", (unsigned long long)vgb_adx_workspace_bytes(total, n_channels));
+    }
     std::vector<AdxChannel> tab(n_channels);
     for (int c = 0; c < n_channels; c++) {
         const vgb_adx_params &p = params[c];
@@ -1554,12 +1633,15 @@ int32_t vgb_adx_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, cons
     VGB_TRY(ensure_ready_locked());
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     char *ws = static_cast<char *>(d_workspace);
-    int16_t *d_hist = d_history_out ? d_history_out : reinterpret_cast<int16_t *>(ws + align_up(tab.size() * sizeof(AdxChannel), 256));
+    const size_t o_hist = align_up(tab.size() * sizeof(AdxChannel), 256), o_seg = o_hist + align_up(tab.size() * 2, 256);
+    int16_t *d_hist = d_history_out ? d_history_out : reinterpret_cast<int16_t *>(ws + o_hist);
+    size_t seg_bytes = 0;
+    const AdxSegArgs seg = adx_seg_carve(tab, 0, n_channels, ws + o_seg, seg_bytes);
     CUDA_TRY(cudaMemcpyAsync(ws, tab.data(), tab.size() * sizeof(AdxChannel), cudaMemcpyHostToDevice, st));  // pageable: staged before return
     tick(4, true, st);
-    launch_adx_encode(d_pcm, reinterpret_cast<const AdxChannel *>(ws), n_channels, d_adpcm, d_hist, st);
+    launch_adx_encode(d_pcm, reinterpret_cast<const AdxChannel *>(ws), n_channels, d_adpcm, d_hist, seg, st);
     tick(4, false, st);
-    g_ctx.launches += 1;
+    g_ctx.launches += seg.seg_count > 1 ? 3 : 1;
     CUDA_TRY(cudaGetLastError());
     return VGB_OK;
 }

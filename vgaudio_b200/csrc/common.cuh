@@ -84,6 +84,18 @@ struct AdxChannel {
     int32_t frame_size, version, padding, type, filter;
     int32_t history;     // decode only (CriAdxParameters.History)
     int16_t coef0, coef1;  // fixed-table pair or CalculateCoefficients (host, once per distinct sample rate)
+    int64_t trace_off;     // encode: first word of the channel in the trace slab of the time-parallel encoder (whole frames)
+};
+
+// Time-parallel ADX encoding (adx.cu): bookkeeping of one launch.  trace == nullptr: plain serial encode.
+constexpr int kAdxMinSegFrames = 256;
+constexpr int kAdxMaxSegments = 64;
+struct AdxSegArgs {
+    uint32_t *trace;             // [trace_off[ch] + frame] the reconstructed pair a whole frame hands on
+    uint32_t *used_start;        // [ch][seg_count] the pair a boundary's run-on started from
+    unsigned long long *stats;   // [0] frames re-encoded by run-ons, [1] by the cascade, [2] boundaries repaired by the cascade
+    int32_t seg_count;
+    int32_t min_seg_frames;
 };
 
 // ---- CRI HCA ------------------------------------------------------------------------------------------------

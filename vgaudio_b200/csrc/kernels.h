@@ -30,8 +30,9 @@ void launch_gc_taps(const uint8_t *adpcm, const GcChannelTable &tab, const int16
                     int16_t *tap_slab, int max_frames, cudaStream_t stream);
 
 // adx.cu — CriAdxCodec.Encode / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171)
+int adx_encode_pick_segments(int n_channels, int max_whole_frames);
 void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
-                       cudaStream_t stream);
+                       AdxSegArgs seg, cudaStream_t stream);  // seg.trace == nullptr: one segment (plain serial encode)
 void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, int32_t *status,
                        cudaStream_t stream);  // status: lowest channel with a fixed-filter number 4..7 (atomicMin), may be null
 
