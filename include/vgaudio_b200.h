@@ -337,6 +337,13 @@ int32_t vgb_hca_encode_dev(const int16_t *d_pcm, const int64_t *pcm_offset, cons
                            void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
 int32_t vgb_hca_encode_dev_status(const void *d_workspace, int32_t n_streams, void *cuda_stream);
 
+/* Mdct.RunMdct(double[] input, double[] output) / RunImdct (Utilities/Mdct.cs:63-92 / :94-119) of the codec's instance
+ * (128 points, CriHcaTables.MdctWindow, scale sqrt(2/128); CriHcaChannel.cs:19) for n_sequences independent sequences of
+ * n_blocks blocks; every sequence starts from a fresh Mdct object's zero state.  in / out: [sequence][block][128] doubles
+ * on the host.  Unit-parity taps: results are bit-identical to the reference's fp64 operation order (no FMA). */
+int32_t vgb_mdct128_batch(const double *in, int32_t n_sequences, int32_t n_blocks, double *out);
+int32_t vgb_imdct128_batch(const double *in, int32_t n_sequences, int32_t n_blocks, double *out);
+
 /* CRI HCA decode: replaces CriHcaDecoder.Decode (Codecs/CriHca/CriHcaDecoder.cs:11-25) for a batch of streams.
  * info[s] is what the caller's container reader parsed (HcaReader -> HcaInfo); the codec reads channel_count,
  * frame_size, the band layout, track_count / channel_config (channel types), sample_count, frame_count and

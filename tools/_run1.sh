@@ -1,6 +1,3 @@
-python -m pytest tests/test_criadx_gpu.py tests/test_multidevice_gpu.py tests/test_cri_golden.py -m gpu -q -x 2>&1 | tail -5
-python tools/secondary_bench.py > gpurun_out/r02_secondary_bench.json 2> gpurun_out/r02_secondary_bench.err; python -c "
-import json
-r=json.load(open('gpurun_out/r02_secondary_bench.json'))
-for e in r['entries']: print(e['path'], 'wall',e['wall_ms'],'kernel',e['kernel_ms'],'floor',e['pcie_floor_ms'],'ratio',e['wall_over_floor'],'roof',e['roofline']['frac'],'cpu',e['cpu_baseline']['value'],e['cpu_baseline']['cores'],e['parity'])"
-tail -3 gpurun_out/r02_secondary_bench.err
+python bench.py --config c5 --steps 3 --warmup 2 --no-cpu > gpurun_out/r02_bench_c5_n1c.json 2> gpurun_out/r02_bench_c5_n1c.err; python -c "
+import json; r=json.load(open('gpurun_out/r02_bench_c5_n1c.json')); print('c5 n1', r['value'], r['ms_per_step'], 'e2e', r['e2e']['ms_per_step'], r['collective'])"
+tail -2 gpurun_out/r02_bench_c5_n1c.err

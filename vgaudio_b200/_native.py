@@ -114,6 +114,8 @@ SIGNATURES = {
     "vgb_hca_encode_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_void_p]),
     "vgb_hca_encode_dev_status": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_mdct128_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vgb_imdct128_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "vgb_hca_query": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "vgb_hca_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_hca_decode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

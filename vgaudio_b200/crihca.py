@@ -113,3 +113,17 @@ def decode_batch(infos: Sequence[N.VgbHcaInfo], frames: Sequence[np.ndarray]) ->
 def decode(info: N.VgbHcaInfo, frames: np.ndarray) -> List[np.ndarray]:
     """One stream: list of int16[sample_count] channels."""
     return decode_batch([info], [frames])[0]
+
+
+def mdct_run(blocks: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """Mdct.RunMdct / RunImdct (Utilities/Mdct.cs:63-119) of the codec's 128-point instance over sequences of blocks:
+    blocks is float64[..., n_blocks, 128]; every leading index is an independent sequence starting from zero state."""
+    a = np.ascontiguousarray(blocks, dtype=np.float64)
+    if a.ndim < 2 or a.shape[-1] != 128:
+        raise ValueError("expected float64[..., n_blocks, 128]")
+    n_blocks = a.shape[-2]
+    n_seq = int(np.prod(a.shape[:-2])) if a.ndim > 2 else 1
+    out = np.empty_like(a)
+    fn = N.lib.vgb_imdct128_batch if inverse else N.lib.vgb_mdct128_batch
+    N.check(fn(a.ctypes.data, n_seq, n_blocks, out.ctypes.data))
+    return out

@@ -2234,6 +2234,32 @@ int32_t vgb_hca_encode_dev_status(const void *d_workspace, int32_t n_streams, vo
     return VGB_OK;
 }
 
+/* Mdct.RunMdct / RunImdct (Utilities/Mdct.cs:63-119) of the codec's 128-point instance for n_sequences independent
+ * sequences of n_blocks blocks (each sequence starts from a fresh Mdct object's all-zero state).  Host buffers
+ * [sequence][block][128] doubles.  Unit-parity taps; the codec kernels carry their own copy of the transform. */
+static int32_t mdct128_impl(const double *in, int32_t n_sequences, int32_t n_blocks, double *out, bool inverse)
+{
+    if (n_sequences < 0 || n_blocks < 0) return fail(VGB_E_ARG, "negative count");
+    if (n_sequences == 0 || n_blocks == 0) return VGB_OK;
+    if (!in || !out) return fail(VGB_E_ARG, "NULL argument");
+    const size_t bytes = (size_t)n_sequences * n_blocks * 128 * sizeof(double);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    VGB_TRY(ensure_ready_locked());
+    VGB_TRY(hca_tables_ready_locked());
+    VGB_TRY(g_ctx.misc.reserve(2 * align_up(bytes, 256)));
+    cudaStream_t st = g_ctx.stream;
+    char *d_in = static_cast<char *>(g_ctx.misc.p), *d_out = d_in + align_up(bytes, 256);
+    CUDA_TRY(cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(launch_hca_mdct128(reinterpret_cast<const double *>(d_in), reinterpret_cast<double *>(d_out), n_sequences, n_blocks, inverse,
+                                g_hca_tables.view, st));
+    g_ctx.launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VGB_OK;
+}
+int32_t vgb_mdct128_batch(const double *in, int32_t n_sequences, int32_t n_blocks, double *out) { return mdct128_impl(in, n_sequences, n_blocks, out, false); }
+int32_t vgb_imdct128_batch(const double *in, int32_t n_sequences, int32_t n_blocks, double *out) { return mdct128_impl(in, n_sequences, n_blocks, out, true); }
+
 static int32_t hca_decode_one(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
                               int16_t *const *pcm_out)
 {

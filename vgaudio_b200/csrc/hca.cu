@@ -941,6 +941,104 @@ hca_decode_seam_kernel(const double *__restrict__ edge, const HcaStream *__restr
         pcm[st.pcm_off + (int64_t)c * st.channel_stride + pos] = hca_pcm_float_to_short(tid < 64 ? a + p : a - p);
 }
 
+// ---- Mdct.RunMdct / RunImdct (Utilities/Mdct.cs:63-119) for the codec's 128-point instance, as a batch --------------------
+// The unit-parity taps SURVEY §8(b) asks for (vgb_mdct128_batch / vgb_imdct128_batch): sequences of 128-sample blocks,
+// each sequence starting from the all-zero state of a fresh Mdct object.  Block k of RunMdct reads input blocks k-1 and
+// k; block k of RunImdct needs the DCT-IV of spectra k-1 and k: both are independent per block, one CTA of 64 threads
+// each.  Same window (CriHcaTables.MdctWindow), scale sqrt(2/128) and operation order as the codec kernels above.
+__device__ __forceinline__ void hca_dct4_128(double *t, const double *in, const HcaTables &T, int i)
+{
+    {   // Dct4 pre-twiddle (Mdct.cs:137-147)
+        const int i2 = i * 2;
+        const double a = in[i2], b = in[kBins - 1 - i2];
+        const double sn = T.sin_tab[7][i], cs = T.cos_tab[7][i];
+        __syncthreads();  // `in` may alias `t`
+        t[i2] = a * cs + b * sn;
+        t[i2 + 1] = a * sn - b * cs;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int stage = 0; stage < 6; stage++) {  // (Mdct.cs:148-175)
+        const int block_bits = 6 - stage, half_bits = block_bits - 1;
+        const int block_size = 1 << block_bits, block_half = 1 << half_bits;
+        if (i < 32) {
+            const int block = i >> half_bits, j = i & (block_half - 1);
+            const int front = (block * block_size + j) * 2, back = front + block_size;
+            const double a = t[front] - t[back];
+            const double b = t[front + 1] - t[back + 1];
+            const double sn = T.sin_tab[half_bits][j], cs = T.cos_tab[half_bits][j];
+            const double f0 = t[front] + t[back], f1 = t[front + 1] + t[back + 1];
+            t[front] = f0;
+            t[front + 1] = f1;
+            t[back] = a * cs + b * sn;
+            t[back + 1] = a * sn - b * cs;
+        }
+        __syncthreads();
+    }
+}
+
+// grid: x = block, y = sequence; in/out [seq][blocks][128]
+__global__ void __launch_bounds__(64)
+hca_mdct128_kernel(const double *__restrict__ in, double *__restrict__ out, int n_blocks, HcaTables T)
+{
+    __shared__ double fold[kBins], t[kBins];
+    const int k = blockIdx.x, i = threadIdx.x;
+    const double *cur = in + ((size_t)blockIdx.y * n_blocks + k) * kBins;
+    const double *prev = cur - kBins;  // Mdct._mdctPrevious: zeros for the first block (:71)
+    auto pv = [&](int j) -> double { return k > 0 ? prev[j] : 0.0; };
+    {   // window + fold (Mdct.cs:77-85)
+        const double a = T.window[64 - i - 1] * -cur[64 + i];
+        const double b = T.window[64 + i] * cur[64 - i - 1];
+        const double cc = T.window[i] * pv(i);
+        const double d = T.window[kBins - i - 1] * pv(kBins - i - 1);
+        fold[i] = a - b;
+        fold[64 + i] = cc - d;
+    }
+    __syncthreads();
+    hca_dct4_128(t, fold, T, i);
+    double *o = out + ((size_t)blockIdx.y * n_blocks + k) * kBins;
+    o[i] = t[T.shuffle[i]] * T.mdct_scale;            // (Mdct.cs:177-180)
+    o[64 + i] = t[T.shuffle[64 + i]] * T.mdct_scale;
+}
+
+__global__ void __launch_bounds__(64)
+hca_imdct128_kernel(const double *__restrict__ in, double *__restrict__ out, int n_blocks, HcaTables T)
+{
+    __shared__ double cur_d[kBins], prev_d[kBins], t[kBins];
+    const int k = blockIdx.x, i = threadIdx.x;
+    const double *cur = in + ((size_t)blockIdx.y * n_blocks + k) * kBins;
+    hca_dct4_128(t, cur, T, i);                       // Dct4 of this block (Mdct.cs:107)
+    cur_d[i] = t[T.shuffle[i]] * T.mdct_scale;
+    cur_d[64 + i] = t[T.shuffle[64 + i]] * T.mdct_scale;
+    __syncthreads();
+    if (k > 0) {                                      // ... and of the previous one: it left the overlap buffer (:114-117)
+        hca_dct4_128(t, cur - kBins, T, i);
+        prev_d[i] = t[T.shuffle[i]] * T.mdct_scale;
+        prev_d[64 + i] = t[T.shuffle[64 + i]] * T.mdct_scale;
+    } else {
+        prev_d[i] = 0.0;
+        prev_d[64 + i] = 0.0;
+    }
+    __syncthreads();
+    double *o = out + ((size_t)blockIdx.y * n_blocks + k) * kBins;
+    // output[i] = window[i] * dct[i + 64] + previous[i];  output[i + 64] = window[i + 64] * -dct[127 - i] - previous[i + 64]
+    // previous[i] = window[127 - i] * -prevDct[63 - i];   previous[i + 64] = window[63 - i] * prevDct[i]      (:108-117)
+    const double p0 = k > 0 ? T.window[kBins - 1 - i] * -prev_d[64 - i - 1] : 0.0;
+    const double p1 = k > 0 ? T.window[64 - i - 1] * prev_d[i] : 0.0;
+    o[i] = T.window[i] * cur_d[i + 64] + p0;
+    o[i + 64] = T.window[i + 64] * -cur_d[kBins - 1 - i] - p1;
+}
+
+cudaError_t launch_hca_mdct128(const double *in, double *out, int n_sequences, int n_blocks, bool inverse, const HcaTables &tables,
+                               cudaStream_t stream)
+{
+    if (n_sequences <= 0 || n_blocks <= 0) return cudaSuccess;
+    const dim3 grid((unsigned)n_blocks, (unsigned)n_sequences);
+    if (inverse) hca_imdct128_kernel<<<grid, 64, 0, stream>>>(in, out, n_blocks, tables);
+    else hca_mdct128_kernel<<<grid, 64, 0, stream>>>(in, out, n_blocks, tables);
+    return cudaGetLastError();
+}
+
 size_t hca_decode_smem_bytes(const HcaConfig &cfg)
 {
     const size_t nch = (size_t)cfg.channel_count;

@@ -50,6 +50,10 @@ cudaError_t launch_hca_decode(const uint8_t *frames, const HcaStream *streams, i
                               double *edge_scratch, int16_t *pcm, int32_t *status_out,
                               cudaStream_t stream);  // edge_scratch: 2*128 doubles per channel-frame
 
+// Mdct.RunMdct / RunImdct (Utilities/Mdct.cs:63-119), the codec's 128-point instance, n_sequences x n_blocks blocks of 128 doubles
+cudaError_t launch_hca_mdct128(const double *in, double *out, int n_sequences, int n_blocks, bool inverse, const HcaTables &tables,
+                               cudaStream_t stream);
+
 // interleave.cu — InterleaveExtensions.Interleave / DeInterleave (Utilities/Interleave.cs:9-166) for n_items payloads
 cudaError_t launch_interleave(const void *in, int64_t in_channel_stride, int64_t in_item_stride, void *out, int64_t out_item_stride,
                               int n_items, int count, int64_t in_size, int64_t interleave, int64_t out_size, cudaStream_t stream);
