@@ -240,6 +240,7 @@ def test_mdct_taps_match_the_oracle_bit_for_bit(vg, oracle):
         assert np.array_equal(spec[s].view(np.uint64), want.view(np.uint64)), s
         want_back = oracle.hca_imdct(want)
         assert np.array_equal(back[s].view(np.uint64), want_back.view(np.uint64)), s
-        # time-domain aliasing cancels: block k of the IMDCT output is input block k-1 (the transform's one-block delay)
-        assert np.abs(back[s][1:] - x[s][:-1]).max() < 1e-12
+        # time-domain aliasing cancels: block k of the IMDCT output is input block k-1 (the transform's one-block delay),
+        # up to the binary32 precision of the window data (CriHcaTables.MdctWindow is stored as float32)
+        assert np.abs(back[s][1:] - x[s][:-1]).max() < 2e-6 * max(1.0, np.abs(x[s]).max())
     assert vg.crihca.mdct_run(np.zeros((0, 128))).shape == (0, 128)

@@ -77,3 +77,23 @@ def test_gpu_wav_sample_interleave_round_trip(vg, count, n, extra):
     back = vg.interleave.interleaved_byte_to_short(padded, count)
     for c in range(count):
         assert np.array_equal(back[c], chans[c])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("count,size,ilv", [(2, 0x2000 * 5 + 3664, 0x2000), (4, 18 * 8 * 100, 18 * 8), (1, 4096, 1024), (3, 48000, 16000), (2, 65536 + 16, 65536)])
+def test_tma_variant_matches_oracle(vg, oracle, count, size, ilv):
+    """VGB_INTERLEAVE_TMA=1: the same shuffle as bulk copies (cp.async.bulk + mbarrier ring); eligible shapes (everything a
+    multiple of 16 bytes, input size == output size) must give the oracle's bytes in both directions."""
+    import os
+
+    rng = np.random.default_rng(count * 1000 + ilv)
+    chans = [rng.integers(0, 256, size, dtype=np.uint8) for _ in range(count)]
+    os.environ["VGB_INTERLEAVE_TMA"] = "1"
+    try:
+        got = vg.interleave.interleave(chans, ilv)
+        assert got.tobytes() == oracle.interleave(chans, ilv).tobytes()
+        back = vg.interleave.deinterleave(got, ilv, count)
+    finally:
+        os.environ.pop("VGB_INTERLEAVE_TMA", None)
+    for c in range(count):
+        assert np.array_equal(back[c], chans[c]), c
