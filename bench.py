@@ -51,6 +51,7 @@ def parse_args():
                     help="BASELINE.json configuration: c2 GC-ADPCM encode (default, the headline), c3 GC-ADPCM decode of 8192 channels, "
                          "c4 HCA encode of 512 streams, c5 65 536-file mixed batch with NCCL scatter/gather (strong scaling)")
     ap.add_argument("--files", type=int, default=65536, help="c5: number of files in the whole job")
+    ap.add_argument("--c5-chunks", type=int, default=8, help="c5: chunks per rank of the scatter / encode / gather pipeline (1: no overlap)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

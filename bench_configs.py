@@ -363,73 +363,102 @@ def _c5_fill(torch, slab, offs, lens, file_ids, device):
         del idx, f, inside, t, x
 
 
+class _Chunk:
+    """One (rank, chunk) work unit of c5: its files (GC-ADPCM first, then ADX, longest first), where its PCM lies in the
+    root's slab and in the owner's receive buffer, and the layout of its output block
+    [GC payloads (16-aligned) | coefficient table | ADX payloads]."""
+
+    def __init__(self, vg, lens, is_gc, slab_sample_off):
+        self.n = len(lens)
+        self.lens = lens.astype(np.int64)
+        self.n_gc = int(is_gc.sum())
+        self.n_adx = self.n - self.n_gc
+        pad = (self.lens + 7) // 8 * 8
+        self.file_off = np.concatenate(([0], np.cumsum(pad)[:-1])).astype(np.int64) if self.n else np.zeros(0, np.int64)  # samples, chunk relative
+        self.samples_padded = int(pad.sum())
+        self.slab_off = int(slab_sample_off)                                                                               # samples in the root slab
+        self.gc_lens = self.lens[:self.n_gc].astype(np.int32)
+        self.adx_lens = self.lens[self.n_gc:].astype(np.int32)
+        self.gc_bytes = np.array([vg.gcadpcm.sample_count_to_byte_count(int(v)) for v in self.gc_lens], dtype=np.int64)
+        self.adx_bytes = np.array([vg.lib.vgb_adx_encoded_byte_count(int(v), 0, 18) for v in self.adx_lens], dtype=np.int64)
+        g16, a16 = (self.gc_bytes + 15) // 16 * 16, (self.adx_bytes + 15) // 16 * 16
+        self.gc_out = np.concatenate(([0], np.cumsum(g16)[:-1])).astype(np.int64) if self.n_gc else np.zeros(0, np.int64)
+        self.coef_at = int(g16.sum())
+        self.adx_at = (self.coef_at + self.n_gc * 32 + 15) // 16 * 16
+        self.adx_out = (self.adx_at + np.concatenate(([0], np.cumsum(a16)[:-1]))).astype(np.int64) if self.n_adx else np.zeros(0, np.int64)
+        self.out_bytes = (self.adx_at + int(a16.sum()) + 255) // 256 * 256
+        self.gc_frames = int(((self.gc_lens.astype(np.int64) + 13) // 14).sum())
+
+
 def run_c5(args, env, ctx):
     torch, dist, vg, N, bench = ctx["torch"], ctx["dist"], ctx["vg"], ctx["N"], ctx["bench"]
     rank, local_rank, world = env
     device = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
+    compute = torch.cuda.current_stream()
+    comm = torch.cuda.Stream(device=device)
     n_files = args.files
+    K = max(1, args.c5_chunks) if world > 1 else 1   # a single rank has nothing to overlap
     lens = _c5_lengths(n_files)
     is_gc = (np.arange(n_files) % 2) == 0                       # even index -> GC-ADPCM, odd -> ADX (Linear, v4, 18-byte frames)
-    # ---- partition (identical on every rank): greedy longest-first on an estimated cost, ADX samples weigh more
-    adx_w = float(os.environ.get("VGB_C5_ADX_WEIGHT", "1.0"))
-    weight = np.where(is_gc, lens, (lens * adx_w).astype(np.int64)).astype(np.int64)
+    # ---- plan (identical on every rank): files -> ranks by greedy longest-first, a rank's files dealt round-robin (longest
+    # first) into K chunks, inside a chunk GC-ADPCM first and longest first (neighbouring channels of a warp are alike)
     part = np.zeros(n_files, dtype=np.int32)
     load = np.zeros(world, dtype=np.int64)
-    N.check(vg.lib.vgb_partition_lpt(weight.ctypes.data, n_files, world, part.ctypes.data, load.ctypes.data))
-    # rank-major, codec-major, longest first inside (neighbouring channels of a warp then have similar lengths)
-    order = np.lexsort((-lens, ~is_gc, part))
-    lens_o, gc_o, part_o = lens[order], is_gc[order], part[order]
-    pad = (lens_o + 7) // 8 * 8
-    offs_o = np.concatenate(([0], np.cumsum(pad)[:-1])).astype(np.int64)          # sample offsets in the root's slab
-    total_samples = int(pad.sum())
-    rank_lo = np.searchsorted(part_o, np.arange(world), side="left")
-    rank_hi = np.searchsorted(part_o, np.arange(world), side="right")
-    pcm_counts = np.array([int(pad[rank_lo[r]:rank_hi[r]].sum()) * 2 for r in range(world)], dtype=np.int64)   # bytes
-    pcm_offsets = np.array([int(offs_o[rank_lo[r]]) * 2 if rank_hi[r] > rank_lo[r] else 0 for r in range(world)], dtype=np.int64)
+    N.check(vg.lib.vgb_partition_lpt(lens.ctypes.data, n_files, world, part.ctypes.data, load.ctypes.data))
+    chunks = [[None] * K for _ in range(world)]
+    slab_cursor = 0
+    file_order = []                                              # slab order of the original file indices
+    for r in range(world):
+        mine = np.flatnonzero(part == r)
+        mine = mine[np.argsort(-lens[mine], kind="stable")]
+        for k in range(K):
+            sel = mine[k::K]
+            sel = sel[np.lexsort((-lens[sel], ~is_gc[sel]))]
+            ch = _Chunk(vg, lens[sel], is_gc[sel], slab_cursor)
+            ch.files = sel
+            chunks[r][k] = ch
+            slab_cursor += ch.samples_padded
+            file_order.append(sel)
+    total_padded = slab_cursor
+    file_order = np.concatenate(file_order)
+    slab_file_off = np.concatenate([chunks[r][k].slab_off + chunks[r][k].file_off for r in range(world) for k in range(K)])
+    my = chunks[rank]
+    my_pcm_off = np.concatenate(([0], np.cumsum([c.samples_padded for c in my])[:-1])).astype(np.int64)       # samples in my receive buffer
+    my_out_off = np.concatenate(([0], np.cumsum([c.out_bytes for c in my])[:-1])).astype(np.int64)
+    gathered_off = {}                                            # root: where (rank, chunk) lands in the gathered buffer
+    cur = 0
+    for r in range(world):
+        for k in range(K):
+            gathered_off[(r, k)] = cur
+            cur += chunks[r][k].out_bytes
+    gathered_bytes = cur
 
-    # ---- my share
-    lo, hi = int(rank_lo[rank]), int(rank_hi[rank])
-    my_lens, my_gc = lens_o[lo:hi], gc_o[lo:hi]
-    my_off = offs_o[lo:hi] - (offs_o[lo] if hi > lo else 0)
-    n_gc, n_adx = int(my_gc.sum()), int((~my_gc).sum())
-    gc_lens = my_lens[:n_gc].astype(np.int32)
-    adx_lens = my_lens[n_gc:].astype(np.int32)
-    gc_off, adx_off = my_off[:n_gc].copy(), my_off[n_gc:].copy()
-    gc_bytes = np.array([vg.gcadpcm.sample_count_to_byte_count(int(v)) for v in gc_lens], dtype=np.int64)
-    adx_bytes = np.array([vg.lib.vgb_adx_encoded_byte_count(int(v), 0, 18) for v in adx_lens], dtype=np.int64)
-    # my output buffer: [GC payloads (16-aligned each) | coefficient table | ADX payloads]
-    gc_out_off = np.concatenate(([0], np.cumsum((gc_bytes + 15) // 16 * 16)[:-1])).astype(np.int64) if n_gc else np.zeros(0, np.int64)
-    gc_out_total = int(((gc_bytes + 15) // 16 * 16).sum())
-    coef_at = gc_out_total
-    adx_at = (coef_at + n_gc * 32 + 15) // 16 * 16
-    adx_out_off = (adx_at + np.concatenate(([0], np.cumsum((adx_bytes + 15) // 16 * 16)[:-1]))).astype(np.int64) if n_adx else np.zeros(0, np.int64)
-    my_out_bytes = adx_at + int(((adx_bytes + 15) // 16 * 16).sum())
-    out_counts = np.zeros(world, dtype=np.int64)
-    out_counts[rank] = my_out_bytes
-    if world > 1:
-        t = torch.as_tensor(out_counts, device=device)
-        dist.all_reduce(t)
-        out_counts = t.cpu().numpy()
-    out_offsets = np.concatenate(([0], np.cumsum((out_counts + 255) // 256 * 256)[:-1])).astype(np.int64)
-
-    # ---- buffers.  Root: the whole PCM slab (its own share is used in place) and the gathered outputs.
+    # ---- buffers.  Root: the whole PCM slab (its own chunks are encoded in place, their outputs written straight into the
+    # gathered buffer); others: a receive buffer for their PCM and an output buffer.
     if rank == 0:
-        slab = torch.zeros(total_samples + 8, dtype=torch.int16, device=device)
-        _c5_fill(torch, slab, offs_o, lens_o, order, device)
-        gathered = torch.zeros(int(out_offsets[-1] + (out_counts[-1] + 255) // 256 * 256) + 256, dtype=torch.uint8, device=device)
-        my_pcm = slab[int(pcm_offsets[0] // 2):int(pcm_offsets[0] // 2) + int(pcm_counts[0] // 2) + 8]
+        slab = torch.zeros(total_padded + 8, dtype=torch.int16, device=device)
+        _c5_fill(torch, slab, slab_file_off, lens[file_order], file_order, device)
+        gathered = torch.zeros(gathered_bytes + 256, dtype=torch.uint8, device=device)
+        pcm_base = [slab.data_ptr() + 2 * c.slab_off for c in my]
+        out_base = [gathered.data_ptr() + gathered_off[(0, k)] for k in range(K)]
+        my_pcm = my_out = None
     else:
         slab = gathered = None
-        my_pcm = torch.zeros(int(pcm_counts[rank] // 2) + 8, dtype=torch.int16, device=device)
-    my_out = torch.zeros(my_out_bytes + 256, dtype=torch.uint8, device=device)
-    gc_frames = int(((gc_lens.astype(np.int64) + 13) // 14).sum())
-    gws_bytes = int(vg.lib.vgb_gcadpcm_workspace_bytes(gc_frames, max(n_gc, 1)))
-    gws = torch.empty(gws_bytes, dtype=torch.uint8, device=device)
-    aws_bytes = int(vg.lib.vgb_adx_workspace_bytes(int(adx_lens.astype(np.int64).sum()), max(n_adx, 1)))
-    aws = torch.empty(aws_bytes, dtype=torch.uint8, device=device)
-    adx_params = (N.VgbAdxParams * max(n_adx, 1))()
-    for i in range(n_adx):
+        my_pcm = torch.zeros(int(sum(c.samples_padded for c in my)) + 8, dtype=torch.int16, device=device)
+        my_out = torch.zeros(int(sum(c.out_bytes for c in my)) + 256, dtype=torch.uint8, device=device)
+        pcm_base = [my_pcm.data_ptr() + 2 * int(o) for o in my_pcm_off]
+        out_base = [my_out.data_ptr() + int(o) for o in my_out_off]
+    # the two codecs of a chunk, and consecutive chunks, run on separate streams: every encode ends in a thin tail (the
+    # boundary run-ons, the cascade) that another stream's kernels fill; two chunks in flight -> two workspaces each
+    LANES = 2
+    gc_streams = [torch.cuda.Stream(device=device) for _ in range(LANES)]
+    adx_streams = [torch.cuda.Stream(device=device) for _ in range(LANES)]
+    gws_bytes = int(vg.lib.vgb_gcadpcm_workspace_bytes(max(c.gc_frames for c in my), max(max(c.n_gc for c in my), 1)))
+    gws = [torch.empty(gws_bytes, dtype=torch.uint8, device=device) for _ in range(LANES)]
+    aws_bytes = int(vg.lib.vgb_adx_workspace_bytes(max(int(c.adx_lens.astype(np.int64).sum()) for c in my), max(max(c.n_adx for c in my), 1)))
+    aws = [torch.empty(aws_bytes, dtype=torch.uint8, device=device) for _ in range(LANES)]
+    adx_params = (N.VgbAdxParams * max(max(c.n_adx for c in my), 1))()
+    for i in range(len(adx_params)):
         adx_params[i] = N.VgbAdxParams(SAMPLE_RATE, 500, 18, 4, 0, 0, 3, 0)
 
     # ---- communicator inside the library (the id travels over torch.distributed)
@@ -444,32 +473,84 @@ def run_c5(args, env, ctx):
         raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
         N.check(vg.lib.vgb_nccl_init(raw, world, rank))
 
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    def exchange(scatter_k, gather_k):
+        """One NCCL group on the comm stream: the root sends every peer its PCM chunk `scatter_k` and receives the output
+        blocks of chunk `gather_k`; a peer does the opposite.  Full duplex: both directions move at once."""
+        sp, sb, speer, rp, rb, rpeer = [], [], [], [], [], []
+        if rank == 0:
+            for r in range(1, world):
+                if scatter_k is not None:
+                    c = chunks[r][scatter_k]
+                    sp.append(slab.data_ptr() + 2 * c.slab_off); sb.append(2 * c.samples_padded); speer.append(r)
+                if gather_k is not None:
+                    rp.append(gathered.data_ptr() + gathered_off[(r, gather_k)]); rb.append(chunks[r][gather_k].out_bytes); rpeer.append(r)
+        else:
+            if scatter_k is not None:
+                rp.append(pcm_base[scatter_k]); rb.append(2 * my[scatter_k].samples_padded); rpeer.append(0)
+            if gather_k is not None:
+                sp.append(out_base[gather_k]); sb.append(my[gather_k].out_bytes); speer.append(0)
+        if not sp and not rp:
+            return
+        arr = lambda v, t: (t * max(len(v), 1))(*v)
+        N.check(vg.lib.vgb_sendrecv_dev(arr(sp, C.c_void_p), arr(sb, C.c_int64), arr(speer, C.c_int32), len(sp),
+                                        arr(rp, C.c_void_p), arr(rb, C.c_int64), arr(rpeer, C.c_int32), len(rp), comm.cuda_stream))
 
-    def step(record=False):
-        if record:
-            evs[0].record(stream)
-        if world > 1:
-            N.check(vg.lib.vgb_scatterv_dev(slab.data_ptr() if rank == 0 else None, pcm_offsets.ctypes.data, pcm_counts.ctypes.data,
-                                            my_pcm.data_ptr(), 0, stream.cuda_stream))
-        if record:
-            evs[1].record(stream)
-        if n_gc:
-            N.check(vg.lib.vgb_gcadpcm_encode_dev(my_pcm.data_ptr(), gc_off.ctypes.data, gc_lens.ctypes.data, None, n_gc, None,
-                                                  my_out.data_ptr() + coef_at, my_out.data_ptr(), gc_out_off.ctypes.data, gws.data_ptr(),
-                                                  gws_bytes, stream.cuda_stream))
-        if n_adx:
-            N.check(vg.lib.vgb_adx_encode_dev(my_pcm.data_ptr(), adx_off.ctypes.data, adx_lens.ctypes.data, adx_params, n_adx, None,
-                                              my_out.data_ptr(), adx_out_off.ctypes.data, aws.data_ptr(), aws_bytes, stream.cuda_stream))
-        if record:
-            evs[2].record(stream)
-        if world > 1:
-            N.check(vg.lib.vgb_gatherv_dev(my_out.data_ptr(), gathered.data_ptr() if rank == 0 else None, out_offsets.ctypes.data,
-                                           out_counts.ctypes.data, 0, stream.cuda_stream))
-        if record:
-            evs[3].record(stream)
+    def encode(k, ready, done):
+        """Chunk k on its lane's two streams, after event `ready`; `done` (a list) receives one event per stream."""
+        c = my[k]
+        lane = k % LANES
+        for st in (gc_streams[lane], adx_streams[lane]):
+            st.wait_event(ready)
+        if c.n_gc:
+            off = c.file_off[:c.n_gc].copy()
+            N.check(vg.lib.vgb_gcadpcm_encode_dev(pcm_base[k], off.ctypes.data, c.gc_lens.ctypes.data, None, c.n_gc, None,
+                                                  out_base[k] + c.coef_at, out_base[k], c.gc_out.ctypes.data, gws[lane].data_ptr(), gws_bytes,
+                                                  gc_streams[lane].cuda_stream))
+        if c.n_adx:
+            off = c.file_off[c.n_gc:].copy()
+            N.check(vg.lib.vgb_adx_encode_dev(pcm_base[k], off.ctypes.data, c.adx_lens.ctypes.data, adx_params, c.n_adx, None,
+                                              out_base[k], c.adx_out.ctypes.data, aws[lane].data_ptr(), aws_bytes, adx_streams[lane].cuda_stream))
+        for st in (gc_streams[lane], adx_streams[lane]):
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
 
-    N.check(vg.lib.vgb_set_kernel_timing(1))
+    def step(phases=None):
+        """Pipeline over the K chunks: comm step t = {scatter chunk t, gather chunk t-2}; encode chunk t follows comm step t."""
+        enc_done = [[] for _ in range(K)]
+        start = torch.cuda.Event()
+        start.record(compute)
+        comm.wait_event(start)
+        arrived = start
+        for t in range(K + 2):
+            sk = t if t < K else None
+            gk = t - 2 if t - 2 >= 0 else None
+            if world > 1 and (sk is not None or gk is not None):
+                if gk is not None:
+                    for ev in enc_done[gk]:
+                        comm.wait_event(ev)
+                if phases is not None:
+                    phases.append(("comm", t, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                    phases[-1][2].record(comm)
+                exchange(sk, gk)
+                if phases is not None:
+                    phases[-1][3].record(comm)
+                arrived = torch.cuda.Event()
+                arrived.record(comm)
+            if sk is not None:
+                if phases is not None:
+                    phases.append(("enc", t, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                    gc_streams[sk % LANES].wait_event(arrived)
+                    phases[-1][2].record(gc_streams[sk % LANES])
+                encode(sk, arrived, enc_done[sk])
+                if phases is not None:
+                    phases[-1][3].record(gc_streams[sk % LANES])
+        compute.wait_stream(comm)
+        for evs in enc_done:
+            for ev in evs:
+                compute.wait_event(ev)
+
+    N.check(vg.lib.vgb_set_kernel_timing(0))
     for _ in range(args.warmup):
         step()
     _barrier(torch, dist, world)
@@ -477,107 +558,118 @@ def run_c5(args, env, ctx):
     sampler.start()
     launches0 = vg.lib.vgb_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase = np.zeros(3)
-    ev0.record(stream)
+    ev0.record(compute)
     for _ in range(args.steps):
-        step(record=True)
-        torch.cuda.synchronize()
-        phase += np.array([evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
-    ev1.record(stream)
+        step()
+    ev1.record(compute)
     torch.cuda.synchronize()
-    my_ms = ev0.elapsed_time(ev1) / args.steps
-    ms = _max_over_ranks(torch, dist, world, device, my_ms)
+    ms = _max_over_ranks(torch, dist, world, device, ev0.elapsed_time(ev1) / args.steps)
     launches = vg.lib.vgb_kernel_launch_count() - launches0
     clocks = sampler.stop()
-    phase /= args.steps
+    # one more, instrumented step (untimed) for the phase breakdown
+    phases = []
+    _barrier(torch, dist, world)
+    step(phases)
+    torch.cuda.synchronize()
+    comm_ms = sum(p[2].elapsed_time(p[3]) for p in phases if p[0] == "comm")
+    enc_ms = sum(p[2].elapsed_time(p[3]) for p in phases if p[0] == "enc")
     enc_all = np.zeros(world)
-    enc_all[rank] = phase[1]
-    sc_ms = _max_over_ranks(torch, dist, world, device, phase[0])
-    ga_ms = _max_over_ranks(torch, dist, world, device, phase[2])
+    enc_all[rank] = enc_ms
+    comm_all = _max_over_ranks(torch, dist, world, device, comm_ms)
     if world > 1:
         t = torch.as_tensor(enc_all, device=device)
         dist.all_reduce(t)
         enc_all = t.cpu().numpy()
     total = int(lens.sum())
     value = total / (ms / 1e3) / 1e6
+    scatter_bytes = int(sum(2 * chunks[r][k].samples_padded for r in range(1, world) for k in range(K)))
+    gather_bytes = int(sum(chunks[r][k].out_bytes for r in range(1, world) for k in range(K)))
 
     # ---- e2e: every rank's files from ITS OWN pinned host memory through the host API (one H2D link per GPU)
     e2e = None
     if not args.no_e2e:
         torch.cuda.synchronize()
-        h_pcm = torch.empty(my_pcm.numel(), dtype=torch.int16, pin_memory=True)
-        h_pcm.copy_(my_pcm)
-        h_out = torch.empty(my_out_bytes + 256, dtype=torch.uint8, pin_memory=True)
-        gc_in = (C.c_void_p * max(n_gc, 1))(*[h_pcm.data_ptr() + 2 * int(o) for o in gc_off])
-        gc_tab = (C.c_void_p * max(n_gc, 1))(*[h_out.data_ptr() + int(o) for o in gc_out_off])
-        ad_in = (C.c_void_p * max(n_adx, 1))(*[h_pcm.data_ptr() + 2 * int(o) for o in adx_off])
-        ad_o = (C.c_void_p * max(n_adx, 1))(*[h_out.data_ptr() + int(o) for o in adx_out_off])
+        n_samp = int(sum(c.samples_padded for c in my))
+        h_pcm = torch.empty(n_samp + 8, dtype=torch.int16, pin_memory=True)
+        if rank == 0:
+            for k, c in enumerate(my):
+                h_pcm[int(my_pcm_off[k]):int(my_pcm_off[k]) + c.samples_padded].copy_(slab[c.slab_off:c.slab_off + c.samples_padded])
+        else:
+            h_pcm[:n_samp].copy_(my_pcm[:n_samp])
+        h_out = torch.empty(int(sum(c.out_bytes for c in my)) + 256, dtype=torch.uint8, pin_memory=True)
+        gc_in, gc_tab, ad_in, ad_tab, gl, al = [], [], [], [], [], []
+        for k, c in enumerate(my):
+            gc_in += [h_pcm.data_ptr() + 2 * int(my_pcm_off[k] + o) for o in c.file_off[:c.n_gc]]
+            gc_tab += [h_out.data_ptr() + int(my_out_off[k] + o) for o in c.gc_out]
+            ad_in += [h_pcm.data_ptr() + 2 * int(my_pcm_off[k] + o) for o in c.file_off[c.n_gc:]]
+            ad_tab += [h_out.data_ptr() + int(my_out_off[k] + o) for o in c.adx_out]
+            gl += list(c.gc_lens); al += list(c.adx_lens)
+        n_gc, n_adx = len(gl), len(al)
+        gl, al = np.array(gl, dtype=np.int32), np.array(al, dtype=np.int32)
+        gc_in, gc_tab = (C.c_void_p * max(n_gc, 1))(*gc_in), (C.c_void_p * max(n_gc, 1))(*gc_tab)
+        ad_in, ad_tab = (C.c_void_p * max(n_adx, 1))(*ad_in), (C.c_void_p * max(n_adx, 1))(*ad_tab)
         h_coefs = np.zeros((max(n_gc, 1), 16), dtype=np.int16)
+        ap = (N.VgbAdxParams * max(n_adx, 1))(*[N.VgbAdxParams(SAMPLE_RATE, 500, 18, 4, 0, 0, 3, 0) for _ in range(max(n_adx, 1))])
 
         def step_e2e():
             if n_gc:
-                N.check(vg.lib.vgb_gcadpcm_encode_batch(gc_in, gc_lens.ctypes.data, None, None, n_gc, h_coefs.ctypes.data, gc_tab, None, None))
+                N.check(vg.lib.vgb_gcadpcm_encode_batch(gc_in, gl.ctypes.data, None, None, n_gc, h_coefs.ctypes.data, gc_tab, None, None))
             if n_adx:
-                N.check(vg.lib.vgb_adx_encode_batch(ad_in, adx_lens.ctypes.data, adx_params, n_adx, None, ad_o, None, None))
+                N.check(vg.lib.vgb_adx_encode_batch(ad_in, al.ctypes.data, ap, n_adx, None, ad_tab, None, None))
 
         step_e2e()
         _barrier(torch, dist, world)
         t0 = time.perf_counter()
         step_e2e()
         e_ms = _max_over_ranks(torch, dist, world, device, (time.perf_counter() - t0) * 1e3)
-        same = bool((h_out[:gc_out_total].to(device) == my_out[:gc_out_total]).all().item()) if n_gc else True
-        if n_adx:
-            same = same and bool((h_out[adx_at:my_out_bytes].to(device) == my_out[adx_at:my_out_bytes]).all().item())
+        dev_out = gathered if rank == 0 else my_out
+        same = True
+        for k, c in enumerate(my):
+            base = gathered_off[(0, k)] if rank == 0 else int(my_out_off[k])
+            if c.n_gc:
+                same = same and bool((h_out[int(my_out_off[k]):int(my_out_off[k]) + c.coef_at].to(device) == dev_out[base:base + c.coef_at]).all().item())
+            if c.n_adx:
+                lo, hi = c.adx_at, int(c.adx_out[-1] + c.adx_bytes[-1])
+                same = same and bool((h_out[int(my_out_off[k]) + lo:int(my_out_off[k]) + hi].to(device) == dev_out[base + lo:base + hi]).all().item())
         e2e = {"value": round(total / (e_ms / 1e3) / 1e6, 3), "unit": "Msamples/s", "ms_per_step": round(e_ms, 3),
-               "h2d_bytes_per_step": int(total * 2), "d2h_bytes_per_step": int(out_counts.sum()),
+               "h2d_bytes_per_step": int(total * 2), "d2h_bytes_per_step": int(gathered_bytes),
+               "pcie_floor_ms": round(total * 2 / world / 55e9 * 1e3, 1),
                "api": "vgb_gcadpcm_encode_batch + vgb_adx_encode_batch per rank on its own files from pinned host memory (one PCIe link per GPU)",
                "matches_device_resident": same}
 
-    # ---- parity on the root: 128 GC + 128 ADX files drawn across the gathered buffer, against the oracle
+    # ---- parity on the root: >= 128 GC + 128 ADX files drawn across every rank's blocks of the gathered buffer
     parity = cpu = None
     if rank == 0 and not args.no_cpu:
         from oracle import pyoracle
 
-        src_buf = gathered if world > 1 else my_out
-        base0 = 0 if world == 1 else None
         rng = np.random.default_rng(7)
         checked_gc = checked_adx = 0
         ok = True
         cpu_samples, cpu_t = 0, 0.0
+        want_each = max(1, -(-128 // (world * K)))
         for r in range(world):
-            rlo, rhi = int(rank_lo[r]), int(rank_hi[r])
-            r_lens, r_gc = lens_o[rlo:rhi], gc_o[rlo:rhi]
-            r_ngc = int(r_gc.sum())
-            r_gcb = np.array([vg.gcadpcm.sample_count_to_byte_count(int(v)) for v in r_lens[:r_ngc]], dtype=np.int64)
-            r_adb = np.array([vg.lib.vgb_adx_encoded_byte_count(int(v), 0, 18) for v in r_lens[r_ngc:]], dtype=np.int64)
-            r_gc_off = np.concatenate(([0], np.cumsum((r_gcb + 15) // 16 * 16)[:-1])).astype(np.int64) if r_ngc else np.zeros(0, np.int64)
-            r_coef_at = int(((r_gcb + 15) // 16 * 16).sum())
-            r_adx_at = (r_coef_at + r_ngc * 32 + 15) // 16 * 16
-            r_adx_off = (r_adx_at + np.concatenate(([0], np.cumsum((r_adb + 15) // 16 * 16)[:-1]))).astype(np.int64) if len(r_adb) else np.zeros(0, np.int64)
-            base = int(out_offsets[r]) if world > 1 else 0
-            want_each = max(1, 128 // world)
-            for i in rng.choice(r_ngc, min(want_each, r_ngc), replace=False) if r_ngc else []:
-                L = int(r_lens[i])
-                o = int(offs_o[rlo + i])
-                x = slab[o:o + L].cpu().numpy()
-                t0 = time.perf_counter()
-                co = pyoracle.calculate_coefficients(x)
-                want = pyoracle.encode(x, co)
-                cpu_t += time.perf_counter() - t0
-                cpu_samples += L
-                got = src_buf[base + int(r_gc_off[i]):base + int(r_gc_off[i]) + int(r_gcb[i])].cpu().numpy()
-                gco = src_buf[base + r_coef_at + 32 * int(i):base + r_coef_at + 32 * int(i) + 32].cpu().numpy().view(np.int16)
-                ok = ok and np.array_equal(got, want) and np.array_equal(gco, co)
-                checked_gc += 1
-            n_ad = len(r_adb)
-            for i in rng.choice(n_ad, min(want_each, n_ad), replace=False) if n_ad else []:
-                L = int(r_lens[r_ngc + i])
-                o = int(offs_o[rlo + r_ngc + i])
-                x = slab[o:o + L].cpu().numpy()
-                want, _ = pyoracle.adx_encode(x, SAMPLE_RATE, 18, 4, 0, 3, 0)
-                got = src_buf[base + int(r_adx_off[i]):base + int(r_adx_off[i]) + int(r_adb[i])].cpu().numpy()
-                ok = ok and np.array_equal(got, want)
-                checked_adx += 1
+            for k in range(K):
+                c = chunks[r][k]
+                base = gathered_off[(r, k)]
+                for i in (rng.choice(c.n_gc, min(want_each, c.n_gc), replace=False) if c.n_gc else []):
+                    L, o = int(c.gc_lens[i]), c.slab_off + int(c.file_off[i])
+                    x = slab[o:o + L].cpu().numpy()
+                    t0 = time.perf_counter()
+                    co = pyoracle.calculate_coefficients(x)
+                    want = pyoracle.encode(x, co)
+                    cpu_t += time.perf_counter() - t0
+                    cpu_samples += L
+                    got = gathered[base + int(c.gc_out[i]):base + int(c.gc_out[i]) + int(c.gc_bytes[i])].cpu().numpy()
+                    gco = gathered[base + c.coef_at + 32 * int(i):base + c.coef_at + 32 * int(i) + 32].cpu().numpy().view(np.int16)
+                    ok = ok and np.array_equal(got, want) and np.array_equal(gco, co)
+                    checked_gc += 1
+                for i in (rng.choice(c.n_adx, min(want_each, c.n_adx), replace=False) if c.n_adx else []):
+                    L, o = int(c.adx_lens[i]), c.slab_off + int(c.file_off[c.n_gc + i])
+                    x = slab[o:o + L].cpu().numpy()
+                    want, _ = pyoracle.adx_encode(x, SAMPLE_RATE, 18, 4, 0, 3, 0)
+                    got = gathered[base + int(c.adx_out[i]):base + int(c.adx_out[i]) + int(c.adx_bytes[i])].cpu().numpy()
+                    ok = ok and np.array_equal(got, want)
+                    checked_adx += 1
         parity = {"gc_files_checked": checked_gc, "adx_files_checked": checked_adx, "bytes_equal_oracle": bool(ok)}
         cores = os.cpu_count() or 1
         if cpu_t > 0:
@@ -590,17 +682,21 @@ def run_c5(args, env, ctx):
     if rank != 0:
         return None
     mean_enc = float(enc_all.mean()) if world > 0 else 0.0
+    peak, peak_src = _peak()
+    per_gpu = total * 2.567 / (float(enc_all.max()) / 1e3) / 1e9 / world if enc_all.max() > 0 else None
     line = _base_line("mixed GC-ADPCM + ADX batch encode Msamples/sec", value, world, args, ms, "strong", "int32",
                       {"workload": f"{n_files} mono files, 1-10 s x 48 kHz, even -> GC-ADPCM (coefs + encode), odd -> CRI ADX (Linear, v4, 18 B frames); whole job",
-                       "total_samples": total, "files_per_rank": [int(rank_hi[r] - rank_lo[r]) for r in range(world)],
-                       "l2": "inputs (34.6 GB) larger than L2, no flush needed", "parallelism": f"{world} ranks, files partitioned longest-first, one NCCL scatterv + gatherv per step"})
+                       "total_samples": total, "files_per_rank": [int((part == r).sum()) for r in range(world)], "chunks_per_rank": K,
+                       "l2": "inputs (34.6 GB) larger than L2, no flush needed",
+                       "parallelism": f"{world} ranks, files partitioned longest-first; the root holds the PCM, per chunk one NCCL group scatters chunk t and gathers chunk t-2 while chunk t-1 encodes"})
     line.update({"e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                 "collective": {"scatter_ms": round(sc_ms, 3), "gather_ms": round(ga_ms, 3), "scatter_bytes": int(pcm_counts.sum() - pcm_counts[0]),
-                                "gather_bytes": int(out_counts.sum() - out_counts[0]), "nccl_version": int(vg.lib.vgb_nccl_version()),
-                                "encode_ms_per_rank": [round(float(v), 3) for v in enc_all],
-                                "imbalance": round(float(enc_all.max() / mean_enc), 4) if mean_enc > 0 else None},
-                 "roofline": {"bound": "hbm", "kernel": "gc_encode_kernel + adx_encode_kernel", "achieved": round(total * 2.567 / (float(enc_all.max()) / 1e3) / 1e9 / world, 2) if enc_all.max() > 0 else None,
-                              "peak": _peak()[0], "unit": "GB/s", "frac": round(total * 2.567 / (float(enc_all.max()) / 1e3) / 1e9 / world / _peak()[0], 5) if enc_all.max() > 0 else None,
-                              "traffic": None, "peak_source": _peak()[1], "note": "per-GPU algorithmic bytes (2 B in + ~0.57 B out per sample) over the slowest rank's encode time"},
+                 "collective": {"comm_busy_ms": round(comm_all, 3), "scatter_bytes": scatter_bytes, "gather_bytes": gather_bytes,
+                                "nccl_version": int(vg.lib.vgb_nccl_version()), "encode_ms_per_rank": [round(float(v), 3) for v in enc_all],
+                                "imbalance": round(float(enc_all.max() / mean_enc), 4) if mean_enc > 0 else None,
+                                "exposed_ms": round(ms - float(enc_all.max()), 3),
+                                "note": "comm_busy_ms = summed duration of the NCCL groups of one step on the busiest rank; exposed_ms = step time minus the slowest rank's encode time; run with --c5-chunks 1 for separate scatter / gather times"},
+                 "roofline": {"bound": "hbm", "kernel": "gc_encode_kernel + adx_encode_kernel", "achieved": round(per_gpu, 2) if per_gpu else None,
+                              "peak": peak, "unit": "GB/s", "frac": round(per_gpu / peak, 5) if per_gpu else None, "traffic": None, "peak_source": peak_src,
+                              "note": "per-GPU algorithmic bytes (2 B in + ~0.57 B out per sample) over the slowest rank's encode time"},
                  "cpu_baseline": cpu, "parity": parity})
     return line

@@ -63,6 +63,8 @@ int32_t vgb_device_count(void);
  *   vgb_nccl_init        every rank, with its CUDA device current (after vgb_init): joins the communicator
  *   vgb_scatterv_dev     root: bytes [send_offset[r], +counts[r]) of d_send go to rank r's d_recv; asynchronous on stream
  *   vgb_gatherv_dev      rank r's counts[r] bytes at d_send land at d_recv + recv_offset[r] on the root
+ *   vgb_sendrecv_dev     one NCCL group of arbitrary sends and receives (both directions at once: the pipelined batch path
+ *                        scatters chunk k+1 while it gathers chunk k-1 over the full-duplex links)
  *   vgb_partition_lpt    greedy longest-first bin packing of units (files / channels) onto parts by weight (samples):
  *                        part_out[u] = part of unit u, load_out[p] = summed weight (may be NULL)
  * ------------------------------------------------------------------------------------------------------- */
@@ -75,6 +77,8 @@ int32_t vgb_scatterv_dev(const void *d_send, const int64_t *send_offset, const i
                          void *d_recv, int32_t root, void *cuda_stream);
 int32_t vgb_gatherv_dev(const void *d_send, void *d_recv, const int64_t *recv_offset, const int64_t *counts /* [n_ranks] bytes */,
                         int32_t root, void *cuda_stream);
+int32_t vgb_sendrecv_dev(const void *const *send_ptr, const int64_t *send_bytes, const int32_t *send_peer, int32_t n_send,
+                         void *const *recv_ptr, const int64_t *recv_bytes, const int32_t *recv_peer, int32_t n_recv, void *cuda_stream);
 int32_t vgb_partition_lpt(const int64_t *weight, int32_t n_units, int32_t n_parts, int32_t *part_out, int64_t *load_out);
 const char *vgb_last_error(void);
 /* Pinned host memory, so the host entry points can DMA straight from/to the caller's buffers. */

@@ -116,7 +116,8 @@ def test_time_parallel_encode_is_bit_exact(vg, oracle, seg):
     cfgs = [_cfg(vg, sample_rate=48000, version=4 - (i % 2), type=2 + (i % 3), filter=i % 4) for i in range(len(chans))]
     cfgs[8] = _cfg(vg, sample_rate=44100, frame_size=34, version=4, type=3)   # not the standard layout
     cfgs[9] = _cfg(vg, sample_rate=48000, padding=45, version=4, type=3)      # padded stream
-    saved = os.environ.get("VGB_ADX_SEGMENTS")
+    saved = {k: os.environ.get(k) for k in ("VGB_ADX_SEGMENTS", "VGB_ADX_MIN_SEG_FRAMES")}
+    os.environ["VGB_ADX_MIN_SEG_FRAMES"] = "256"  # the default (4096) is sized for the run-on tail; short inputs must still be cut
     if seg is None:
         os.environ.pop("VGB_ADX_SEGMENTS", None)
     else:
@@ -124,10 +125,11 @@ def test_time_parallel_encode_is_bit_exact(vg, oracle, seg):
     try:
         adpcm, hist = vg.criadx.encode_batch(chans, cfgs)
     finally:
-        if saved is None:
-            os.environ.pop("VGB_ADX_SEGMENTS", None)
-        else:
-            os.environ["VGB_ADX_SEGMENTS"] = saved
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     for c, pcm in enumerate(chans):
         p = cfgs[c]
         want, want_hist = oracle.adx_encode(pcm, p.sample_rate, p.frame_size, p.version, p.padding, p.type, p.filter)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "vgb_nccl_version": (C.c_int32, []),
     "vgb_scatterv_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_gatherv_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_sendrecv_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_partition_lpt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vgb_last_error": (C.c_char_p, []),
     "vgb_host_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_uint64]),

@@ -496,13 +496,25 @@ adx_decode_kernel(const uint8_t *__restrict__ adpcm, const AdxChannel *__restric
 
 // Segments per channel of the time-parallel ADX encode: thread-per-item kernels want every SM full of threads
 // (~512 resident per SM at this register count), the run-on at a boundary is a handful of frames.
+// Shortest segment in frames.  Measured with the oracle on the synthetic set: a chain started from raw history meets the
+// true one after 100-600 frames as a rule (quantisation step = maxDistance / 7 is hundreds of LSB on loud material, so the
+// two reconstructions rarely coincide twice in a row), hence segments of at least 4096 frames; tests lower it.
+int adx_min_segment_frames()
+{
+    if (const char *env = std::getenv("VGB_ADX_MIN_SEG_FRAMES")) {
+        const int v = std::atoi(env);
+        if (v >= 1) return v;
+    }
+    return kAdxMinSegFrames;
+}
+
 int adx_encode_pick_segments(int n_channels, int max_whole_frames)
 {
     if (const char *env = std::getenv("VGB_ADX_SEGMENTS")) {
         const int v = std::atoi(env);
         if (v >= 1) return v > kAdxMaxSegments ? kAdxMaxSegments : v;
     }
-    const int max_s = std::max(1, std::min(kAdxMaxSegments, max_whole_frames / kAdxMinSegFrames));
+    const int max_s = std::max(1, std::min(kAdxMaxSegments, max_whole_frames / adx_min_segment_frames()));
     const long long want = (4ll * 148 * 512 + n_channels - 1) / std::max(n_channels, 1);  // about four waves of threads
     return (int)std::max<long long>(1, std::min<long long>(want, max_s));
 }
@@ -513,7 +525,7 @@ void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels
     if (n_channels <= 0) return;
     if (sa.seg_count < 1 || !sa.trace) sa.seg_count = 1;
     if (sa.seg_count > kAdxMaxSegments) sa.seg_count = kAdxMaxSegments;
-    sa.min_seg_frames = kAdxMinSegFrames;
+    sa.min_seg_frames = adx_min_segment_frames();
     const int blocks = (n_channels + kAdxThreads - 1) / kAdxThreads;
     if (sa.stats) cudaMemsetAsync(sa.stats, 0, 4 * sizeof(unsigned long long), stream);
     adx_encode_kernel<kAdxChain><<<dim3(blocks, sa.seg_count), kAdxThreads, 0, stream>>>(pcm, tab, n_channels, adpcm, history_out, sa);

@@ -200,6 +200,29 @@ int32_t vgb_gatherv_dev(const void *d_send, void *d_recv, const int64_t *recv_of
     return VGB_OK;
 }
 
+int32_t vgb_sendrecv_dev(const void *const *send_ptr, const int64_t *send_bytes, const int32_t *send_peer, int32_t n_send,
+                         void *const *recv_ptr, const int64_t *recv_bytes, const int32_t *recv_peer, int32_t n_recv, void *cuda_stream)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_comm) return abi_fail(VGB_E_STATE, "no communicator: call vgb_nccl_init on every rank first");
+    if (n_send < 0 || n_recv < 0 || (n_send > 0 && (!send_ptr || !send_bytes || !send_peer)) || (n_recv > 0 && (!recv_ptr || !recv_bytes || !recv_peer)))
+        return abi_fail(VGB_E_ARG, "bad arguments");
+    for (int i = 0; i < n_send; i++)
+        if (send_bytes[i] < 0 || send_peer[i] < 0 || send_peer[i] >= g_ranks || send_peer[i] == g_rank || (send_bytes[i] > 0 && !send_ptr[i]))
+            return abi_fail(VGB_E_ARG, "send %d: bad peer / size / pointer", i);
+    for (int i = 0; i < n_recv; i++)
+        if (recv_bytes[i] < 0 || recv_peer[i] < 0 || recv_peer[i] >= g_ranks || recv_peer[i] == g_rank || (recv_bytes[i] > 0 && !recv_ptr[i]))
+            return abi_fail(VGB_E_ARG, "recv %d: bad peer / size / pointer", i);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    NCCL_TRY(g_api.GroupStart());
+    for (int i = 0; i < n_send; i++)
+        if (send_bytes[i] > 0) NCCL_TRY(g_api.Send(send_ptr[i], (size_t)send_bytes[i], ncclInt8, send_peer[i], g_comm, st));
+    for (int i = 0; i < n_recv; i++)
+        if (recv_bytes[i] > 0) NCCL_TRY(g_api.Recv(recv_ptr[i], (size_t)recv_bytes[i], ncclInt8, recv_peer[i], g_comm, st));
+    NCCL_TRY(g_api.GroupEnd());
+    return VGB_OK;
+}
+
 int32_t vgb_partition_lpt(const int64_t *weight, int32_t n_units, int32_t n_parts, int32_t *part_out, int64_t *load_out)
 {
     if (n_units < 0 || n_parts < 1 || (n_units > 0 && (!weight || !part_out))) return abi_fail(VGB_E_ARG, "bad arguments");

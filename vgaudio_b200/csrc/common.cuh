@@ -88,7 +88,7 @@ struct AdxChannel {
 };
 
 // Time-parallel ADX encoding (adx.cu): bookkeeping of one launch.  trace == nullptr: plain serial encode.
-constexpr int kAdxMinSegFrames = 256;
+constexpr int kAdxMinSegFrames = 4096;  // a boundary's run-on is some hundred frames here (the fixed predictor's error decays slowly); VGB_ADX_MIN_SEG_FRAMES overrides
 constexpr int kAdxMaxSegments = 64;
 struct AdxSegArgs {
     uint32_t *trace;             // [trace_off[ch] + frame] the reconstructed pair a whole frame hands on
