@@ -360,6 +360,123 @@ int32_t vgb_imdct128_batch(const double *in, int32_t n_sequences, int32_t n_bloc
 int32_t vgb_hca_decode_batch(const uint8_t *const *frames, const vgb_hca_info *info, int32_t n_streams,
                              int16_t *const *pcm_out);
 
+
+/* =====================================================================================================================
+ * Containers either side of the codec path: the WAVE front end, the DSP / ADX / HCA writers, the
+ * DSP reader, CRI encryption, and the batch converter that replaces the CLI's file-level Parallel.ForEach.  All payload
+ * movement (de-interleave, block / frame interleave, key streams, substitution + CRC) runs on the GPU; header fields are
+ * host integer logic.  Sizes come first (vgb_*_file_size), the caller allocates, the call fills.
+ * ===================================================================================================================== */
+
+/* WaveStructure (Containers/Wave/WaveStructure.cs) + where the data chunk's payload sits in the file. */
+typedef struct vgb_wave_info {
+    int32_t channel_count, sample_rate, bits_per_sample, sample_count;
+    int32_t looping, loop_start, loop_end, reserved;
+    int64_t data_offset, data_size;
+} vgb_wave_info;
+
+/* RiffParser.ParseRiff (Utilities/Riff/RiffParser.cs:38-86) + WaveReader.ReadFile / ValidateWaveFile
+ * (Containers/Wave/WaveReader.cs:13-51, :71-95) on a file image in host memory: chunk walk ("fmt ", "smpl", "data";
+ * 2-byte alignment; a later chunk of the same id replaces an earlier one), validation in the reference's order with its
+ * messages in vgb_last_error() (VGB_E_DATA = InvalidDataException), loop points from the first smpl loop, WithLoop's range
+ * check (Formats/AudioFormatBaseBuilder.cs:23-50).  Host only. */
+int32_t vgb_wave_parse(const uint8_t *file, int64_t length, vgb_wave_info *info_out);
+
+/* data.Data.InterleavedByteToShort(channelCount) (WaveReader.cs:47, Interleave.cs:188-207) for a batch of parsed files:
+ * pcm_out is a flat file-major table of channel rows (sample_count samples each).  8-bit files come out as PCM16 through
+ * Pcm8Codec.Decode ((b - 0x80) << 8, Codecs/Pcm8/Pcm8Codec.cs:23), which is what every encoder asks AudioData for. */
+int32_t vgb_wave_read_batch(const uint8_t *const *files, const vgb_wave_info *info, int32_t n_files, int16_t *const *pcm_out);
+
+/* What DspWriter reads from GcAdpcmFormat and DspConfiguration (Containers/Dsp/DspWriter.cs:17-36, DspConfiguration.cs):
+ * sample_count / loop points are the format's; 0 in the three option fields selects the reference's defaults
+ * (SamplesPerInterleave 0x3800, LoopPointAlignment 1, TrimFile true). */
+typedef struct vgb_dsp_desc {
+    int32_t channel_count, sample_rate, sample_count, looping, loop_start, loop_end;
+    int32_t samples_per_interleave, loop_point_alignment, no_trim;
+} vgb_dsp_desc;
+int64_t vgb_dsp_file_size(const vgb_dsp_desc *desc); /* FileSize (:17); negative = VGB_E_* */
+
+/* DspWriter.WriteStream (:42-99) for n_files files: 0x60-byte big-endian header per channel, then the payload (mono: the
+ * channel; else Interleave(BytesPerInterleave, AudioDataSize)).  adpcm / coefs ([ch][16]) / gain / start_hist ([ch][2]) /
+ * loop_context ([ch][3] = PredScale, Hist1, Hist2, e.g. from vgb_gcadpcm_seek_context_batch) are flat file-major tables
+ * over all channels; gain, start_hist may be NULL (zeros), loop_context may be NULL when nothing loops.  adpcm[c] holds
+ * SampleCountToByteCount(sample_count) bytes.  files_out[i] receives vgb_dsp_file_size bytes. */
+int32_t vgb_dsp_write_batch(const vgb_dsp_desc *files, int32_t n_files, const uint8_t *const *adpcm, const int16_t *coefs,
+                            const int16_t *gain, const int16_t *start_hist, const int16_t *loop_context, uint8_t *const *files_out);
+
+#define VGB_DSP_MAX_CHANNELS 64
+typedef struct vgb_dsp_info { /* DspStructure (Containers/Dsp/DspStructure.cs) */
+    int32_t sample_count, nibble_count, sample_rate, looping, format, start_address, end_address, current_address;
+    int32_t channel_count, frames_per_interleave, loop_start, loop_end;
+    int16_t coefs[VGB_DSP_MAX_CHANNELS][16], gain[VGB_DSP_MAX_CHANNELS];
+    int16_t start_context[VGB_DSP_MAX_CHANNELS][3], loop_context[VGB_DSP_MAX_CHANNELS][3];
+} vgb_dsp_info;
+/* DspReader.ReadHeader (Containers/Dsp/DspReader.cs:57-104), host only; VGB_E_DATA with the reference's messages. */
+int32_t vgb_dsp_parse(const uint8_t *file, int64_t length, vgb_dsp_info *info_out);
+/* DspReader.ReadData (:106-119): adpcm_out is a flat file-major table of channel rows, SampleCountToByteCount(sample_count)
+ * bytes each; multi-channel payloads are de-interleaved on the device. */
+int32_t vgb_dsp_read_batch(const uint8_t *const *files, const int64_t *lengths, const vgb_dsp_info *info, int32_t n_files,
+                           uint8_t *const *adpcm_out);
+
+/* What AdxWriter reads from CriAdxFormat and AdxConfiguration (Containers/Adx/AdxWriter.cs:18-55).  sample_count and the
+ * loop points are the UNALIGNED values of the PCM (the format adds alignment_samples, CriAdxFormat.cs:16-18);
+ * highpass_frequency is 500 for anything the encoder made (CriAdxFormat.cs:84). */
+typedef struct vgb_adx_desc {
+    int32_t channel_count, sample_rate, sample_count, looping, loop_start, loop_end, alignment_samples;
+    int32_t frame_size, version, type, highpass_frequency, encryption_type, no_trim;
+} vgb_adx_desc;
+typedef struct vgb_adx_key { int32_t seed, mult, inc; } vgb_adx_key; /* CriAdxKey */
+int32_t vgb_adx_key_from_code(uint64_t key_code, vgb_adx_key *key_out);       /* CriAdxKey(ulong), CriAdxKey.cs:18-24 */
+int32_t vgb_adx_key_from_string(const char *key_string, vgb_adx_key *key_out); /* CriAdxKey(string), :26-41 (ASCII) */
+int64_t vgb_adx_file_size(const vgb_adx_desc *desc);                           /* FileSize (:18) */
+/* AdxWriter.WriteStream (:70-140): header, frame-interleaved audio (encrypted copy when key != NULL,
+ * CriAdxEncryption.EncryptDecrypt), footer.  audio / audio_len / history are flat file-major tables over all channels
+ * (channels of a file must have equal lengths); history may be NULL. */
+int32_t vgb_adx_write_batch(const vgb_adx_desc *files, int32_t n_files, const uint8_t *const *audio, const int32_t *audio_len,
+                            const int16_t *history, const vgb_adx_key *key, uint8_t *const *files_out);
+/* CriAdxEncryption.EncryptDecrypt(byte[][] adpcm, key, encryptionType, frameSize) (CriAdxEncryption.cs:8-44) on the
+ * channels of one file, in place; length must be a whole number of frames. */
+int32_t vgb_adx_crypt_batch(uint8_t *const *audio, int32_t n_channels, int32_t length, const vgb_adx_key *key,
+                            int32_t encryption_type, int32_t frame_size);
+
+/* CriHcaKey (Codecs/CriHca/CriHcaKey.cs): key_type 0, 1 or 56 (key_code used by 56 only); 256-byte substitution tables. */
+int32_t vgb_hca_key_tables(int32_t key_type, uint64_t key_code, uint8_t *decrypt_out, uint8_t *encrypt_out);
+/* CriHcaEncryption.Crypt (CriHcaEncryption.cs:12-33) for a batch of streams, in place: substitution over the first
+ * frame_size-2 bytes of every frame, CRC-16 recomputed.  frames[s] = frame_count[s] * frame_size bytes. */
+int32_t vgb_hca_crypt_batch(uint8_t *const *frames, const int32_t *frame_count, int32_t n_streams, int32_t frame_size,
+                            int32_t key_type, uint64_t key_code, int32_t decrypt);
+/* HcaWriter.WriteStream (Containers/Hca/HcaWriter.cs:37-178): chunked header ("HCA", "fmt", "comp", "loop", "ciph", "rva",
+ * "comm" / "pad"; ids masked with 0x80 when a key is given), header CRC, frames (encrypted when key_type >= 0; -1 = no key).
+ * comment / volume may be NULL (none / 1.0).  files_out[i] receives header_size + frame_count * frame_size bytes. */
+int32_t vgb_hca_write_batch(const vgb_hca_info *info, int32_t n_files, const uint8_t *const *frames, int32_t key_type,
+                            uint64_t key_code, const char *const *comment, const float *volume, uint8_t *const *files_out);
+
+/* Batch converter: replaces BatchConvert's Parallel.ForEach over files (src/VGAudio.Cli/Batch.cs:24-46, each body =
+ * Convert.ConvertFile: WaveReader -> GetFormat<T> (encode) -> writer) for WAVE inputs held in host memory.  Files are
+ * coalesced into GPU batches; per batch: one H2D of the raw data chunks, de-interleave -> encode -> (loop context) ->
+ * file assembly on the device, one D2H of the finished files; neighbouring batches overlap copies and kernels.
+ * Zero-initialised options = the reference's defaults. */
+#define VGB_CONTAINER_DSP 1
+#define VGB_CONTAINER_ADX 2
+#define VGB_CONTAINER_HCA 3
+typedef struct vgb_convert_options {
+    int32_t out_type;                   /* VGB_CONTAINER_* */
+    int32_t no_trim;                    /* Configuration.TrimFile = !no_trim */
+    int32_t dsp_samples_per_interleave, dsp_loop_point_alignment;
+    int32_t adx_version, adx_frame_size, adx_type, adx_filter_plus1; /* 0 = 4, 18, Linear, filter 2 (AdxConfiguration.cs) */
+    int32_t adx_encryption_type, adx_has_key, adx_key_seed, adx_key_mult, adx_key_inc;
+    int32_t hca_quality, hca_bitrate, hca_limit_bitrate;             /* CriHcaParameters */
+    int32_t hca_key_type;               /* -1 = no key; NOTE: 0 is a key type, set -1 explicitly */
+    int32_t reserved;
+    uint64_t hca_key_code;
+    int64_t group_bytes;                /* input bytes per GPU batch; 0 = 256 MiB */
+} vgb_convert_options;
+/* Pass files_out == NULL for the sizing pass: out_sizes[i] = size of output i (0 for a file that failed), status_out[i]
+ * (may be NULL) = VGB_OK or the error of file i - a bad file does not stop the batch (Batch.cs:39-43).  The second pass
+ * fills files_out[i] for every file whose status is VGB_OK.  cb receives the number of files finished. */
+int32_t vgb_convert_wave_batch(const uint8_t *const *files, const int64_t *lengths, int32_t n_files, const vgb_convert_options *options,
+                               int64_t *out_sizes, uint8_t *const *files_out, int32_t *status_out, vgb_progress_cb cb, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,188 @@ def hca_mdct_tables(bits: int):
 def crc16(data: bytes) -> int:
     buf = np.frombuffer(data, dtype=np.uint8)
     return int(lib().vgo_crc16(buf.ctypes.data, len(buf)))
+
+
+# ---- container layer (oracle/containers.c) -------------------------------------------------------
+class WaveInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "bits_per_sample", "sample_count", "looping",
+                                         "loop_start", "loop_end", "reserved")] + [("data_offset", C.c_int64), ("data_size", C.c_int64)]
+
+
+class DspDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "sample_count", "looping", "loop_start", "loop_end",
+                                         "samples_per_interleave", "loop_point_alignment", "trim_file")]
+
+
+class DspInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("sample_count", "nibble_count", "sample_rate", "looping", "format", "start_address",
+                                         "end_address", "current_address", "channel_count", "frames_per_interleave",
+                                         "loop_start", "loop_end")] + [
+        ("coefs", (C.c_int16 * 16) * 64), ("gain", C.c_int16 * 64), ("start_ctx", (C.c_int16 * 3) * 64), ("loop_ctx", (C.c_int16 * 3) * 64)]
+
+
+class AdxDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "sample_count", "looping", "loop_start", "loop_end",
+                                         "alignment_samples", "frame_size", "version", "type", "highpass_frequency",
+                                         "encryption_type", "trim_file")]
+
+
+def _u8(b) -> np.ndarray:
+    return np.frombuffer(bytes(b), dtype=np.uint8) if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, dtype=np.uint8).ravel()
+
+
+def _ptrs(rows):
+    return (C.c_void_p * max(len(rows), 1))(*[r.ctypes.data for r in rows])
+
+
+def wave_parse(file):
+    """(status, WaveInfo): status 0 or a VGO_E_* code."""
+    L = lib()
+    f = _u8(file)
+    info = WaveInfo()
+    L.vgo_wave_parse.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    return int(L.vgo_wave_parse(f.ctypes.data, f.size, C.byref(info))), info
+
+
+def wave_read(file, info: WaveInfo):
+    L = lib()
+    f = _u8(file)
+    rows = [np.zeros(info.sample_count, dtype=np.int16) for _ in range(info.channel_count)]
+    fn = L.vgo_wave_read16 if info.bits_per_sample == 16 else L.vgo_wave_read8_as16
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    fn(f.ctypes.data, C.byref(info), _ptrs(rows))
+    return rows
+
+
+def wave_write16(channels, sample_rate=48000, loop=None) -> np.ndarray:
+    """WaveWriter (16-bit codec): the reference's own way to make the files its reader test parses."""
+    L = lib()
+    rows = [np.ascontiguousarray(c, dtype=np.int16) for c in channels]
+    n = rows[0].size
+    L.vgo_wave_file_size.restype = C.c_int64
+    L.vgo_wave_file_size.argtypes = [C.c_int, C.c_int, C.c_int]
+    out = np.zeros(L.vgo_wave_file_size(len(rows), n, int(loop is not None)), dtype=np.uint8)
+    L.vgo_wave_write16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.vgo_wave_write16.restype = None
+    L.vgo_wave_write16(_ptrs(rows), len(rows), n, sample_rate, int(loop is not None), loop[0] if loop else 0, loop[1] if loop else 0,
+                       out.ctypes.data)
+    return out
+
+
+def dsp_write(adpcm, coefs, sample_rate, sample_count, loop=None, loop_ctx=None, gain=None, start_hist=None,
+              samples_per_interleave=0x3800, loop_point_alignment=1, trim_file=True) -> np.ndarray:
+    L = lib()
+    rows = [_u8(a) for a in adpcm]
+    d = DspDesc(len(rows), sample_rate, sample_count, int(loop is not None), loop[0] if loop else 0, loop[1] if loop else 0,
+                samples_per_interleave, loop_point_alignment, int(trim_file))
+    L.vgo_dsp_file_size.restype = C.c_int64
+    L.vgo_dsp_file_size.argtypes = [C.c_void_p]
+    out = np.zeros(L.vgo_dsp_file_size(C.byref(d)), dtype=np.uint8)
+    co = np.ascontiguousarray(coefs, dtype=np.int16)
+    g = np.ascontiguousarray(gain, dtype=np.int16) if gain is not None else None
+    sh = np.ascontiguousarray(start_hist, dtype=np.int16) if start_hist is not None else None
+    lc = np.ascontiguousarray(loop_ctx, dtype=np.int16) if loop_ctx is not None else None
+    L.vgo_dsp_write.argtypes = [C.c_void_p] * 7
+    st = L.vgo_dsp_write(C.byref(d), _ptrs(rows), co.ctypes.data, g.ctypes.data if g is not None else None,
+                         sh.ctypes.data if sh is not None else None, lc.ctypes.data if lc is not None else None, out.ctypes.data)
+    if st != 0:
+        raise ValueError(f"vgo_dsp_write: {st}")
+    return out
+
+
+def dsp_parse(file):
+    L = lib()
+    f = _u8(file)
+    info = DspInfo()
+    L.vgo_dsp_parse.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    return int(L.vgo_dsp_parse(f.ctypes.data, f.size, C.byref(info))), info
+
+
+def dsp_read_data(file, info: DspInfo):
+    L = lib()
+    f = _u8(file)
+    rows = [np.zeros(sample_count_to_byte_count(info.sample_count), dtype=np.uint8) for _ in range(info.channel_count)]
+    L.vgo_dsp_read_data.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    st = L.vgo_dsp_read_data(f.ctypes.data, f.size, C.byref(info), _ptrs(rows))
+    if st != 0:
+        raise ValueError(f"vgo_dsp_read_data: {st}")
+    return rows
+
+
+def adx_key(key_code=None, key_string=None):
+    L = lib()
+    k = (C.c_int32 * 3)()
+    if key_string is not None:
+        L.vgo_adx_key_from_string.argtypes = [C.c_char_p, C.c_void_p]
+        L.vgo_adx_key_from_string.restype = None
+        L.vgo_adx_key_from_string(key_string.encode("ascii"), k)
+    else:
+        L.vgo_adx_key_from_code.argtypes = [C.c_uint64, C.c_void_p]
+        L.vgo_adx_key_from_code.restype = None
+        L.vgo_adx_key_from_code(int(key_code), k)
+    return (int(k[0]), int(k[1]), int(k[2]))
+
+
+def adx_crypt(audio, key, encryption_type, frame_size):
+    L = lib()
+    rows = [np.array(a, dtype=np.uint8, copy=True) for a in audio]
+    k = (C.c_int32 * 3)(*key)
+    L.vgo_adx_crypt_channel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.vgo_adx_crypt_channel.restype = None
+    for c, r in enumerate(rows):
+        L.vgo_adx_crypt_channel(r.ctypes.data, r.size, k, encryption_type, frame_size, c, len(rows))
+    return rows
+
+
+def adx_write(audio, history, sample_rate, sample_count, loop=None, alignment_samples=0, frame_size=18, version=4, type=ADX_LINEAR,
+              highpass_frequency=500, encryption_type=0, key=None, trim_file=True) -> np.ndarray:
+    L = lib()
+    rows = [_u8(a) for a in audio]
+    d = AdxDesc(len(rows), sample_rate, sample_count, int(loop is not None), loop[0] if loop else 0, loop[1] if loop else 0,
+                alignment_samples, frame_size, version, type, highpass_frequency, encryption_type, int(trim_file))
+    L.vgo_adx_file_size.restype = C.c_int64
+    L.vgo_adx_file_size.argtypes = [C.c_void_p]
+    out = np.zeros(L.vgo_adx_file_size(C.byref(d)), dtype=np.uint8)
+    h = np.ascontiguousarray(history, dtype=np.int16)
+    k = (C.c_int32 * 3)(*key) if key is not None else None
+    L.vgo_adx_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    st = L.vgo_adx_write(C.byref(d), _ptrs(rows), rows[0].size, h.ctypes.data, k, out.ctypes.data)
+    if st != 0:
+        raise ValueError(f"vgo_adx_write: {st}")
+    return out
+
+
+def hca_key_tables(key_type, key_code=0):
+    L = lib()
+    dec, enc = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    L.vgo_hca_key_tables.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    st = L.vgo_hca_key_tables(key_type, key_code, dec.ctypes.data, enc.ctypes.data)
+    if st != 0:
+        raise ValueError(f"vgo_hca_key_tables: {st}")
+    return dec, enc
+
+
+def hca_crypt_frames(frames, frame_size, table) -> np.ndarray:
+    L = lib()
+    out = np.array(frames, dtype=np.uint8, copy=True).ravel()
+    t = np.ascontiguousarray(table, dtype=np.uint8)
+    L.vgo_hca_crypt_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.vgo_hca_crypt_frame.restype = None
+    for f in range(out.size // frame_size):
+        L.vgo_hca_crypt_frame(out.ctypes.data + f * frame_size, frame_size, t.ctypes.data)
+    return out
+
+
+def hca_write(info: HcaInfo, frames, encrypt_table=None, key_type=0, comment=None, volume=1.0) -> np.ndarray:
+    L = lib()
+    fr = _u8(frames)
+    out = np.zeros(info.header_size + info.frame_size * info.frame_count, dtype=np.uint8)
+    t = np.ascontiguousarray(encrypt_table, dtype=np.uint8) if encrypt_table is not None else None
+    vbits = int(np.array([volume], dtype=np.float32).view(np.uint32)[0])
+    L.vgo_hca_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p]
+    st = L.vgo_hca_write(C.byref(info), fr.ctypes.data, t.ctypes.data if t is not None else None, key_type,
+                         comment.encode("utf-8") if comment is not None else None, vbits, out.ctypes.data)
+    if st != 0:
+        raise ValueError(f"vgo_hca_write: {st}")
+    return out

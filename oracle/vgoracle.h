@@ -117,6 +117,56 @@ uint16_t vgo_crc16(const uint8_t *data, int size);                              
 int vgo_interleave(const uint8_t *const *inputs, int count, int in_size, int interleave_size, int out_size, uint8_t *output);
 int vgo_deinterleave(const uint8_t *input, int length, int interleave_size, int count, int out_size, uint8_t *const *outputs);
 
+
+/* ---- container layer either side of the codec path (containers.c).  The reference pins this layer
+ * by build -> parse round trips only (Tests/Containers/DspTests.cs, WaveTests.cs): file BYTES are "parity unpinned" ---- */
+enum { VGO_E_ARG = -1, VGO_E_TRUNCATED = -2, VGO_E_NOT_RIFF = -3, VGO_E_NOT_WAVE = -4, VGO_E_NO_FMT = -5, VGO_E_NO_DATA = -6,
+       VGO_E_NOT_PCM = -7, VGO_E_BITS = -8, VGO_E_CHANNELS = -9, VGO_E_BLOCK_ALIGN = -10, VGO_E_LOOP = -11, VGO_E_NIBBLES = -12 };
+typedef struct vgo_wave_info { /* WaveStructure.cs + where the data chunk's payload sits in the file */
+    int32_t channel_count, sample_rate, bits_per_sample, sample_count, looping, loop_start, loop_end, reserved;
+    int64_t data_offset, data_size;
+} vgo_wave_info;
+int vgo_wave_parse(const uint8_t *file, int64_t len, vgo_wave_info *out);        /* RiffParser.cs:38-86, WaveReader.cs:13-95 */
+void vgo_wave_read16(const uint8_t *file, const vgo_wave_info *w, int16_t *const *channels);      /* Interleave.cs:188-207 */
+void vgo_wave_read8_as16(const uint8_t *file, const vgo_wave_info *w, int16_t *const *channels);  /* + Pcm8Codec.cs:23 */
+int64_t vgo_wave_file_size(int channels, int samples, int looping);              /* WaveWriter.cs:24-29 */
+void vgo_wave_write16(const int16_t *const *pcm, int channels, int samples, int sample_rate, int looping, int loop_start,
+                      int loop_end, uint8_t *out);                               /* WaveWriter.cs:52-132 */
+
+typedef struct vgo_dsp_desc { /* what DspWriter reads from GcAdpcmFormat + DspConfiguration */
+    int32_t channel_count, sample_rate, sample_count, looping, loop_start, loop_end;
+    int32_t samples_per_interleave /* 0x3800 */, loop_point_alignment /* 1 */, trim_file /* 1 */;
+} vgo_dsp_desc;
+int64_t vgo_dsp_file_size(const vgo_dsp_desc *d);                                /* DspWriter.cs:17 */
+int vgo_dsp_write(const vgo_dsp_desc *d, const uint8_t *const *adpcm, const int16_t *coefs, const int16_t *gain,
+                  const int16_t *start_hist, const int16_t *loop_ctx, uint8_t *out);   /* DspWriter.cs:42-99 */
+#define VGO_DSP_MAX_CHANNELS 64
+typedef struct vgo_dsp_info { /* DspStructure.cs */
+    int32_t sample_count, nibble_count, sample_rate, looping, format, start_address, end_address, current_address;
+    int32_t channel_count, frames_per_interleave, loop_start, loop_end;
+    int16_t coefs[VGO_DSP_MAX_CHANNELS][16], gain[VGO_DSP_MAX_CHANNELS], start_ctx[VGO_DSP_MAX_CHANNELS][3], loop_ctx[VGO_DSP_MAX_CHANNELS][3];
+} vgo_dsp_info;
+int vgo_dsp_parse(const uint8_t *file, int64_t len, vgo_dsp_info *out);          /* DspReader.cs:57-104 */
+int vgo_dsp_read_data(const uint8_t *file, int64_t len, const vgo_dsp_info *o, uint8_t *const *outputs); /* :106-119 */
+
+typedef struct vgo_adx_desc { /* what AdxWriter reads from CriAdxFormat + AdxConfiguration; sample_count and the loop points
+                                 are the UNALIGNED values (the format adds alignment_samples, CriAdxFormat.cs:16-18) */
+    int32_t channel_count, sample_rate, sample_count, looping, loop_start, loop_end, alignment_samples;
+    int32_t frame_size, version, type, highpass_frequency, encryption_type, trim_file;
+} vgo_adx_desc;
+void vgo_adx_key_from_code(uint64_t key_code, int32_t key[3]);                   /* CriAdxKey.cs:18-24: seed, mult, inc */
+void vgo_adx_key_from_string(const char *s, int32_t key[3]);                     /* CriAdxKey.cs:26-41 */
+void vgo_adx_crypt_channel(uint8_t *adpcm, int length, const int32_t key[3], int encryption_type, int frame_size,
+                           int channel_num, int channel_count);                  /* CriAdxEncryption.cs:16-44 */
+int64_t vgo_adx_file_size(const vgo_adx_desc *d);                                /* AdxWriter.cs:18 */
+int vgo_adx_write(const vgo_adx_desc *d, const uint8_t *const *audio, int audio_len, const int16_t *history,
+                  const int32_t *key, uint8_t *out);                             /* AdxWriter.cs:70-140 */
+
+int vgo_hca_key_tables(int key_type, uint64_t key_code, uint8_t *decrypt, uint8_t *encrypt); /* CriHcaKey.cs */
+void vgo_hca_crypt_frame(uint8_t *frame, int frame_size, const uint8_t *table);  /* CriHcaEncryption.cs:21-33 */
+int vgo_hca_write(const vgo_hca_info *h, const uint8_t *frames, const uint8_t *encrypt_table, int key_type,
+                  const char *comment, uint32_t volume_bits, uint8_t *out);      /* HcaWriter.cs:37-178 */
+
 #ifdef __cplusplus
 }
 #endif

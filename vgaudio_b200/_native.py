@@ -54,6 +54,54 @@ class VgbHcaInfo(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+
+class VgbWaveInfo(C.Structure):
+    """WaveStructure (Containers/Wave/WaveStructure.cs) + the data chunk's place in the file."""
+
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "bits_per_sample", "sample_count", "looping",
+                                         "loop_start", "loop_end", "reserved")] + [("data_offset", C.c_int64), ("data_size", C.c_int64)]
+
+
+class VgbDspDesc(C.Structure):
+    """What DspWriter reads from GcAdpcmFormat + DspConfiguration (Containers/Dsp/DspWriter.cs:17-36)."""
+
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "sample_count", "looping", "loop_start", "loop_end",
+                                         "samples_per_interleave", "loop_point_alignment", "no_trim")]
+
+
+DSP_MAX_CHANNELS = 64
+
+
+class VgbDspInfo(C.Structure):
+    """DspStructure (Containers/Dsp/DspStructure.cs)."""
+
+    _fields_ = [(n, C.c_int32) for n in ("sample_count", "nibble_count", "sample_rate", "looping", "format", "start_address",
+                                         "end_address", "current_address", "channel_count", "frames_per_interleave",
+                                         "loop_start", "loop_end")] + [
+        ("coefs", (C.c_int16 * 16) * DSP_MAX_CHANNELS), ("gain", C.c_int16 * DSP_MAX_CHANNELS),
+        ("start_context", (C.c_int16 * 3) * DSP_MAX_CHANNELS), ("loop_context", (C.c_int16 * 3) * DSP_MAX_CHANNELS)]
+
+
+class VgbAdxDesc(C.Structure):
+    """What AdxWriter reads from CriAdxFormat + AdxConfiguration (Containers/Adx/AdxWriter.cs:18-55)."""
+
+    _fields_ = [(n, C.c_int32) for n in ("channel_count", "sample_rate", "sample_count", "looping", "loop_start", "loop_end",
+                                         "alignment_samples", "frame_size", "version", "type", "highpass_frequency",
+                                         "encryption_type", "no_trim")]
+
+
+class VgbAdxKey(C.Structure):
+    _fields_ = [("seed", C.c_int32), ("mult", C.c_int32), ("inc", C.c_int32)]
+
+
+class VgbConvertOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("out_type", "no_trim", "dsp_samples_per_interleave", "dsp_loop_point_alignment",
+                                         "adx_version", "adx_frame_size", "adx_type", "adx_filter_plus1",
+                                         "adx_encryption_type", "adx_has_key", "adx_key_seed", "adx_key_mult", "adx_key_inc",
+                                         "hca_quality", "hca_bitrate", "hca_limit_bitrate", "hca_key_type", "reserved")] + [
+        ("hca_key_code", C.c_uint64), ("group_bytes", C.c_int64)]
+
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64)
 
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against include/vgaudio_b200.h
@@ -134,6 +182,22 @@ SIGNATURES = {
     "vgb_debug_last_coefs_done": (C.c_int32, [C.c_void_p, C.c_int32]),
     "vgb_gcadpcm_debug_records": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "vgb_gcadpcm_debug_splice_stats": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "vgb_wave_parse": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "vgb_wave_read_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_dsp_file_size": (C.c_int64, [C.c_void_p]),
+    "vgb_dsp_write_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgb_dsp_parse": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "vgb_dsp_read_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vgb_adx_key_from_code": (C.c_int32, [C.c_uint64, C.c_void_p]),
+    "vgb_adx_key_from_string": (C.c_int32, [C.c_char_p, C.c_void_p]),
+    "vgb_adx_file_size": (C.c_int64, [C.c_void_p]),
+    "vgb_adx_write_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgb_adx_crypt_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "vgb_hca_key_tables": (C.c_int32, [C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "vgb_hca_crypt_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32]),
+    "vgb_hca_write_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgb_convert_wave_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
 }
 
 

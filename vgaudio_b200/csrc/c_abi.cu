@@ -42,6 +42,7 @@ int32_t fail(int32_t code, const char *fmt, ...)
 
 }  // namespace
 namespace vgb {
+void containers_release();  // containers.cu
 int32_t abi_fail(int32_t code, const char *fmt, ...)  // for the other translation units of the boundary (collective.cu)
 {
     char buf[512];
@@ -926,6 +927,7 @@ static int32_t shutdown_current(void)  // releases the context this thread point
 
 int32_t vgb_shutdown(void)
 {
+    vgb::containers_release();  // containers.cu keeps its own slabs and streams on the primary device
     for (auto &c : g_extra) {
         t_ctx = c.get();
         shutdown_current();
@@ -934,6 +936,24 @@ int32_t vgb_shutdown(void)
     t_ctx = &g_primary;
     return shutdown_current();
 }
+
+}  // extern "C"
+
+namespace vgb {  // hooks for containers.cu
+int32_t abi_ensure_ready()
+{
+    Context &c = g_primary;
+    std::lock_guard<std::mutex> lock(c.mu);
+    Context *saved = t_ctx;
+    t_ctx = &c;
+    const int32_t s = ensure_ready_locked();
+    t_ctx = saved;
+    return s;
+}
+void abi_count_launches(int n) { g_primary.launches += n; }
+}  // namespace vgb
+
+extern "C" {
 
 /* Bind several devices (vgb_init(n_devices, flags)).  devices[0] becomes the primary device - the one the
  * *_dev entry points, the timers and the debug taps refer to; every host-pointer *_batch call is then sharded over all
