@@ -47,11 +47,13 @@ def parse_args():
     ap.add_argument("--channels", type=int, default=1024, help="channels per GPU")
     ap.add_argument("--seconds", type=float, default=30.0, help="audio seconds per channel")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "batch"],
                     help="BASELINE.json configuration: c2 GC-ADPCM encode (default, the headline), c3 GC-ADPCM decode of 8192 channels, "
-                         "c4 HCA encode of 512 streams, c5 65 536-file mixed batch with NCCL scatter/gather (strong scaling)")
+                         "c4 HCA encode of 512 streams, c5 65 536-file mixed batch with NCCL scatter/gather (strong scaling), "
+                         "batch WAVE files -> .dsp/.adx/.hca files through the batch converter (--files, default 2048)")
     ap.add_argument("--files", type=int, default=65536, help="c5: number of files in the whole job")
     ap.add_argument("--c5-chunks", type=int, default=8, help="c5: chunks per rank of the scatter / encode / gather pipeline (1: no overlap)")
+    ap.add_argument("--out-format", default="dsp", choices=["dsp", "adx", "hca"], help="batch: container to write")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

@@ -700,3 +700,162 @@ def run_c5(args, env, ctx):
                               "note": "per-GPU algorithmic bytes (2 B in + ~0.57 B out per sample) over the slowest rank's encode time"},
                  "cpu_baseline": cpu, "parity": parity})
     return line
+
+
+# ======================================================================================================================
+# batch: WAVE files in -> .dsp / .adx / .hca files out through vgb_convert_wave_batch (the CLI's
+# Batch.cs job).  One GPU; the whole chain (RIFF parse, H2D of the data chunks, de-interleave, encode, loop context, file
+# assembly, D2H) is inside the timed region - there is no device-resident variant of a file converter.
+# ======================================================================================================================
+def _batch_files(torch, bench, n_files, device, seed=0):
+    """Synthetic WAVE images in pinned host memory: mono / stereo, 1-6 s at 48 kHz, every eighth file looping."""
+    rng = np.random.default_rng(1234 + seed)
+    lens = rng.integers(1 * SAMPLE_RATE, 6 * SAMPLE_RATE + 1, n_files)
+    chans = np.where(np.arange(n_files) % 3 == 2, 2, 1)
+    files, meta = [], []
+    n_max = int(lens.max())
+    pool = bench.make_batch_gpu(torch, 64, n_max, 7 + seed, device, degenerate=False).cpu().numpy()  # 64 distinct signals
+    for i in range(n_files):
+        n, ch = int(lens[i]), int(chans[i])
+        # distinct content per file: a signal of the pool from a file-specific offset, second channel from another signal
+        rows = [np.roll(pool[(i * 2 + c) % 64], -(i * 37 + c * 101) % n_max)[:n] for c in range(ch)]
+        loop = (int(n // 5), int(n - n // 7)) if i % 8 == 5 else None
+        data = np.stack(rows, axis=1).astype("<i2").tobytes()
+        fmt = np.array([1, ch], dtype="<u2").tobytes() + np.array([SAMPLE_RATE, SAMPLE_RATE * 2 * ch], dtype="<u4").tobytes() + \
+            np.array([2 * ch, 16], dtype="<u2").tobytes()
+        smpl = b""
+        if loop:
+            body = np.zeros(15, dtype="<i4")
+            body[7] = 1
+            body[11], body[12] = loop
+            smpl = b"smpl" + np.array([0x3c], dtype="<u4").tobytes() + body.tobytes()
+        body = b"WAVE" + b"fmt " + np.array([16], dtype="<u4").tobytes() + fmt + smpl + b"data" + np.array([len(data)], dtype="<u4").tobytes() + data
+        img = b"RIFF" + np.array([len(body)], dtype="<u4").tobytes() + body
+        t = torch.empty(len(img), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = np.frombuffer(img, dtype=np.uint8)
+        files.append(t)
+        meta.append((rows, n, loop))
+    return files, meta
+
+
+def run_batch(args, env, ctx):
+    torch, vg, N, bench = ctx["torch"], ctx["vg"], ctx["N"], ctx["bench"]
+    rank, local_rank, world = env
+    if world != 1:
+        raise SystemExit("--config batch runs on one GPU (files of a job are independent: run one process per GPU on disjoint file lists)")
+    from vgaudio_b200 import containers as ct
+
+    device = torch.device("cuda", local_rank)
+    n_files = args.files if args.files != 65536 else 2048
+    out_type = {"dsp": ct.CONTAINER_DSP, "adx": ct.CONTAINER_ADX, "hca": ct.CONTAINER_HCA}[args.out_format]
+    files, meta = _batch_files(torch, bench, n_files, device)
+    total_samples = sum(len(m[0]) * m[1] for m in meta)
+    in_bytes = sum(int(f.numel()) for f in files)
+    opt = ct.convert_options(out_type, hca_quality=2)
+    n = len(files)
+    ftab = (C.c_void_p * n)(*[f.data_ptr() for f in files])
+    lens = (C.c_int64 * n)(*[int(f.numel()) for f in files])
+    sizes = (C.c_int64 * n)()
+    status = (C.c_int32 * n)()
+    N.check(vg.lib.vgb_convert_wave_batch(ftab, lens, n, C.byref(opt), sizes, None, status, None, None))
+    outs = [torch.empty(int(sizes[i]), dtype=torch.uint8, pin_memory=True) for i in range(n)]
+    otab = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    out_bytes = sum(int(sizes[i]) for i in range(n))
+
+    def step():
+        N.check(vg.lib.vgb_convert_wave_batch(ftab, lens, n, C.byref(opt), sizes, otab, status, None, None))
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
+    launches0 = vg.lib.vgb_kernel_launch_count()
+    stage = np.zeros(4)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = vg.lib.vgb_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    # the stage timers of overlapping groups overlap too: one more, untimed, pass with one group in flight gives clean ones
+    os.environ["VGB_CONVERT_SERIAL"] = "1"
+    stage[:] = 0
+    for _ in range(args.steps):
+        step()
+        buf = (C.c_float * 4)()
+        vg.lib.vgb_convert_debug_stage_ms(buf, 4)
+        stage += np.array(list(buf))
+    del os.environ["VGB_CONVERT_SERIAL"]
+    stage /= args.steps
+    value = total_samples / (ms / 1e3) / 1e6
+    peak, peak_src = _peak()
+    pcm_bytes = 2 * total_samples
+    # byte movers: the split kernel reads the data chunks and writes the channel rows (2 x PCM bytes); the assembly kernel
+    # reads the encoded payload and writes the files (2 x output bytes)
+    split_gbs = 2 * pcm_bytes / (stage[0] / 1e3) / 1e9 if stage[0] > 0 else None
+    asm_gbs = 2 * out_bytes / (stage[3] / 1e3) / 1e9 if stage[3] > 0 else None
+
+    # ---- parity + CPU baseline: the oracle's WaveReader -> encoder -> writer chain, one file per task ---------------------
+    cpu = parity = None
+    if not args.no_cpu:
+        from oracle import pyoracle as o
+
+        def one(i):
+            img = files[i].numpy()
+            st, info = o.wave_parse(img)
+            rows = o.wave_read(img, info)
+            loop = (info.loop_start, info.loop_end) if info.looping else None
+            if out_type == ct.CONTAINER_DSP:
+                coefs = np.stack([o.calculate_coefficients(p) for p in rows])
+                adpcm = [o.encode(p, c) for p, c in zip(rows, coefs)]
+                ctxs = None
+                if loop:
+                    ctxs = np.stack([np.array(o.gc_loop_context(a, o.decode(a, c, info.sample_count), loop[0]), dtype=np.int16)
+                                     for a, c in zip(adpcm, coefs)])
+                return o.dsp_write(adpcm, coefs, info.sample_rate, info.sample_count, loop, ctxs)
+            if out_type == ct.CONTAINER_ADX:
+                ch = info.channel_count
+                align = (-loop[0]) % (64 if ch == 1 else 32) if loop else 0
+                enc = [o.adx_encode(p, info.sample_rate, 18, 4, align, 3, 0) for p in rows]
+                return o.adx_write([e[0] for e in enc], [e[1] for e in enc], info.sample_rate, info.sample_count, loop, align)
+            hinfo, frames = o.hca_encode(rows, info.sample_rate, quality=2, loop=loop)
+            return o.hca_write(hinfo, frames)
+
+        cores = os.cpu_count() or 1
+        sample = list(range(min(n, max(cores, 64))))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            want = list(ex.map(one, sample))
+        cpu_s = time.perf_counter() - t0
+        cpu_samples = sum(len(meta[i][0]) * meta[i][1] for i in sample)
+        cpu = {"value": round(cpu_samples / cpu_s / 1e6, 3), "unit": "Msamples/s", "cores": min(cores, len(sample)), "kind": "port",
+               "sample": f"{len(sample)} of {n} files ({cpu_samples} samples, {cpu_s:.1f} s wall): the oracle's WaveReader -> encoder -> "
+                         f"writer chain, one file per task (ctypes releases the GIL), as Batch.cs runs Convert.ConvertFile per file"}
+        equal = all(outs[i].numpy().tobytes() == want[k].tobytes() for k, i in enumerate(sample))
+        parity = {"files_checked": len(sample), "file_bytes_equal_oracle": bool(equal)}
+
+    line = _base_line(f"batch WAVE -> .{args.out_format} conversion Msamples/sec", value, world, args, ms, "weak", "int32" if out_type != ct.CONTAINER_HCA else "f64",
+                      {"workload": f"{n} WAVE files (2/3 mono, 1/3 stereo, 1-6 s x 48 kHz, 1/8 looping) -> .{args.out_format} through vgb_convert_wave_batch",
+                       "total_samples": int(total_samples), "files_per_s": round(n / (ms / 1e3), 1),
+                       "l2": f"inputs ({in_bytes / 1e9:.2f} GB) larger than L2, no flush needed", "parallelism": "one GPU, files coalesced into 256 MiB batches"})
+    line["e2e"] = {"value": round(value, 3), "unit": "Msamples/s", "ms_per_step": round(ms, 3), "h2d_bytes_per_step": int(in_bytes),
+                   "d2h_bytes_per_step": int(out_bytes), "pcie_floor_ms": round((in_bytes / 55.6e9 + 0) * 1e3, 1),
+                   "api": "vgb_convert_wave_batch: pinned host file images in, pinned host files out (value IS the end-to-end figure: a file "
+                          "converter has no device-resident variant)"}
+    line["gpu_launches"] = int(launches)
+    line["clocks"] = clocks
+    line["stage_ms"] = {"wave_split": round(float(stage[0]), 3), "encode": round(float(stage[1]), 3), "loop_context_decode": round(float(stage[2]), 3),
+                        "file_assembly": round(float(stage[3]), 3)}
+    dom = "wave_split_kernel" if stage[0] >= stage[3] else f"{args.out_format}_assemble_kernel"
+    ach = split_gbs if stage[0] >= stage[3] else asm_gbs
+    line["roofline"] = {"bound": "hbm", "kernel": dom + " (the byte movers; the encode kernels have their own lines under --config c2/c4)",
+                        "achieved": round(ach, 1) if ach else None, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4) if ach else None,
+                        "traffic": None, "peak_source": peak_src,
+                        "byte_movers_gbs": {"wave_split": round(split_gbs, 1) if split_gbs else None, "file_assembly": round(asm_gbs, 1) if asm_gbs else None},
+                        "note": "algorithmic bytes = bytes read + bytes written once each; stage times are CUDA events around the launches of a batch "
+                                "(table uploads included), summed over the batches of a separate pass with one batch in flight (VGB_CONVERT_SERIAL)"}
+    line["cpu_baseline"] = cpu
+    line["parity"] = parity
+    return line

@@ -469,13 +469,16 @@ typedef struct vgb_convert_options {
     int32_t hca_key_type;               /* -1 = no key; NOTE: 0 is a key type, set -1 explicitly */
     int32_t reserved;
     uint64_t hca_key_code;
-    int64_t group_bytes;                /* input bytes per GPU batch; 0 = 256 MiB */
+    int64_t group_bytes;                /* input bytes per GPU batch; 0 = an eighth of the job, 64..512 MiB */
 } vgb_convert_options;
 /* Pass files_out == NULL for the sizing pass: out_sizes[i] = size of output i (0 for a file that failed), status_out[i]
  * (may be NULL) = VGB_OK or the error of file i - a bad file does not stop the batch (Batch.cs:39-43).  The second pass
  * fills files_out[i] for every file whose status is VGB_OK.  cb receives the number of files finished. */
 int32_t vgb_convert_wave_batch(const uint8_t *const *files, const int64_t *lengths, int32_t n_files, const vgb_convert_options *options,
                                int64_t *out_sizes, uint8_t *const *files_out, int32_t *status_out, vgb_progress_cb cb, void *user);
+/* Measurement tap: device time of the most recent vgb_convert_wave_batch summed over its (first 32) batches, out[0..3] =
+ * WAVE split, encode, loop-context decode, file assembly (ms, CUDA events on the kernel stream); returns the batches timed. */
+int32_t vgb_convert_debug_stage_ms(float *out, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -227,7 +227,7 @@ def test_hca_write_and_crypt_match_oracle(vg, oracle):
 def _batch_inputs(oracle):
     specs = [(1, 48000, None, 48000), (2, 30001, None, 44100), (1, 14 * 5000 + 3, (1000, 60000), 32000), (2, 20000, (2000, 20000), 48000),
              (3, 9000, None, 48000), (1, 1, None, 48000), (1, 100000, None, 48000), (2, 777, None, 22050), (6, 5000, None, 48000),
-             (1, 50000, (0, 50000), 48000), (2, 65536, None, 48000)]
+             (1, 50000, (0, 50000), 48000), (2, 65536, None, 48000), (1, 30000, (1001, 29000), 48000), (2, 9000, (7, 8000), 44100)]
     files, meta = [], []
     for k, (ch, n, loop, rate) in enumerate(specs):
         pcm = _pcm(ch, n, first=130 + 2 * k)

@@ -21,7 +21,7 @@ SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "msec
 
 
 def short_name(full):
-    m = re.search(r"(gc_\w+|adx_\w+|hca_\w+|\w*interleave\w*)(<[^>]*>)?", full)
+    m = re.search(r"(gc_\w+|adx_\w+|hca_\w+|wave_\w+|dsp_\w+|\w*interleave\w*)(<[^>]*>)?", full)
     if not m:
         return None
     name = m.group(1)

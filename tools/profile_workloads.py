@@ -8,6 +8,8 @@
   adx     CRI ADX encode + decode, 1024 ch x 30 s                          (adx_encode<chain|run-on|cascade>, adx_decode)
   hca     CRI HCA encode + decode, 128 mono streams x 30 s, + MDCT taps     (hca_encode, hca_decode_parse/unpack/seam, hca_mdct128, hca_imdct128)
   ilv     block interleave / deinterleave, 512 x 2 x 822 864 B, vector and TMA variants
+  ctn     the batch converter on 512 WAVE files: .dsp, keyed .adx, keyed .hca  (wave_split, dsp/adx/hca_assemble; capture with
+          -k regex:"wave_split|assemble" so the codec kernels are not replayed)
 """
 import ctypes as C
 import os
@@ -32,6 +34,16 @@ def main():
     os.environ["VGB_PIPELINE_GROUPS"] = "1"  # one launch per kernel
     stream = torch.cuda.current_stream()
     n = 30 * RATE
+    if what == "ctn":
+        import bench_configs
+        from vgaudio_b200 import containers as ct
+
+        files, _ = bench_configs._batch_files(torch, bench, 512, dev)
+        for opt in (ct.convert_options(ct.CONTAINER_DSP), ct.convert_options(ct.CONTAINER_ADX, adx_has_key=1, adx_key_seed=582, adx_key_mult=17765, adx_key_inc=28959, adx_encryption_type=8),
+                    ct.convert_options(ct.CONTAINER_HCA, hca_quality=2, hca_key_type=56, hca_key_code=12345)):
+            outs, status = ct.convert_wave_batch([f.numpy() for f in files], opt)
+            print(opt.out_type, sum(o.size for o in outs), set(status))
+        return 0
     if what == "c2":
         n_ch = 1024
         pcm = bench.make_batch_gpu(torch, n_ch, n, 0, dev)

@@ -15,8 +15,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -68,7 +70,7 @@ struct WaveItem {            // one WAVE data chunk -> channel rows
     int64_t out_stride;      // samples between channel rows (multiple of 8)
     int32_t channels, samples, bits, tile_samples;
     int32_t tile_first;      // first tile of this item (exclusive prefix sum)
-    int32_t pad;
+    int32_t lead;            // zero samples written in front of every row (an encoder's alignment padding made physical)
 };
 
 struct DspChan {
@@ -133,6 +135,16 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const uint8_t *__restri
     const int ns = min(w.tile_samples, w.samples - s0);
     if (ns <= 0) return;
     const int ch = w.channels;
+    if (s0 == 0 && w.lead > 0)                                  // the first tile also lays down the leading zeros of every row
+        for (int t = threadIdx.x; t < w.lead * ch; t += blockDim.x) pcm[w.out_off + (int64_t)(t / w.lead) * w.out_stride + t % w.lead] = 0;
+    if (ch == 1 && w.bits == 16 && (w.lead & 7) == 0) {         // mono: the data chunk IS the row
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + w.in_off + (int64_t)s0 * 2);
+        int16_t *row = pcm + w.out_off + w.lead + s0;
+        const int n_vec = ns >> 3;
+        for (int v = threadIdx.x; v < n_vec; v += blockDim.x) reinterpret_cast<uint4 *>(row)[v] = src[v];
+        for (int e = (n_vec << 3) + threadIdx.x; e < ns; e += blockDim.x) row[e] = reinterpret_cast<const int16_t *>(src)[e];
+        return;
+    }
     const int n_el = ns * ch;                                   // interleaved elements of this tile
     if (w.bits == 16) {
         const uint8_t *src = in + w.in_off + (int64_t)s0 * ch * 2;   // 16-byte aligned: tile_samples is a multiple of 8
@@ -146,14 +158,20 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const uint8_t *__restri
         for (int e = threadIdx.x; e < n_el; e += blockDim.x) tile[e] = (int16_t)((src[e] - 0x80) << 8);
     }
     __syncthreads();
-    // rows out: pairs of samples per thread (rows start on 16-byte boundaries, s0 is even)
+    // rows out: pairs of samples per thread (rows start on 16-byte boundaries, s0 is even; an odd lead breaks the pairing)
     const int pairs = (ns + 1) >> 1;
+    const bool paired = (w.lead & 1) == 0;
     for (int t = threadIdx.x; t < pairs * ch; t += blockDim.x) {
         const int o = t / pairs, i = (t - o * pairs) * 2;
-        int16_t *row = pcm + w.out_off + (int64_t)o * w.out_stride + s0;
+        int16_t *row = pcm + w.out_off + (int64_t)o * w.out_stride + w.lead + s0;
         const uint32_t a = (uint16_t)tile[i * ch + o];
-        if (i + 1 < ns) *reinterpret_cast<uint32_t *>(row + i) = a | ((uint32_t)(uint16_t)tile[(i + 1) * ch + o] << 16);
-        else row[i] = (int16_t)a;
+        if (i + 1 < ns) {
+            const uint32_t b = (uint16_t)tile[(i + 1) * ch + o];
+            if (paired) *reinterpret_cast<uint32_t *>(row + i) = a | (b << 16);
+            else { row[i] = (int16_t)a; row[i + 1] = (int16_t)b; }
+        } else {
+            row[i] = (int16_t)a;
+        }
     }
 }
 
@@ -206,24 +224,25 @@ __global__ void __launch_bounds__(256) dsp_assemble_kernel(const DspFile *__rest
     }
     const int ch = f.channels;
     uint8_t *data = dst + 0x60 * ch;
-    const int64_t region = (int64_t)f.data_size * ch;
-    const int64_t q0 = (int64_t)(tile - 1) * kTileBytes;
+    // a file is below 2 GiB (FileSize is an int in the reference): 32-bit positions, unsigned so the divisions are cheap
+    const uint32_t region = (uint32_t)f.data_size * (uint32_t)ch;
+    const uint32_t q0 = (uint32_t)(tile - 1) * kTileBytes;
     const int in_blocks = div_round_up(f.in_size, f.bpi), out_blocks = div_round_up(f.data_size, f.bpi);
     const int last_in = f.in_size - (in_blocks - 1) * f.bpi, last_out = f.data_size - (out_blocks - 1) * f.bpi;
     const int copy_blocks = min(in_blocks, out_blocks);
-    const int64_t block_span = (int64_t)f.bpi * ch;
+    const uint32_t block_span = (uint32_t)f.bpi * (uint32_t)ch;
     for (int w = threadIdx.x; w < kTileBytes / 8; w += blockDim.x) {
-        const int64_t q = q0 + (int64_t)w * 8;
+        const uint32_t q = q0 + (uint32_t)w * 8;
         if (q >= region) break;
         int b = (int)(q / block_span);
         if (b > out_blocks - 1) b = out_blocks - 1;
         const int cur_out = b == out_blocks - 1 ? last_out : f.bpi;
-        const int r = (int)(q - (int64_t)b * block_span);
+        const int r = (int)(q - (uint32_t)b * block_span);
         const int i = r / cur_out, k = r - i * cur_out;
         const int cur_in = b == in_blocks - 1 ? last_in : f.bpi;
         const int n = b < copy_blocks ? min(cur_in, cur_out) : 0;
         // fast path: the eight bytes sit in one channel's run and inside the region
-        if (k + 8 <= cur_out && q + 8 <= region) {
+        if (k + 8 <= cur_out && q + 8 <= region && i < ch) {
             uint2 v = make_uint2(0u, 0u);
             if (k < n) {
                 v = *reinterpret_cast<const uint2 *>(adpcm + chans[f.first_ch + i].adpcm_off + (int64_t)f.bpi * b + k);
@@ -348,11 +367,11 @@ __global__ void __launch_bounds__(kHcaFramesPerTile * 32) hca_assemble_kernel(co
 {
     __shared__ uint16_t crc_tab[256];
     __shared__ uint8_t sub[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 256 && sub_table; i += blockDim.x) {
         uint16_t v = (uint16_t)(i << 8);                        // Crc16 table, polynomial 0x8005 (Utilities/Crc16.cs)
         for (int k = 0; k < 8; k++) v = (uint16_t)((v & 0x8000) ? (v << 1) ^ 0x8005 : v << 1);
         crc_tab[i] = v;
-        sub[i] = sub_table ? sub_table[i] : (uint8_t)i;
+        sub[i] = sub_table[i];
     }
     __syncthreads();
     const int fi = find_item(files, n_files, (int)blockIdx.x);
@@ -363,15 +382,30 @@ __global__ void __launch_bounds__(kHcaFramesPerTile * 32) hca_assemble_kernel(co
         for (int t = threadIdx.x; t < f.header_size; t += blockDim.x) dst[t] = hdr_blob[f.hdr_off + t];
         return;
     }
+    if (!sub_table) {  // no key: the frames are one contiguous run behind the header - 16 KB of it per tile
+        const int64_t total = (int64_t)f.frame_size * f.frame_count;
+        const int64_t q0 = (int64_t)(tile - 1) * kTileBytes;
+        const int nb = (int)min((int64_t)kTileBytes, total - q0);
+        const uint8_t *s = frames + f.frames_off + q0;            // 16-byte aligned (frames_off is, q0 is)
+        uint8_t *o = dst + f.header_size + q0;
+        if (((f.out_off + f.header_size) & 15) == 0) {
+            const int n_vec = nb >> 4;
+            for (int v = threadIdx.x; v < n_vec; v += blockDim.x) reinterpret_cast<uint4 *>(o)[v] = reinterpret_cast<const uint4 *>(s)[v];
+            for (int k = (n_vec << 4) + threadIdx.x; k < nb; k += blockDim.x) o[k] = s[k];
+        } else {  // header sizes of looping files are not multiples of 16: aligned loads, byte stores
+            for (int v = threadIdx.x; v < (nb + 15) >> 4; v += blockDim.x) {
+                const uint4 x = reinterpret_cast<const uint4 *>(s)[v];
+                const uint32_t wds[4] = {x.x, x.y, x.z, x.w};
+                for (int k = 0; k < 16 && v * 16 + k < nb; k++) o[v * 16 + k] = (uint8_t)(wds[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = (tile - 1) * kHcaFramesPerTile + warp;
     if (fr >= f.frame_count) return;
     const uint8_t *s = frames + f.frames_off + (int64_t)fr * f.frame_size;
     uint8_t *o = dst + f.header_size + (int64_t)fr * f.frame_size;
-    if (!sub_table) {
-        for (int k = lane; k < f.frame_size; k += 32) o[k] = s[k];
-        return;
-    }
     const int body = f.frame_size - 2;
     const int chunk = (body + 31) / 32;
     const int lo = min(lane * chunk, body), hi = min(lo + chunk, body);
@@ -416,12 +450,20 @@ struct Slab {
     char *c() const { return static_cast<char *>(p); }
 };
 
+constexpr int kWays = 4;  // groups of the batch converter in flight: each has its own working set and kernel stream
+
 struct State {
     std::mutex mu;
     bool ready = false;
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
-    Slab in[2], out[2], pcm, enc, dec, coefs, ws, tab[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_kern[kWays] = {};
+    cudaStream_t s_k = nullptr;  // = s_kern[0]: the stream of the single-shot entry points
+    cudaEvent_t ev_in[kWays] = {}, ev_split[kWays] = {}, ev_k[kWays] = {}, ev_out[kWays] = {};
+    Slab in[kWays], out[kWays], tab[kWays], pcms[kWays], encs[kWays], decs[kWays], coefss[kWays], wss[kWays];
+    Slab &pcm = pcms[0], &enc = encs[0], &coefs = coefss[0];  // working set 0 doubles as the single-shot entry points'
+    // stage timers of the batch converter: per group 5 events (start, split done, encode done, context done, assembled)
+    static constexpr int kTimedGroups = 32, kStageEvents = 5;
+    cudaEvent_t stage[kTimedGroups][kStageEvents] = {};
+    int timed_groups = 0;
 };
 State g_st;
 
@@ -430,13 +472,16 @@ int32_t ensure_state()
     CTN_TRY(vgb::abi_ensure_ready());
     if (g_st.ready) return VGB_OK;
     CTN_CUDA(cudaStreamCreateWithFlags(&g_st.s_in, cudaStreamNonBlocking));
-    CTN_CUDA(cudaStreamCreateWithFlags(&g_st.s_k, cudaStreamNonBlocking));
     CTN_CUDA(cudaStreamCreateWithFlags(&g_st.s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kWays; i++) {
+        CTN_CUDA(cudaStreamCreateWithFlags(&g_st.s_kern[i], cudaStreamNonBlocking));
         CTN_CUDA(cudaEventCreateWithFlags(&g_st.ev_in[i], cudaEventDisableTiming));
+        CTN_CUDA(cudaEventCreateWithFlags(&g_st.ev_split[i], cudaEventDisableTiming));
         CTN_CUDA(cudaEventCreateWithFlags(&g_st.ev_k[i], cudaEventDisableTiming));
         CTN_CUDA(cudaEventCreateWithFlags(&g_st.ev_out[i], cudaEventDisableTiming));
     }
+    g_st.s_k = g_st.s_kern[0];
+    for (auto &grp : g_st.stage) for (auto &e : grp) CTN_CUDA(cudaEventCreate(&e));
     g_st.ready = true;
     return VGB_OK;
 }
@@ -446,9 +491,33 @@ struct Drain {  // no copy may be in flight on caller memory once an entry point
     {
         if (!g_st.ready) return;
         cudaStreamSynchronize(g_st.s_in);
-        cudaStreamSynchronize(g_st.s_k);
+        for (auto st : g_st.s_kern) cudaStreamSynchronize(st);
         cudaStreamSynchronize(g_st.s_out);
         (void)cudaGetLastError();
+    }
+};
+
+// Many small copies in one driver call (cudaMemcpyBatchAsync, CUDA 12.8+): a batch of thousands of files otherwise spends
+// more host time in cudaMemcpyAsync calls than the copies take on the link.  Falls back to one call per copy.
+struct CopyList {
+    std::vector<void *> dst, src;
+    std::vector<size_t> size;
+    void add(void *d, const void *s, size_t n) { if (n) { dst.push_back(d); src.push_back(const_cast<void *>(s)); size.push_back(n); } }
+    int32_t run(cudaMemcpyKind kind, cudaStream_t st)
+    {
+        const size_t n = size.size();
+        if (n == 0) return VGB_OK;
+        static bool batch_ok = std::getenv("VGB_NO_MEMCPY_BATCH") == nullptr;
+        if (batch_ok && n >= 16) {
+            cudaMemcpyAttributes attr{};
+            attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;  // sources stay valid until the entry point has drained its streams
+            size_t attr_idx = 0, fail_idx = 0;
+            if (cudaMemcpyBatchAsync(dst.data(), src.data(), size.data(), n, &attr, &attr_idx, 1, &fail_idx, st) == cudaSuccess) return VGB_OK;
+            (void)cudaGetLastError();
+            batch_ok = false;
+        }
+        for (size_t i = 0; i < n; i++) CTN_CUDA(cudaMemcpyAsync(dst[i], src[i], size[i], kind, st));
+        return VGB_OK;
     }
 };
 
@@ -548,13 +617,19 @@ void adx_build_header(const vgb_adx_desc &d, const AdxGeom &g, const int16_t *hi
 }
 
 // ---- HCA header (HcaWriter.cs:56-170) ----
-uint16_t crc16_host(const uint8_t *data, size_t n)
+uint16_t crc16_host(const uint8_t *data, size_t n)  // Crc16.Compute (Utilities/Crc16.cs:13-19), polynomial 0x8005
 {
+    static uint16_t table[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int i = 0; i < 256; i++) {
+            uint16_t v = (uint16_t)(i << 8);
+            for (int k = 0; k < 8; k++) v = (uint16_t)((v & 0x8000) ? (v << 1) ^ 0x8005 : v << 1);
+            table[i] = v;
+        }
+    });
     uint16_t crc = 0;
-    for (size_t i = 0; i < n; i++) {
-        crc ^= (uint16_t)(data[i] << 8);
-        for (int k = 0; k < 8; k++) crc = (uint16_t)((crc & 0x8000) ? (crc << 1) ^ 0x8005 : crc << 1);
-    }
+    for (size_t i = 0; i < n; i++) crc = (uint16_t)((crc << 8) ^ table[(crc >> 8) ^ data[i]]);
     return crc;
 }
 int32_t hca_build_header(const vgb_hca_info &h, bool masked, int key_type, const char *comment, uint32_t volume_bits,
@@ -654,13 +729,18 @@ void containers_release()  // vgb_shutdown
 {
     std::lock_guard<std::mutex> lock(g_st.mu);
     if (!g_st.ready) return;
-    cudaStreamSynchronize(g_st.s_in); cudaStreamSynchronize(g_st.s_k); cudaStreamSynchronize(g_st.s_out);
-    for (int i = 0; i < 2; i++) {
+    cudaStreamSynchronize(g_st.s_in);
+    for (auto st : g_st.s_kern) cudaStreamSynchronize(st);
+    cudaStreamSynchronize(g_st.s_out);
+    for (int i = 0; i < kWays; i++) {
         g_st.in[i].release(); g_st.out[i].release(); g_st.tab[i].release();
-        cudaEventDestroy(g_st.ev_in[i]); cudaEventDestroy(g_st.ev_k[i]); cudaEventDestroy(g_st.ev_out[i]);
+        g_st.pcms[i].release(); g_st.encs[i].release(); g_st.decs[i].release(); g_st.coefss[i].release(); g_st.wss[i].release();
+        cudaEventDestroy(g_st.ev_in[i]); cudaEventDestroy(g_st.ev_split[i]); cudaEventDestroy(g_st.ev_k[i]); cudaEventDestroy(g_st.ev_out[i]);
+        cudaStreamDestroy(g_st.s_kern[i]);
     }
-    g_st.pcm.release(); g_st.enc.release(); g_st.dec.release(); g_st.coefs.release(); g_st.ws.release();
-    cudaStreamDestroy(g_st.s_in); cudaStreamDestroy(g_st.s_k); cudaStreamDestroy(g_st.s_out);
+    cudaStreamDestroy(g_st.s_in); cudaStreamDestroy(g_st.s_out);
+    for (auto &grp : g_st.stage) for (auto &e : grp) { if (e) cudaEventDestroy(e); e = nullptr; }
+    g_st.timed_groups = 0;
     g_st.ready = false;
     (void)cudaGetLastError();
 }
