@@ -19,6 +19,8 @@
 //                           coefficient.  Records are compacted per bucket (ballot + popc) so each lane's DADD chain
 //                           only contains its own bucket's records.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace vgb {
@@ -240,54 +242,65 @@ __device__ __forceinline__ int16_t gc_quantise_coef(double v)
 //              from a ballot: record order is preserved inside a bucket);
 //   warp 0     (consumer) meanwhile walks the PREVIOUS chunk's blocks in order and lane (bucket, component) adds ONLY
 //              its bucket's records, in record order - exactly the reference's sequence of additions.
-constexpr int kRefineWarps = 4;                    // 1 consumer + 3 producers
-constexpr int kRefineProducers = kRefineWarps - 1;
+// W warps per CTA = 1 consumer + (W - 1) producers.  W = 4 keeps seven CTAs per SM, which holds all 1024 channels of the
+// headline batch at once; W = 8 (7 producers, 61 KB of queues) is kept for experiments with small batches
+// (VGB_REFINE_WIDE_LIMIT).
 
 struct __align__(16) RefineSlot {
-    double2 q[8][33];     // per-bucket queues of one block of 32 records; 33: the 16 accumulator lanes (bucket, comp)
-                          // read entry j of all buckets at once, 528-byte rows put them in 16 distinct bank pairs
+    double2 q[8 * 33];    // per-bucket queues of one block of 32 records, bucket b at q + b * refine_row(NB): 33 entries per
+                          // row with 8 buckets (the 16 accumulator lanes (bucket, comp) read entry j of all buckets at once,
+                          // 528-byte rows put them in 16 distinct bank pairs), 66 / 132 / 264 with 4 / 2 / 1 buckets - room
+                          // for the longer padding the consumer's wider steps need when few buckets share the block
     int32_t count[8];     // records per bucket (buckets the pass does not use stay 0)
 };
+// queue row length and consumer step (entries added per loop iteration; queues are padded to a multiple of it with -0.0)
+__host__ __device__ constexpr int refine_row(int nb) { return nb >= 8 ? 33 : (nb == 4 ? 66 : (nb == 2 ? 132 : 264)); }
+__host__ __device__ constexpr int refine_step(int nb) { return nb >= 4 ? 4 : (nb == 2 ? 8 : 16); }
 
+template <int W>
 struct RefineShared {
-    RefineSlot slot[2][kRefineProducers];  // double-buffered chunks
+    RefineSlot slot[2][W - 1];             // double-buffered chunks
     double cent[8][3];                      // centroids (1, c1, c2)
     double econst[8][3];                    // per-centroid constants of ContrastVectors (:338-340), refreshed every pass
 };
 
 // all kRefineWarps warps, once per chunk; PTX named barrier so that the two code paths may use different instructions
-__device__ __forceinline__ void refine_chunk_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kRefineWarps * 32) : "memory"); }
+template <int W>
+__device__ __forceinline__ void refine_chunk_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory"); }
 
 // consumer side of one pass: ordered accumulation (:382-386 / :67-72).  Lane (bucket*2 + comp) walks its bucket's queue
 // of every block in block order - a pure DADD chain over exactly the bucket's records, in record order.
 struct RefineSum { double acc; int hits; };
-__device__ __forceinline__ RefineSum gc_refine_consume(int lane, int n_blocks, int n_chunks, RefineShared &sh)
+template <int NB, int W>
+__device__ __forceinline__ RefineSum gc_refine_consume(int lane, int n_blocks, int n_chunks, RefineShared<W> &sh)
 {
-    constexpr int P = kRefineProducers;
+    constexpr int P = W - 1;
+    constexpr int STEP = refine_step(NB), ROW = refine_row(NB);
     const int my_bucket = (lane >> 1) & 7, my_comp = lane & 1;
     double a = 0.0;
     int h = 0;
-    refine_chunk_barrier();  // chunk 0 classified
+    refine_chunk_barrier<W>();  // chunk 0 classified
     for (int c = 1; c <= n_chunks; c++) {
         const int first = (c - 1) * P;
         for (int j = 0; j < P && first + j < n_blocks; j++) {
             const RefineSlot &slot = sh.slot[(c - 1) & 1][j];
-            const int n_mine = lane < 16 ? slot.count[my_bucket] : 0;
-            const double *col = reinterpret_cast<const double *>(slot.q[my_bucket]) + my_comp;
-            // four queue entries per step (the producers pad every queue to a multiple of four with -0.0, the additive
-            // identity): loads issued together, then the bare DADD chain.  The trip count differs per lane; lanes whose
-            // bucket is done simply drop out (no selects on the chain, 11 instructions per four records).
-            const int n_pad = (n_mine + 3) & ~3;
-            for (int j0 = 0; j0 < n_pad; j0 += 4) {
-                double v[4];
+            const int n_mine = (lane < 16 && my_bucket < NB) ? slot.count[my_bucket] : 0;
+            const double *col = reinterpret_cast<const double *>(slot.q + (my_bucket < NB ? my_bucket : 0) * ROW) + my_comp;
+            // STEP queue entries per iteration (the producers pad every queue to a multiple of STEP with -0.0, the additive
+            // identity): loads issued together, then the bare DADD chain - the shared-memory latency and the loop overhead are
+            // paid once per STEP records, so the passes with one or two long queues (STEP 16 / 8) run close to the 8.3 cycles
+            // a dependent add costs.  The trip count differs per lane; lanes whose bucket is done simply drop out.
+            const int n_pad = (n_mine + STEP - 1) / STEP * STEP;
+            for (int j0 = 0; j0 < n_pad; j0 += STEP) {
+                double v[STEP];
 #pragma unroll
-                for (int i = 0; i < 4; i++) v[i] = col[2 * (j0 + i)];
+                for (int i = 0; i < STEP; i++) v[i] = col[2 * (j0 + i)];
 #pragma unroll
-                for (int i = 0; i < 4; i++) a += v[i];
+                for (int i = 0; i < STEP; i++) a += v[i];
             }
             h += n_mine;
         }
-        refine_chunk_barrier();
+        refine_chunk_barrier<W>();
     }
     return RefineSum{a, h};
 }
@@ -296,12 +309,13 @@ __device__ __forceinline__ RefineSum gc_refine_consume(int lane, int n_blocks, i
 // record goes to bucket 0), executed by the whole CTA.  On return, in warp 0, lane (bucket*2 + comp) with
 // bucket < max(COUNT,1) holds the ordered sum of that component over the bucket's records in `acc` and the record
 // count in `hits`.
-template <int COUNT>
+template <int COUNT, int W>
 __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames, int n_blocks, const double2 *__restrict__ rec,
-                                               const uint32_t *__restrict__ mask, RefineShared &sh, double &acc, int &hits)
+                                               const uint32_t *__restrict__ mask, RefineShared<W> &sh, double &acc, int &hits)
 {
     constexpr int NB = COUNT > 0 ? COUNT : 1;
-    constexpr int P = kRefineProducers;
+    constexpr int P = W - 1;
+    constexpr int STEP = refine_step(NB), ROW = refine_row(NB);
     const uint32_t lanes_below = (1u << lane) - 1u;
     const int p = warp - 1;                              // producer index (warp 0: unused)
     const int n_chunks = (n_blocks + P - 1) / P;
@@ -352,14 +366,14 @@ __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames,
         if (ok) {
             const int rank = __popc(mine & lanes_below);
             if (rank == 0) slot.count[pick] = __popc(mine);  // the group's first lane publishes its size
-            slot.q[pick][rank] = r;
+            slot.q[pick * ROW + rank] = r;
         }
         __syncwarp();
-        {   // pad every queue to a multiple of four entries with -0.0 (lane = bucket * 4 + i)
-            const int bucket = lane >> 2, i = lane & 3;
+        {   // pad every queue to a multiple of STEP entries with -0.0 (lane = bucket * STEP + i; NB * STEP <= 32)
+            const int bucket = lane / STEP, i = lane % STEP;
             if (bucket < NB) {
                 const int c = slot.count[bucket];
-                if (i < ((4 - (c & 3)) & 3)) slot.q[bucket][c + i] = make_double2(-0.0, -0.0);
+                if (i < ((STEP - (c % STEP)) % STEP)) slot.q[bucket * ROW + c + i] = make_double2(-0.0, -0.0);
             }
         }
     };
@@ -376,7 +390,7 @@ __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames,
     if (warp == 0) {
         // consumer: deliberately small, rolled code (it is the critical path and must stay in the instruction cache
         // next to the producers' large unrolled loop); inlined so that `sh` stays a shared-window address
-        const RefineSum sum = gc_refine_consume(lane, n_blocks, n_chunks, sh);
+        const RefineSum sum = gc_refine_consume<NB, W>(lane, n_blocks, n_chunks, sh);
         acc = sum.acc;
         hits = sum.hits;
         return;
@@ -389,16 +403,19 @@ __device__ __forceinline__ void gc_refine_pass(int warp, int lane, int n_frames,
             const int b = c * P + p;
             if (b < n_blocks) stage(b, ring_r[k], ring_ok[k], sh.slot[c & 1][p]);
             fetch(b + kDepth * P, ring_r[k], ring_ok[k]);
-            refine_chunk_barrier();  // chunk c is classified, chunk c-1 is summed: the two buffers swap roles
+            refine_chunk_barrier<W>();  // chunk c is classified, chunk c-1 is summed: the two buffers swap roles
         }
     }
 }
 
-__global__ void __launch_bounds__(kRefineWarps * 32, 7)  // 7 CTAs per SM: 1024 channels are resident at once
+template <int W>
+__global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 3)  // W = 4: 7 CTAs per SM, 1024 channels are resident at once
 gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, const uint32_t *__restrict__ accept_mask,
                       int16_t *__restrict__ coefs_out)
 {
-    __shared__ RefineShared sh;
+    extern __shared__ __align__(16) unsigned char refine_smem[];
+    RefineShared<W> &sh = *reinterpret_cast<RefineShared<W> *>(refine_smem);
+    constexpr int kRefineProducers = W - 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = blockIdx.x;
@@ -437,10 +454,10 @@ gc_coef_refine_kernel(GcChannelTable tab, const double2 *__restrict__ records, c
         __syncthreads();
         double acc;
         int hits;
-        if (pass == 0) gc_refine_pass<0>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
-        else if (count == 2) gc_refine_pass<2>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
-        else if (count == 4) gc_refine_pass<4>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
-        else gc_refine_pass<8>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        if (pass == 0) gc_refine_pass<0, W>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else if (count == 2) gc_refine_pass<2, W>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else if (count == 4) gc_refine_pass<4, W>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
+        else gc_refine_pass<8, W>(warp, lane, n_frames, n_blocks, rec, mask, sh, acc, hits);
 
         if (warp == 0) {
             // divide (:73-74 / :388-391) and rebuild the centroids (:76 / :393-394)
@@ -484,7 +501,17 @@ void launch_gc_coef_refine(const GcChannelTable &tab, const double2 *records, co
                            int16_t *coefs_out, cudaStream_t stream)
 {
     if (tab.n_channels <= 0) return;
-    gc_coef_refine_kernel<<<tab.n_channels, kRefineWarps * 32, 0, stream>>>(tab, records, mask, coefs_out);
+    static int wide_limit = -1;  // batches up to this many channels take the 8-warp CTA (0: never - it measured no faster)
+    if (wide_limit < 0) {
+        wide_limit = 0;
+        if (const char *env = std::getenv("VGB_REFINE_WIDE_LIMIT")) wide_limit = std::atoi(env);  // tuning knob
+        cudaFuncSetAttribute(gc_coef_refine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefineShared<8>));
+        cudaFuncSetAttribute(gc_coef_refine_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefineShared<4>));
+    }
+    if (tab.n_channels <= wide_limit)
+        gc_coef_refine_kernel<8><<<tab.n_channels, 8 * 32, sizeof(RefineShared<8>), stream>>>(tab, records, mask, coefs_out);
+    else
+        gc_coef_refine_kernel<4><<<tab.n_channels, 4 * 32, sizeof(RefineShared<4>), stream>>>(tab, records, mask, coefs_out);
 }
 
 }  // namespace vgb
