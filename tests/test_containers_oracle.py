@@ -222,3 +222,55 @@ def test_adx_and_hca_file_geometry_matches_oracle(oracle, vg):
     fk = oracle.hca_write(info, frames, enc, 56, comment="hi", volume=0.5)
     assert bytes(fk[:4]) == bytes([0xC8, 0xC3, 0xC1, 0]) and oracle.crc16(bytes(fk[:info.header_size])) == 0
     assert b"\xe3\xef\xed\xed\x00hi\x00" in bytes(fk[:info.header_size])     # masked "comm\0" + UTF8Z comment
+
+
+def test_parsers_agree_on_mutated_and_truncated_files(oracle, vg):
+    """Differential fuzz of the two host parsers (product C++ vs oracle C) on WAVE and DSP images with random header bytes
+    and random truncation: same accept / reject decision, same fields when accepted, and no out-of-bounds read (the
+    images are exact-size numpy buffers; the oracle build under ASan is the memory check)."""
+    from vgaudio_b200 import _native as N
+
+    rng = np.random.default_rng(20260924)
+    waves = [oracle.wave_write16(_sine_channels(ch, 300), 32000, loop) for ch, loop in ((1, None), (2, (3, 250)), (3, None), (8, (0, 300)))]
+    waves.append(_wave8([np.arange(100) % 256, np.arange(100) % 256])[0])
+    n_ok = 0
+    for case in range(3000):
+        img = waves[case % len(waves)].copy()
+        head = min(img.size, 140)
+        for _ in range(int(rng.integers(1, 4))):
+            img[int(rng.integers(0, head))] = int(rng.integers(0, 256))
+        if rng.random() < 0.3:
+            img = img[: int(rng.integers(0, img.size + 1))].copy()
+        st, info = oracle.wave_parse(img)
+        pinfo = N.VgbWaveInfo()
+        pst = vg.lib.vgb_wave_parse(img.ctypes.data if img.size else None, img.size, C.byref(pinfo))
+        assert (st == 0) == (pst == 0), (case, st, pst, vg.lib.vgb_last_error())
+        if st == 0:
+            n_ok += 1
+            for f, _ in N.VgbWaveInfo._fields_:
+                assert getattr(pinfo, f) == getattr(info, f), (case, f)
+    assert 300 < n_ok < 2900   # the mutations produce both outcomes
+
+    pcm = _sine_channels(2, 3000)
+    coefs = np.stack([oracle.calculate_coefficients(p) for p in pcm])
+    adpcm = [oracle.encode(p, c) for p, c in zip(pcm, coefs)]
+    dsps = [oracle.dsp_write(adpcm, coefs, 32000, 3000), oracle.dsp_write(adpcm[:1], coefs[:1], 32000, 3000, (14, 2800), np.zeros((1, 3), np.int16))]
+    n_ok = 0
+    for case in range(2000):
+        img = dsps[case % 2].copy()
+        for _ in range(int(rng.integers(1, 3))):
+            img[int(rng.integers(0, 0xC0))] = int(rng.integers(0, 256))
+        if rng.random() < 0.3:
+            img = img[: int(rng.integers(0, img.size + 1))].copy()
+        st, info = oracle.dsp_parse(img)
+        pinfo = N.VgbDspInfo()
+        pst = vg.lib.vgb_dsp_parse(img.ctypes.data if img.size else None, img.size, C.byref(pinfo)) if img.size else -2
+        if img.size == 0:
+            assert st != 0
+            continue
+        assert (st == 0) == (pst == 0), (case, st, pst, vg.lib.vgb_last_error())
+        if st == 0:
+            n_ok += 1
+            for name in ("sample_count", "nibble_count", "sample_rate", "looping", "channel_count", "frames_per_interleave", "loop_start", "loop_end"):
+                assert getattr(pinfo, name) == getattr(info, name), (case, name)
+    assert n_ok > 100

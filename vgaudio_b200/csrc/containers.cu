@@ -529,11 +529,7 @@ int rd_be16s(const uint8_t *p) { return (int16_t)((p[0] << 8) | p[1]); }
 int32_t rd_be32(const uint8_t *p) { return (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]); }
 
 int gc_sample_to_nibble(int s) { return s / 14 * 16 + s % 14 + 2; }              // GcAdpcmMath.cs:38-44
-int gc_nibble_to_sample(int nib)                                                  // GcAdpcmMath.cs:28-36
-{
-    const int frames = nib / 16, extra = nib % 16;
-    return 14 * frames + (extra < 2 ? 0 : extra - 2);
-}
+int gc_nibble_to_sample(int nib) { return 14 * (nib / 16) + nib % 16 - 2; }       // GcAdpcmMath.cs:29-36 (no clamp: header nibbles 0, 1 give -2, -1)
 
 // ---- DSP geometry (DspWriter.cs:17-36, :105-106) ----
 struct DspGeom { int align, loop_start, loop_end, sample_count, data_size, bpi, in_size; };
