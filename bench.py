@@ -178,7 +178,12 @@ def cpu_baseline(pcm_host: np.ndarray, target_seconds: float):
     coefs, adpcm, used = pyoracle.encode_batch(pcm_host[:want], 0)
     dt = time.perf_counter() - t0
     value = want * n / dt / 1e6
-    return {"value": round(value, 3), "unit": "Msamples/s", "cores": used, "kind": "port",
+    # one channel on one thread, so the reader can see how far the box's `cores` threads really scale
+    t0 = time.perf_counter()
+    pyoracle.encode_batch(pcm_host[4:5] if n_ch > 4 else pcm_host[:1], 1)
+    one = n / (time.perf_counter() - t0) / 1e6
+    return {"value": round(value, 3), "unit": "Msamples/s", "cores": used, "kind": "port", "one_thread_msamples_s": round(one, 3),
+            "parallel_speedup": round(value / one, 1) if one > 0 else None,
             "sample": f"{want} of {n_ch} channels x {n} samples ({dt:.1f} s wall), C restatement of the reference "
                       f"(oracle/gcadpcm.c) one task per channel; the C#/.NET reference cannot run in this image"}, coefs, adpcm, want
 
