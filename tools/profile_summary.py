@@ -30,8 +30,10 @@ def launches(path, out_md, command):
     other = 0.0
     for name, ms, grid in rows:
         head = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").split("(")[0]
-        if "vgb::" in head or head.startswith(("gc_", "adx_", "hca_")):
-            short = head.split("vgb::")[1].split("<")[0] if "vgb::" in head else head.split("<")[0]
+        if head.startswith("void "):  # templated kernels are printed with their return type
+            head = head[5:]
+        if "vgb::" in head or head.startswith(("gc_", "adx_", "hca_", "wave_", "dsp_", "interleave", "deinterleave")):
+            short = head.split("vgb::")[1] if "vgb::" in head else head  # keep the template argument: <0> chain, <1> run-on, <2> cascade
             ours.setdefault((short, grid), []).append(ms)
         else:
             other += ms
