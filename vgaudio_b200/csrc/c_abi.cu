@@ -253,7 +253,7 @@ GcSegArgs seg_view(void *ws, const GcWorkspace &w, int32_t seg_count)
     a.used_start = reinterpret_cast<uint32_t *>(b + w.off_used_start);
     a.stats = reinterpret_cast<unsigned long long *>(b + w.off_stats);
     a.seg_count = seg_count;
-    a.min_seg_frames = kGcMinSegFrames;  // launch_gc_encode sets the effective value
+    a.min_seg_frames = 0;  // the caller stores gc_encode_pick_segments' choice; 0 lets launch_gc_encode take the default
     return a;
 }
 
@@ -364,7 +364,10 @@ int32_t run_gc_encode(const int16_t *d_pcm, const GcLayout &lay, const int16_t *
     if (after_coefs) CUDA_TRY(cudaEventRecord(after_coefs, stream));
     if (do_encode) {
         const int enc_frames = max_encode_frames(lay);
-        const GcSegArgs seg = seg_view(d_ws, w, gc_encode_pick_segments(lay.n_channels, enc_frames));
+        int min_seg = 0;
+        const int seg_count = gc_encode_pick_segments(lay.n_channels, enc_frames, &min_seg);
+        GcSegArgs seg = seg_view(d_ws, w, seg_count);
+        seg.min_seg_frames = min_seg;
         tick(2, true, stream);
         launch_gc_encode(d_pcm, tab, d_coefs_out, d_adpcm, lay.max_frames, 0, INT_MAX, seg, stream);
         tick(2, false, stream);
@@ -1498,8 +1501,9 @@ AdxSegArgs adx_seg_carve(std::vector<AdxChannel> &tab, int first, int n, char *b
     a.trace = reinterpret_cast<uint32_t *>(base);
     a.used_start = reinterpret_cast<uint32_t *>(base + o_used);
     a.stats = reinterpret_cast<unsigned long long *>(base + o_stats);
-    a.seg_count = adx_encode_pick_segments(n, max_whole);
-    a.min_seg_frames = kAdxMinSegFrames;
+    int min_seg = 0;
+    a.seg_count = adx_encode_pick_segments(n, max_whole, &min_seg);
+    a.min_seg_frames = min_seg;
     return a;
 }
 

@@ -763,10 +763,10 @@ int gc_encode_min_segment_frames()
 // the last, partly filled wave is the only loss - and (b) segments longer than the run-on tail (above).  Measured on C2
 // (512 item rows): 75.5 ms with one segment, 48 ms with 3, 39.0 with 17, 38.7 with 24, 38.8 with 34, 45 with 48
 // (profiles/r02_seg_sweep.md; the last two already lose boundaries to the cascade).
-int gc_encode_pick_segments(int n_channels, int max_frames)
+int gc_encode_pick_segments(int n_channels, int max_frames, int *min_seg_out)
 {
-    const int min_seg = gc_encode_min_segment_frames();
-    const int max_s = std::min(kGcMaxSegments, std::max(1, max_frames / min_seg));
+    int min_seg = gc_encode_min_segment_frames();
+    if (min_seg_out) *min_seg_out = min_seg;
     if (const char *env = std::getenv("VGB_GC_SEGMENTS")) {
         const int v = std::atoi(env);
         if (v >= 1) return v > kGcMaxSegments ? kGcMaxSegments : v;
@@ -784,6 +784,14 @@ int gc_encode_pick_segments(int n_channels, int max_frames)
     }
     const int rows = (n_channels + 1) / 2;
     const int want = (int)((5ll * slots + rows - 1) / rows);  // about five waves of items
+    // A batch of SHORT channels too small to fill the machine with kGcMinSegFrames-long segments is latency bound (a
+    // segment's serial chain): halve the minimum when a channel yields fewer than eight segments.  More boundaries then end
+    // in the cascade, but a few serial repairs cost less than chains twice as long (batch converter, 2048 files of 1-6 s:
+    // encode stage 56 -> 44 ms).  Long channels keep the full minimum: with 2048-frame segments the 128-channel groups of the
+    // pipelined host call lost more to the cascade's serial repairs than they gained (C2 end to end 75 -> 80 ms).
+    if (!std::getenv("VGB_GC_MIN_SEG_FRAMES") && max_frames / min_seg < std::min(want, 8)) min_seg = std::max(kEncChunkFrames, min_seg / 2);
+    if (min_seg_out) *min_seg_out = min_seg;
+    const int max_s = std::min(kGcMaxSegments, std::max(1, max_frames / min_seg));
     return std::max(1, std::min(want, max_s));
 }
 
@@ -796,7 +804,7 @@ void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16
     const int blocks = (tab.n_channels + per_block - 1) / per_block;
     if (sa.seg_count < 1) sa.seg_count = 1;
     if (sa.seg_count > kGcMaxSegments) sa.seg_count = kGcMaxSegments;
-    sa.min_seg_frames = gc_encode_min_segment_frames();
+    if (sa.min_seg_frames <= 0) sa.min_seg_frames = gc_encode_min_segment_frames();  // else: chosen by gc_encode_pick_segments
     cudaMemsetAsync(sa.stats, 0, kGcStatWords * sizeof(unsigned long long), stream);
     gc_encode_kernel<kGcChain><<<dim3(blocks, sa.seg_count), kEncWarps * 32, 0, stream>>>(pcm, tab, coefs, adpcm, frame_begin, frame_end, sa);
     if (sa.seg_count > 1) {

@@ -15,7 +15,7 @@ void launch_gc_coef_refine(const GcChannelTable &tab, const double2 *records, co
                            int16_t *coefs_out, cudaStream_t stream);
 
 // gc_encode.cu — GcAdpcmEncoder.Encode / DspEncodeFrame / DspEncodeCoef (Codecs/GcAdpcm/GcAdpcmEncoder.cs:14-171)
-int gc_encode_pick_segments(int n_channels, int max_frames);  // segments per channel for the time-parallel encode
+int gc_encode_pick_segments(int n_channels, int max_frames, int *min_seg_out = nullptr);  // segments per channel (and the shortest segment) for the time-parallel encode
 void launch_gc_encode(const int16_t *pcm, const GcChannelTable &tab, const int16_t *coefs, uint8_t *adpcm,
                       int max_frames, int frame_begin, int frame_end, GcSegArgs seg, cudaStream_t stream);
 void launch_gc_encode_frames(int16_t *pcm_in_out, const int32_t *sample_count, const int16_t *coefs, int n_frames,
@@ -30,7 +30,7 @@ void launch_gc_taps(const uint8_t *adpcm, const GcChannelTable &tab, const int16
                     int16_t *tap_slab, int max_frames, cudaStream_t stream);
 
 // adx.cu — CriAdxCodec.Encode / Decode (Codecs/CriAdx/CriAdxCodec.cs:9-171)
-int adx_encode_pick_segments(int n_channels, int max_whole_frames);
+int adx_encode_pick_segments(int n_channels, int max_whole_frames, int *min_seg_out = nullptr);
 void launch_adx_encode(const int16_t *pcm, const AdxChannel *tab, int n_channels, uint8_t *adpcm, int16_t *history_out,
                        AdxSegArgs seg, cudaStream_t stream);  // seg.trace == nullptr: one segment (plain serial encode)
 void launch_adx_decode(const uint8_t *adpcm, const AdxChannel *tab, int n_channels, int16_t *pcm, int32_t *status,
