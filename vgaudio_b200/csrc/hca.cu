@@ -145,39 +145,45 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
         chs[tid].coded_count = cfg.channel_type[tid] == 2 ? cfg.base_band_count : cfg.base_band_count + cfg.stereo_band_count;
     }
 
-    // ---- PcmToFloat (:845-858) + RunMdct (:834-843, Mdct.cs:63-92): two subframes at a time
-    const int grp = tid >> 6, i = tid & 63;
-    double *t = work + grp * kBins;
-    double *in = fold + grp * kBins;
-    for (int c = 0; c < nch; c++) {
-        const int16_t *src = pcm + st.pcm_off + (int64_t)c * st.channel_stride;
-        for (int sf2 = 0; sf2 < kSub; sf2 += 2) {
-            const int sf = sf2 + grp;
-            const int64_t base = (int64_t)k * kFrame + sf * kBins;  // first sample of this subframe
-            auto sample = [&](int64_t idx) -> double { return (double)hca_virtual_sample(src, st, idx) * (1.0 / 32768.0); };
-            {   // window + fold into the DCT input (Mdct.cs:77-85); `previous` = the 128 samples before this subframe
-                const double a = T.window[64 - i - 1] * -sample(base + 64 + i);
-                const double b = T.window[64 + i] * sample(base + 64 - i - 1);
-                const double cc = T.window[i] * sample(base - kBins + i);
-                const double d = T.window[kBins - i - 1] * sample(base - kBins + kBins - i - 1);
-                in[i] = a - b;
-                in[64 + i] = cc - d;
-            }
-            __syncthreads();
-            {   // Dct4 pre-twiddle (Mdct.cs:137-147)
-                const int i2 = i * 2;
-                const double a = in[i2], b = in[kBins - 1 - i2];
-                const double sn = T.sin_tab[7][i], cs = T.cos_tab[7][i];
-                t[i2] = a * cs + b * sn;
-                t[i2 + 1] = a * sn - b * cs;
-            }
-            __syncthreads();
+    // ---- PcmToFloat (:845-858) + RunMdct (:834-843, Mdct.cs:63-92): FOUR subframes at a time, one WARP per subframe.  A
+    // 128-point DCT-IV stage has exactly 32 butterflies, so a warp owns a whole transform and every step inside it is
+    // separated by __syncwarp instead of a CTA barrier (the first version ran two subframes on 64 threads each, half of
+    // them idle in the butterfly stages, with nine CTA barriers per pair).  Scratch: the `scaled` array, not yet in use.
+    {
+        const int wsub = tid >> 5, ln = tid & 31;
+        double *t = scaled + wsub * kBins;
+        double *in = scaled + (4 + wsub) * kBins;
+        for (int c = 0; c < nch; c++) {
+            const int16_t *src = pcm + st.pcm_off + (int64_t)c * st.channel_stride;
+            for (int sf4 = 0; sf4 < kSub; sf4 += 4) {
+                const int sf = sf4 + wsub;
+                const int64_t base = (int64_t)k * kFrame + sf * kBins;  // first sample of this subframe
+                auto sample = [&](int64_t idx) -> double { return (double)hca_virtual_sample(src, st, idx) * (1.0 / 32768.0); };
+#pragma unroll
+                for (int h = 0; h < 2; h++) {  // window + fold into the DCT input (Mdct.cs:77-85); `previous` = the 128 samples before this subframe
+                    const int i = ln + 32 * h;
+                    const double a = T.window[64 - i - 1] * -sample(base + 64 + i);
+                    const double b = T.window[64 + i] * sample(base + 64 - i - 1);
+                    const double cc = T.window[i] * sample(base - kBins + i);
+                    const double d = T.window[kBins - i - 1] * sample(base - kBins + kBins - i - 1);
+                    in[i] = a - b;
+                    in[64 + i] = cc - d;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {  // Dct4 pre-twiddle (Mdct.cs:137-147)
+                    const int i = ln + 32 * h, i2 = i * 2;
+                    const double a = in[i2], b = in[kBins - 1 - i2];
+                    const double sn = T.sin_tab[7][i], cs = T.cos_tab[7][i];
+                    t[i2] = a * cs + b * sn;
+                    t[i2 + 1] = a * sn - b * cs;
+                }
+                __syncwarp();
 #pragma unroll 1
-            for (int stage = 0; stage < 6; stage++) {  // (Mdct.cs:148-175)
-                const int block_bits = 6 - stage, half_bits = block_bits - 1;
-                const int block_size = 1 << block_bits, block_half = 1 << half_bits;
-                if (i < 32) {  // a 128-point stage has 32 butterflies of two complex pairs each
-                    const int block = i >> half_bits, j = i & (block_half - 1);
+                for (int stage = 0; stage < 6; stage++) {  // (Mdct.cs:148-175): 32 butterflies of two complex pairs each
+                    const int block_bits = 6 - stage, half_bits = block_bits - 1;
+                    const int block_size = 1 << block_bits, block_half = 1 << half_bits;
+                    const int block = ln >> half_bits, j = ln & (block_half - 1);
                     const int front = (block * block_size + j) * 2, back = front + block_size;
                     const double a = t[front] - t[back];
                     const double b = t[front + 1] - t[back + 1];
@@ -187,14 +193,15 @@ hca_encode_kernel(const int16_t *__restrict__ pcm, const HcaStream *__restrict__
                     t[front + 1] = f1;
                     t[back] = a * cs + b * sn;
                     t[back + 1] = a * sn - b * cs;
+                    __syncwarp();
                 }
-                __syncthreads();
+                double *out = spectra + ((size_t)c * kSub + sf) * kBins;
+#pragma unroll
+                for (int h = 0; h < 4; h++) out[ln + 32 * h] = t[T.shuffle[ln + 32 * h]] * T.mdct_scale;  // (Mdct.cs:177-180)
+                __syncwarp();
             }
-            double *out = spectra + ((size_t)c * kSub + sf) * kBins;
-            out[i] = t[T.shuffle[i]] * T.mdct_scale;            // (Mdct.cs:177-180)
-            out[64 + i] = t[T.shuffle[64 + i]] * T.mdct_scale;
-            __syncthreads();
         }
+        __syncthreads();  // the spectra of every subframe and channel are in place; `scaled` is free again
     }
 
     // ---- EncodeIntensityStereo (:711-764): the energy sums are order-sensitive fp64 -> one thread per (pair, sf)
