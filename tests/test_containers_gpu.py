@@ -322,3 +322,63 @@ def test_convert_8bit_and_empty_batches(vg, oracle):
     assert status == [0] and outs[0].tobytes() == oracle.dsp_write(adpcm, coefs, 32000, 30000).tobytes()
     outs, status = ct.convert_wave_batch([], ct.convert_options(ct.CONTAINER_DSP))
     assert outs == [] and status == []
+
+
+def test_convert_option_variants_match_oracle(vg, oracle):
+    """The writer options of the converter: DSP interleave size / no-trim / loop alignment, ADX version 3, frame size,
+    Fixed and Exponential types (padded streams take the encoder's general path there), encryption type 9, HCA quality and
+    key types 0 / 1 - each against the oracle chain with the same options."""
+    from vgaudio_b200 import containers as ct
+
+    files, meta = [], []
+    for k, (ch, n, loop, rate) in enumerate([(2, 30000, (1001, 29000), 48000), (1, 20000, (777, 19000), 32000), (4, 12000, None, 44100),
+                                             (1, 48000, None, 48000), (2, 5000, (31, 4999), 22050)]):
+        pcm = _pcm(ch, n, first=300 + 3 * k)
+        files.append(oracle.wave_write16(pcm, rate, loop))
+        meta.append((pcm, n, loop, rate))
+
+    # DSP: 14 * 32 samples per interleave, loop points aligned to 14, trimming off
+    outs, status = ct.convert_wave_batch(files, ct.convert_options(ct.CONTAINER_DSP, dsp_samples_per_interleave=14 * 32, dsp_loop_point_alignment=14, no_trim=1))
+    for k, (pcm, n, loop, rate) in enumerate(meta):
+        coefs, adpcm = _encode_gc(oracle, pcm)
+        ctx = _loop_ctx(oracle, adpcm, coefs, n, loop[0]) if loop else None
+        if loop and loop[1] + (-loop[0]) % 14 > n:   # the aligned loop end lies past the audio: the reference throws for mono
+            continue
+        want = oracle.dsp_write(adpcm, coefs, rate, n, loop, ctx, None, None, 14 * 32, 14, False)
+        assert status[k] == 0 and outs[k].tobytes() == want.tobytes(), ("dsp", k)
+
+    # ADX: version 3, 34-byte frames, each encoding type; key code -> encryption type 9
+    okey = oracle.adx_key(key_code=0x123456789A)
+    for typ in (2, 3, 4):
+        opt = ct.convert_options(ct.CONTAINER_ADX, adx_version=3, adx_frame_size=34, adx_type=typ, adx_filter_plus1=2, adx_has_key=1,
+                                 adx_key_seed=okey[0], adx_key_mult=okey[1], adx_key_inc=okey[2], adx_encryption_type=9)
+        outs, status = ct.convert_wave_batch(files, opt)
+        for k, (pcm, n, loop, rate) in enumerate(meta):
+            ch, spf = len(pcm), 64
+            align = (-loop[0]) % (spf * 2 if ch == 1 else spf) if loop else 0
+            enc = [oracle.adx_encode(p, rate, 34, 3, align, typ, 1) for p in pcm]
+            want = oracle.adx_write([e[0] for e in enc], [e[1] for e in enc], rate, n, loop, align, 34, 3, typ, 500, 9, okey)
+            assert status[k] == 0 and outs[k].tobytes() == want.tobytes(), ("adx", typ, k, int(np.flatnonzero(outs[k] != want)[0]))
+
+    # HCA: quality Low, key types 0 and 1
+    for key_type in (0, 1):
+        outs, status = ct.convert_wave_batch(files, ct.convert_options(ct.CONTAINER_HCA, hca_quality=4, hca_key_type=key_type))
+        table = oracle.hca_key_tables(key_type)[1]
+        for k, (pcm, n, loop, rate) in enumerate(meta):
+            info, frames = oracle.hca_encode(pcm, rate, quality=4, loop=loop)
+            want = oracle.hca_write(info, frames, table, key_type)
+            assert status[k] == 0 and outs[k].tobytes() == want.tobytes(), ("hca", key_type, k)
+
+
+def test_convert_all_bad_and_many_channels(vg, oracle):
+    from vgaudio_b200 import containers as ct
+
+    bad = [np.frombuffer(b"not a riff file", dtype=np.uint8), np.zeros(0, dtype=np.uint8), oracle.wave_write16(_pcm(1, 10), 48000, None)[:20].copy()]
+    outs, status = ct.convert_wave_batch(bad, ct.convert_options(ct.CONTAINER_ADX))
+    assert outs == [None, None, None] and all(s != 0 for s in status)
+    pcm = _pcm(40, 3000, first=400)
+    f = oracle.wave_write16(pcm, 16000, (100, 2900))
+    outs, status = ct.convert_wave_batch([f], ct.convert_options(ct.CONTAINER_DSP))
+    coefs, adpcm = _encode_gc(oracle, pcm)
+    want = oracle.dsp_write(adpcm, coefs, 16000, 3000, (100, 2900), _loop_ctx(oracle, adpcm, coefs, 3000, 100))
+    assert status == [0] and outs[0].tobytes() == want.tobytes()
