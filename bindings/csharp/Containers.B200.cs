@@ -54,7 +54,7 @@ namespace VGAudio.Native
         private const string Lib = "vgaudio_b200";
 
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int vgb_wave_parse(byte* file, long length, VgbWaveInfo* info);
-        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int vgb_wave_read_batch(byte** files, VgbWaveInfo* info, int nFiles, short** pcmOut);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int vgb_wave_read_batch(byte** files, long* lengths, VgbWaveInfo* info, int nFiles, short** pcmOut);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern long vgb_dsp_file_size(VgbDspDesc* desc);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         public static extern int vgb_dsp_write_batch(VgbDspDesc* files, int nFiles, byte** adpcm, short* coefs, short* gain, short* startHist,

@@ -384,8 +384,10 @@ int32_t vgb_wave_parse(const uint8_t *file, int64_t length, vgb_wave_info *info_
 
 /* data.Data.InterleavedByteToShort(channelCount) (WaveReader.cs:47, Interleave.cs:188-207) for a batch of parsed files:
  * pcm_out is a flat file-major table of channel rows (sample_count samples each).  8-bit files come out as PCM16 through
- * Pcm8Codec.Decode ((b - 0x80) << 8, Codecs/Pcm8/Pcm8Codec.cs:23), which is what every encoder asks AudioData for. */
-int32_t vgb_wave_read_batch(const uint8_t *const *files, const vgb_wave_info *info, int32_t n_files, int16_t *const *pcm_out);
+ * Pcm8Codec.Decode ((b - 0x80) << 8, Codecs/Pcm8/Pcm8Codec.cs:23), which is what every encoder asks AudioData for.  A
+ * description that does not fit its image (data_offset + payload > lengths[i]) is VGB_E_ARG. */
+int32_t vgb_wave_read_batch(const uint8_t *const *files, const int64_t *lengths, const vgb_wave_info *info, int32_t n_files,
+                            int16_t *const *pcm_out);
 
 /* What DspWriter reads from GcAdpcmFormat and DspConfiguration (Containers/Dsp/DspWriter.cs:17-36, DspConfiguration.cs):
  * sample_count / loop points are the format's; 0 in the three option fields selects the reference's defaults

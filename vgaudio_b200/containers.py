@@ -39,7 +39,8 @@ def wave_read_batch(files: Sequence) -> List[Tuple[N.VgbWaveInfo, List[np.ndarra
     rows = [np.zeros(infos[i].sample_count, dtype=np.int16) for i in range(len(arrs)) for _ in range(infos[i].channel_count)]
     ftab = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     rtab = (C.c_void_p * max(len(rows), 1))(*[r.ctypes.data for r in rows])
-    N.check(N.lib.vgb_wave_read_batch(ftab, infos, len(arrs), rtab))
+    lens = (C.c_int64 * max(len(arrs), 1))(*[a.size for a in arrs])
+    N.check(N.lib.vgb_wave_read_batch(ftab, lens, infos, len(arrs), rtab))
     out, r = [], 0
     for i in range(len(arrs)):
         ch = infos[i].channel_count
