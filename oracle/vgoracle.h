@@ -17,6 +17,11 @@
  *   - CRI ADX ...................... reference has zero tests => "parity unpinned".
  *   - CRI HCA tables ............... pinned bit-exact by CriHcaTableTests.cs literals; encoder output unpinned.
  *
+ *   - Interleave / DeInterleave ... pinned by the reference's golden vectors (Tests/Utilities/InterleaveTests.cs,
+ *                                  DeinterleaveTests.cs), replayed literally in tests/test_interleave_reference_vectors.py
+ *   - seek table / loop context .... pinned by the KATs of GcAdpcmLoopContextTests.cs / GcAdpcmSeekTableTests.cs
+ *   - containers (containers.c) .... build -> parse round trips only (WaveTests.cs, DspTests.cs): file bytes unpinned
+ *
  * All file:line citations are relative to /root/reference/src/VGAudio/.
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fno-fast-math).
  */
