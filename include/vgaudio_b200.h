@@ -171,6 +171,10 @@ int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offs
                                const vgb_gc_params *params /* sample_count must be >= 0 */, int32_t n_channels,
                                int16_t *d_pcm, const int64_t *pcm_offset,
                                void *d_workspace, uint64_t workspace_bytes, void *cuda_stream);
+/* vgb_gcadpcm_decode_dev is asynchronous; a frame header that selects a predictor outside 0..7 (the reference's
+ * IndexOutOfRangeException, GcAdpcmDecoder.cs:31-32) leaves the lowest such channel in the workspace.  This call
+ * synchronises the stream and maps it: VGB_OK or VGB_E_DATA. */
+int32_t vgb_gcadpcm_decode_dev_status(const void *d_workspace, int32_t n_channels, void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Post-encode channel rebuild: what GcAdpcmChannelBuilder.GetSeekTable / GetLoopContext
@@ -478,6 +482,12 @@ typedef struct vgb_convert_options {
  * fills files_out[i] for every file whose status is VGB_OK.  cb receives the number of files finished. */
 int32_t vgb_convert_wave_batch(const uint8_t *const *files, const int64_t *lengths, int32_t n_files, const vgb_convert_options *options,
                                int64_t *out_sizes, uint8_t *const *files_out, int32_t *status_out, vgb_progress_cb cb, void *user);
+/* The decode direction of the batch job: .dsp file images in, 16-bit WAVE file images out - DspReader (Containers/Dsp/DspReader.cs:15-127)
+ * -> GcAdpcmFormat.ToPcm16 (GcAdpcmFormat.cs:42-54, from the header's coefficients and start history) -> WaveWriter
+ * (Containers/Wave/WaveWriter.cs:52-132: RIFF / fmt (extensible above two channels) / smpl when looping / data).  Same two-pass
+ * protocol and per-file status as vgb_convert_wave_batch. */
+int32_t vgb_convert_dsp_to_wave_batch(const uint8_t *const *files, const int64_t *lengths, int32_t n_files, int64_t *out_sizes,
+                                      uint8_t *const *files_out, int32_t *status_out);
 /* Measurement tap: device time of the most recent vgb_convert_wave_batch summed over its (first 32) batches, out[0..3] =
  * WAVE split, encode, loop-context decode, file assembly (ms, CUDA events on the kernel stream); returns the batches timed. */
 int32_t vgb_convert_debug_stage_ms(float *out, int32_t n);

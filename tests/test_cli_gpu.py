@@ -44,3 +44,17 @@ def test_batch_directory_to_dsp_and_hca(tmp_path, oracle):
         rows, n, loop = pcm[name]
         info, frames = oracle.hca_encode(rows, 32000, quality=3, loop=loop)
         assert (out2 / name).with_suffix(".hca").read_bytes() == oracle.hca_write(info, frames, table, 56).tobytes(), name
+
+
+def test_batch_directory_dsp_to_wav(tmp_path, oracle):
+    src = tmp_path / "in"
+    src.mkdir()
+    rows = [synth.channel(260 + c, 20000) for c in range(2)]
+    coefs = np.stack([oracle.calculate_coefficients(p) for p in rows])
+    adpcm = [oracle.encode(p, c) for p, c in zip(rows, coefs)]
+    (src / "x.dsp").write_bytes(oracle.dsp_write(adpcm, coefs, 32000, 20000).tobytes())
+    out = tmp_path / "wav"
+    r = subprocess.run([CLI, "-i", str(src), "-o", str(out), "--out-format", "wav"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "1 files converted, 0 failed" in r.stdout, (r.stdout, r.stderr)
+    want = oracle.wave_write16([oracle.decode(a, c, 20000) for a, c in zip(adpcm, coefs)], 32000, None)
+    assert (out / "x.wav").read_bytes() == want.tobytes()

@@ -382,3 +382,32 @@ def test_convert_all_bad_and_many_channels(vg, oracle):
     coefs, adpcm = _encode_gc(oracle, pcm)
     want = oracle.dsp_write(adpcm, coefs, 16000, 3000, (100, 2900), _loop_ctx(oracle, adpcm, coefs, 3000, 100))
     assert status == [0] and outs[0].tobytes() == want.tobytes()
+
+
+def test_convert_dsp_to_wave_matches_oracle(vg, oracle):
+    """The decode direction: DspReader -> GcAdpcmDecoder (header coefficients, start history) -> WaveWriter, file bytes
+    against the oracle chain; a truncated and a non-DSP image fail alone."""
+    from vgaudio_b200 import containers as ct
+
+    files, want = [], []
+    for k, (ch, n, loop, spi) in enumerate([(1, 14 * 300, None, 0x3800), (1, 50001, (100, 50001), 0x3800), (2, 30000, (1000, 29000), 0x3800),
+                                            (3, 7777, None, 14 * 16), (6, 20011, (17, 20011), 0x3800), (2, 1, None, 0x3800), (8, 9000, None, 14 * 8)]):
+        pcm = _pcm(ch, n, first=500 + 4 * k)
+        coefs, adpcm = _encode_gc(oracle, pcm)
+        ctx = _loop_ctx(oracle, adpcm, coefs, n, loop[0]) if loop else None
+        hist = np.array([[7 * c, -3 * c] for c in range(ch)], dtype=np.int16)
+        f = oracle.dsp_write(adpcm, coefs, 22050 + k, n, loop, ctx, None, hist, spi, 1, False)
+        files.append(f)
+        dec = [oracle.decode(a, c, n, int(h[0]), int(h[1])) for a, c, h in zip(adpcm, coefs, hist)]
+        want.append(oracle.wave_write16(dec, 22050 + k, loop))
+    files.append(files[2][:200].copy())
+    files.append(np.frombuffer(b"\x00\x00\x00\x64" + b"\x00\x00\x00\x05" + b"\x00" * 0x58 + b"\x00" * 64, dtype=np.uint8))   # sample count 100, nibble count 5
+    outs, status = ct.convert_dsp_to_wave_batch(files)
+    for k, w in enumerate(want):
+        assert status[k] == 0 and outs[k].size == w.size, k
+        assert outs[k].tobytes() == w.tobytes(), (k, int(np.flatnonzero(outs[k] != w)[0]))
+    assert status[len(want)] != 0 and status[len(want) + 1] != 0 and outs[len(want)] is None
+    # and the round trip through both directions of the batch job
+    back, st2 = ct.convert_wave_batch([outs[0], outs[2]], ct.convert_options(ct.CONTAINER_DSP))
+    info = ct.dsp_parse(back[1])
+    assert st2 == [0, 0] and info.channel_count == 2 and info.sample_count == 29000 and (info.loop_start, info.loop_end) == (1000, 29000)  # trimmed to the loop end (DspWriter.cs:22)

@@ -151,6 +151,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
          C.c_void_p],
     ),
+    "vgb_gcadpcm_decode_dev_status": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "vgb_adx_encoded_byte_count": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "vgb_adx_encode_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
@@ -197,6 +198,7 @@ SIGNATURES = {
     "vgb_hca_crypt_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32]),
     "vgb_hca_write_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_convert_debug_stage_ms": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "vgb_convert_dsp_to_wave_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgb_convert_wave_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
 }

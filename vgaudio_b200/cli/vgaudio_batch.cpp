@@ -5,7 +5,7 @@
 // WaveReader -> encoder -> writer chain of a chunk of files runs as ONE coalesced call on the device
 // (vgb_convert_wave_batch).  A file that fails is reported and skipped, like the reference's try/catch (:39-43).
 //
-//   vgaudio_batch -i <indir> -o <outdir> --out-format dsp|adx|hca [-r] [--no-trim] [--hcaquality Highest|High|Middle|Low|Lowest]
+//   vgaudio_batch -i <indir> -o <outdir> --out-format dsp|adx|hca|wav [-r]   (wav: .dsp inputs are decoded) [--no-trim] [--hcaquality Highest|High|Middle|Low|Lowest]
 //                 [--bitrate N] [--limit-bitrate] [--keycode N] [--keystring S] [--adxtype Linear|Fixed|Exp|ExpEnc...]
 //                 [--framesize N] [--version 3|4] [--chunk-mb N]
 #include <sys/stat.h>
@@ -37,7 +37,7 @@ static bool read_file(const fs::path &p, std::vector<uint8_t> &out)
 
 static int usage()
 {
-    std::fprintf(stderr, "usage: vgaudio_batch -i <indir> -o <outdir> --out-format dsp|adx|hca [-r] [--no-trim] [--hcaquality Q] [--bitrate N]\n"
+    std::fprintf(stderr, "usage: vgaudio_batch -i <indir> -o <outdir> --out-format dsp|adx|hca|wav [-r] [--no-trim] [--hcaquality Q] [--bitrate N]\n"
                          "                     [--limit-bitrate] [--keycode N] [--keystring S] [--adxtype linear|fixed|exp] [--framesize N] [--version 3|4]\n"
                          "                     [--chunk-mb N]\n");
     return 2;
@@ -77,10 +77,11 @@ int main(int argc, char **argv)
         } else return usage();
     }
     if (in_dir.empty() || out_dir.empty()) return usage();
+    const bool to_wave = fmt == "wav";  // the decode direction: .dsp files in, 16-bit WAVE files out
     if (fmt == "dsp") opt.out_type = VGB_CONTAINER_DSP;
     else if (fmt == "adx") opt.out_type = VGB_CONTAINER_ADX;
     else if (fmt == "hca") opt.out_type = VGB_CONTAINER_HCA;
-    else return usage();
+    else if (!to_wave) return usage();
     if (opt.out_type == VGB_CONTAINER_ADX && (have_code || !key_string.empty())) {
         vgb_adx_key k{};
         const int32_t s = !key_string.empty() ? vgb_adx_key_from_string(key_string.c_str(), &k) : vgb_adx_key_from_code(key_code, &k);
@@ -97,7 +98,7 @@ int main(int argc, char **argv)
         if (!e.is_regular_file()) return;
         std::string ext = e.path().extension().string();
         std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
-        if (ext == ".wav" || ext == ".wave") files.push_back(e.path());
+        if (to_wave ? ext == ".dsp" : (ext == ".wav" || ext == ".wave")) files.push_back(e.path());
     };
     if (recurse) for (auto &e : fs::recursive_directory_iterator(in_dir, ec)) take(e);
     else for (auto &e : fs::directory_iterator(in_dir, ec)) take(e);
@@ -123,14 +124,18 @@ int main(int argc, char **argv)
         std::vector<int64_t> len(n), out_size(n);
         std::vector<int32_t> status(n);
         for (int k = 0; k < n; k++) { ptr[k] = in[k].data(); len[k] = (int64_t)in[k].size(); bytes_in += in[k].size(); }
-        if (vgb_convert_wave_batch(ptr.data(), len.data(), n, &opt, out_size.data(), nullptr, status.data(), nullptr, nullptr) != VGB_OK) {
+        auto convert = [&](uint8_t *const *outs) {
+            return to_wave ? vgb_convert_dsp_to_wave_batch(ptr.data(), len.data(), n, out_size.data(), outs, status.data())
+                           : vgb_convert_wave_batch(ptr.data(), len.data(), n, &opt, out_size.data(), outs, status.data(), nullptr, nullptr);
+        };
+        if (convert(nullptr) != VGB_OK) {
             std::fprintf(stderr, "%s\n", vgb_last_error());
             return 1;
         }
         std::vector<std::vector<uint8_t>> out(n);
         std::vector<uint8_t *> optr(n, nullptr);
         for (int k = 0; k < n; k++) if (status[k] == VGB_OK) { out[k].resize((size_t)out_size[k]); optr[k] = out[k].data(); }
-        if (vgb_convert_wave_batch(ptr.data(), len.data(), n, &opt, out_size.data(), optr.data(), status.data(), nullptr, nullptr) != VGB_OK) {
+        if (convert(optr.data()) != VGB_OK) {
             std::fprintf(stderr, "%s\n", vgb_last_error());
             return 1;
         }

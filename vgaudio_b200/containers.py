@@ -251,3 +251,18 @@ def convert_wave_batch(files: Sequence, options: N.VgbConvertOptions, progress=N
     cb = N.PROGRESS_CB(lambda user, delta: progress(delta)) if progress else None
     N.check(N.lib.vgb_convert_wave_batch(ftab, lens, n, C.byref(options), sizes, otab, status, cb, None))
     return outs, [int(status[i]) for i in range(n)]
+
+
+def convert_dsp_to_wave_batch(files: Sequence) -> Tuple[List[Optional[np.ndarray]], List[int]]:
+    """The decode direction of the batch job: .dsp images in, 16-bit WAVE images out (DspReader -> ToPcm16 -> WaveWriter)."""
+    arrs = [_bytes_arr(f) for f in files]
+    n = len(arrs)
+    ftab = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * max(n, 1))(*[a.size for a in arrs])
+    sizes = (C.c_int64 * max(n, 1))()
+    status = (C.c_int32 * max(n, 1))()
+    N.check(N.lib.vgb_convert_dsp_to_wave_batch(ftab, lens, n, sizes, None, status))
+    outs = [np.zeros(sizes[i], dtype=np.uint8) if status[i] == 0 else None for i in range(n)]
+    otab = (C.c_void_p * max(n, 1))(*[o.ctypes.data if o is not None else None for o in outs])
+    N.check(N.lib.vgb_convert_dsp_to_wave_batch(ftab, lens, n, sizes, otab, status))
+    return outs, [int(status[i]) for i in range(n)]

@@ -1351,6 +1351,22 @@ int32_t vgb_gcadpcm_decode_dev(const uint8_t *d_adpcm, const int64_t *adpcm_offs
     return run_gc_decode(d_adpcm, lay, d_coefs, d_pcm, d_workspace, w, static_cast<cudaStream_t>(cuda_stream));
 }
 
+/* The decoder's status word of the most recent vgb_gcadpcm_decode_dev on this workspace (see the header). */
+int32_t vgb_gcadpcm_decode_dev_status(const void *d_workspace, int32_t n_channels, void *cuda_stream)
+{
+    if (!d_workspace || n_channels < 0) return fail(VGB_E_ARG, "bad arguments");
+    if (n_channels == 0) return VGB_OK;
+    const GcWorkspace w = carve(32, n_channels);
+    const GcChannelTable tab = table_view(const_cast<void *>(d_workspace), w, n_channels);
+    int32_t bad_channel = INT_MAX;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CUDA_TRY(cudaMemcpyAsync(&bad_channel, tab.status, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad_channel >= 0 && bad_channel < n_channels)  // IndexOutOfRangeException at GcAdpcmDecoder.cs:31-32
+        return fail(VGB_E_DATA, "channel %d: a frame header selects a predictor outside 0..7", bad_channel);
+    return VGB_OK;
+}
+
 int32_t vgb_set_kernel_timing(int32_t enabled)
 {
     std::lock_guard<std::mutex> lock(g_ctx.mu);

@@ -176,6 +176,46 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const uint8_t *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// WAVE writer, 16-bit codec (WaveWriter.WriteDataChunk -> ShortToInterleavedByte, Interleave.cs:169-186): the inverse of
+// wave_split_kernel.  Tile 0 of a file also copies the host-built RIFF header.  The data chunk starts at a multiple of four
+// bytes (every chunk size the writer emits is one), so the interleaved samples leave as 32-bit words.
+// ---------------------------------------------------------------------------------------------------------------
+struct WaveJoinItem {
+    int64_t pcm_off;         // samples into the PCM slab: row of channel 0
+    int64_t pcm_stride;      // samples between channel rows
+    int64_t out_off;         // bytes into the output slab (multiple of 16)
+    int64_t hdr_off;         // bytes into the header blob
+    int32_t header_size, channels, samples, tile_samples;
+    int32_t tile_first;
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(256) wave_join_kernel(const int16_t *__restrict__ pcm, const WaveJoinItem *__restrict__ items, int n_items,
+                                                         const uint8_t *__restrict__ hdr_blob, uint8_t *__restrict__ out)
+{
+    __shared__ __align__(16) int16_t tile[kSplitSmemSamples];
+    const int it = find_item(items, n_items, (int)blockIdx.x);
+    const WaveJoinItem w = items[it];
+    const int t = (int)blockIdx.x - w.tile_first;
+    uint8_t *dst = out + w.out_off;
+    if (t == 0)
+        for (int k = threadIdx.x; k < w.header_size; k += blockDim.x) dst[k] = hdr_blob[w.hdr_off + k];
+    const int s0 = t * w.tile_samples;
+    const int ns = min(w.tile_samples, w.samples - s0);
+    if (ns <= 0) return;
+    const int ch = w.channels;
+    for (int k = threadIdx.x; k < ns * ch; k += blockDim.x) {  // rows in (coalesced per row), interleaved order in shared memory
+        const int o = k / ns, i = k - o * ns;
+        tile[i * ch + o] = pcm[w.pcm_off + (int64_t)o * w.pcm_stride + s0 + i];
+    }
+    __syncthreads();
+    uint8_t *data = dst + w.header_size + (int64_t)s0 * ch * 2;   // 4-byte aligned: s0 * ch is even (tile_samples is a multiple of 8)
+    const int n_el = ns * ch, n_words = n_el >> 1;
+    for (int k = threadIdx.x; k < n_words; k += blockDim.x) reinterpret_cast<uint32_t *>(data)[k] = reinterpret_cast<const uint32_t *>(tile)[k];
+    if ((n_el & 1) && threadIdx.x == 0) reinterpret_cast<int16_t *>(data)[n_el - 1] = tile[n_el - 1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // DSP writer.  Tile 0 of a file writes the channel headers (big-endian halfwords), the others 16 KB of the data
 // region each: byte q of the region belongs to block b, channel i, offset k (Interleave.cs:43-79 semantics: shorter
 // last block on either side, zero fill) and comes from channel i's byte bpi*b + k.
@@ -620,6 +660,37 @@ void adx_build_header(const vgb_adx_desc &d, const AdxGeom &g, const int16_t *hi
     h.resize((size_t)g.audio_offset);
 }
 
+const uint8_t kPcmGuid[16] = {0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xAA, 0x00, 0x38, 0x9B, 0x71};
+
+// ---- WAVE header, 16-bit codec (WaveWriter.cs:24-153): everything in front of the samples ----
+int wave_channel_mask(int n)
+{
+    switch (n) { case 4: return 0x0033; case 5: return 0x0133; case 6: return 0x0633; case 7: return 0x01f3; case 8: return 0x06f3; default: return (int)((1u << n) - 1u); }
+}
+void le16(uint8_t *p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+void le32(uint8_t *p, int32_t v) { le16(p, (int)((uint32_t)v & 0xffff)); le16(p + 2, (int)((uint32_t)v >> 16)); }
+void wave_build_header(int channels, int samples, int sample_rate, bool looping, int loop_start, int loop_end, std::vector<uint8_t> &h)
+{
+    const int fmt = channels > 2 ? 40 : 16;
+    const int header = 12 + 8 + fmt + (looping ? 8 + 0x3c : 0) + 8;
+    const int64_t data_bytes = (int64_t)channels * samples * 2;
+    h.assign((size_t)header, 0);
+    uint8_t *p = h.data();
+    std::memcpy(p, "RIFF", 4); le32(p + 4, (int32_t)(header - 8 + data_bytes)); std::memcpy(p + 8, "WAVE", 4); p += 12;
+    std::memcpy(p, "fmt ", 4); le32(p + 4, fmt);
+    le16(p + 8, channels > 2 ? 0xFFFE : 1); le16(p + 10, channels); le32(p + 12, sample_rate);
+    le32(p + 16, (int32_t)((uint32_t)sample_rate * 2u * (uint32_t)channels)); le16(p + 20, 2 * channels); le16(p + 22, 16);
+    if (channels > 2) { le16(p + 24, 22); le16(p + 26, 16); le32(p + 28, wave_channel_mask(channels)); std::memcpy(p + 32, kPcmGuid, 16); }
+    p += 8 + fmt;
+    if (looping) {
+        std::memcpy(p, "smpl", 4); le32(p + 4, 0x3c);
+        le32(p + 8 + 28, 1);
+        le32(p + 8 + 36 + 8, loop_start); le32(p + 8 + 36 + 12, loop_end);
+        p += 8 + 0x3c;
+    }
+    std::memcpy(p, "data", 4); le32(p + 4, (int32_t)data_bytes);
+}
+
 // ---- HCA header (HcaWriter.cs:56-170) ----
 uint16_t crc16_host(const uint8_t *data, size_t n)  // Crc16.Compute (Utilities/Crc16.cs:13-19), polynomial 0x8005
 {
@@ -701,8 +772,6 @@ int32_t hca_key_tables(int key_type, uint64_t key_code, uint8_t *dec, uint8_t *e
     for (int i = 0; i < 256; i++) enc[dec[i]] = (uint8_t)i;
     return VGB_OK;
 }
-
-const uint8_t kPcmGuid[16] = {0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xAA, 0x00, 0x38, 0x9B, 0x71};
 
 int wave_tile_samples(int channels)
 {
