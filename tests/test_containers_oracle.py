@@ -274,3 +274,53 @@ def test_parsers_agree_on_mutated_and_truncated_files(oracle, vg):
             for name in ("sample_count", "nibble_count", "sample_rate", "looping", "channel_count", "frames_per_interleave", "loop_start", "loop_end"):
                 assert getattr(pinfo, name) == getattr(info, name), (case, name)
     assert n_ok > 100
+
+
+def test_converter_sizing_pass_is_host_only_and_matches_oracle_sizes(oracle, vg):
+    """vgb_convert_wave_batch / vgb_convert_dsp_to_wave_batch with files_out == NULL: parse, validate and size every output on
+    the host (no device needed); sizes equal the oracle writers' file sizes, a bad file gets a status and size 0."""
+    from vgaudio_b200 import _native as N
+    from vgaudio_b200 import containers as ct
+
+    specs = [(1, 48000, None, 48000), (2, 30001, (5, 30000), 44100), (3, 777, None, 22050), (1, 14 * 5000 + 3, (1000, 60000), 32000), (6, 100, None, 8000)]
+    files, meta = [], []
+    for ch, n, loop, rate in specs:
+        pcm = _sine_channels(ch, n, rate)
+        files.append(oracle.wave_write16(pcm, rate, loop))
+        meta.append((pcm, n, loop, rate))
+    files.append(np.frombuffer(b"RIFF\x10\x00\x00\x00WAVEjunkjunkjunk", dtype=np.uint8))
+    n = len(files)
+    ftab = (C.c_void_p * n)(*[f.ctypes.data for f in files])
+    lens = (C.c_int64 * n)(*[f.size for f in files])
+    for out_type in (ct.CONTAINER_DSP, ct.CONTAINER_ADX, ct.CONTAINER_HCA):
+        sizes, status = (C.c_int64 * n)(), (C.c_int32 * n)()
+        opt = ct.convert_options(out_type, hca_quality=2)
+        assert vg.lib.vgb_convert_wave_batch(ftab, lens, n, C.byref(opt), sizes, None, status, None, None) == 0
+        assert status[n - 1] != 0 and sizes[n - 1] == 0
+        for k, (pcm, ns, loop, rate) in enumerate(meta):
+            ch = len(pcm)
+            assert status[k] == 0, (out_type, k, vg.lib.vgb_last_error())
+            if out_type == ct.CONTAINER_DSP:
+                zeros = [np.zeros(oracle.sample_count_to_byte_count(ns), np.uint8) for _ in range(ch)]
+                want = oracle.dsp_write(zeros, np.zeros((ch, 16), np.int16), rate, ns, loop, np.zeros((ch, 3), np.int16) if loop else None).size
+            elif out_type == ct.CONTAINER_ADX:
+                align = (-loop[0]) % (64 if ch == 1 else 32) if loop else 0
+                audio = [np.zeros(oracle.lib().vgo_adx_encoded_byte_count(ns, align, 18), np.uint8) for _ in range(ch)]
+                want = oracle.adx_write(audio, [0] * ch, rate, ns, loop, align).size
+            else:
+                info = oracle.hca_init(oracle.hca_params(pcm, rate, 2, 0, False, loop))
+                want = info.header_size + info.frame_size * info.frame_count
+            assert sizes[k] == want, (out_type, k)
+    # the decode direction: .dsp images -> WAVE sizes
+    dsps = []
+    for pcm, ns, loop, rate in meta[:3]:
+        ch = len(pcm)
+        zeros = [np.zeros(oracle.sample_count_to_byte_count(ns), np.uint8) for _ in range(ch)]
+        dsps.append(oracle.dsp_write(zeros, np.zeros((ch, 16), np.int16), rate, ns, loop, np.zeros((ch, 3), np.int16) if loop else None, trim_file=False))
+    m = len(dsps)
+    dtab = (C.c_void_p * m)(*[f.ctypes.data for f in dsps])
+    dl = (C.c_int64 * m)(*[f.size for f in dsps])
+    sizes, status = (C.c_int64 * m)(), (C.c_int32 * m)()
+    assert vg.lib.vgb_convert_dsp_to_wave_batch(dtab, dl, m, sizes, None, status) == 0
+    for k, (pcm, ns, loop, rate) in enumerate(meta[:3]):
+        assert status[k] == 0 and sizes[k] == oracle.wave_write16(pcm, rate, loop).size, k
