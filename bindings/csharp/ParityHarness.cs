@@ -18,6 +18,7 @@ using System.Linq;
 using VGAudio.Codecs.CriAdx;
 using VGAudio.Codecs.CriHca;
 using VGAudio.Codecs.GcAdpcm;
+using VGAudio.Formats;
 using VGAudio.Formats.CriHca;
 using VGAudio.Formats.Pcm16;
 using VGAudio.Native;
@@ -113,6 +114,27 @@ internal static unsafe class ParityHarness
         return slab;
     }
 
+    // WaveReader -> GetFormat<T> (encode) -> writer, as Convert.ConvertFile runs it (src/VGAudio.Cli/Convert.cs:18-36), with the
+    // writer configuration the params column names (CreateConfiguration.cs:118-150: keystring -> ADX type 8, keycode -> HCA key)
+    private static byte[] ManagedConvert(byte[] wave, string kind, Dictionary<string, string> p)
+    {
+        AudioData audio = new VGAudio.Containers.Wave.WaveReader().Read(wave);
+        switch (kind)
+        {
+            case "wave_to_dsp":
+                return new VGAudio.Containers.Dsp.DspWriter().GetFile(audio);
+            case "wave_to_adx":
+                var adx = new VGAudio.Containers.Adx.AdxConfiguration();
+                if (p.TryGetValue("keystring", out string ks)) { adx.EncryptionKey = new CriAdxKey(ks); adx.EncryptionType = 8; }
+                return new VGAudio.Containers.Adx.AdxWriter().GetFile(audio, adx);
+            default:
+                var hca = new VGAudio.Containers.Hca.HcaConfiguration();
+                if (p.TryGetValue("quality", out string q)) hca.Quality = (CriHcaQuality)int.Parse(q);
+                if (p.TryGetValue("keycode", out string kc)) hca.EncryptionKey = new CriHcaKey(ulong.Parse(kc));
+                return new VGAudio.Containers.Hca.HcaWriter().GetFile(audio, hca);
+        }
+    }
+
     // ---- vectors mode --------------------------------------------------------------------------------------------------
     private static int Vectors(string dir)
     {
@@ -122,7 +144,7 @@ internal static unsafe class ParityHarness
             if (line.StartsWith("#") || line.Trim().Length == 0) continue;
             string[] f = line.Split('\t');
             var p = Params(f[2]);
-            short[][] pcm = f[3].Split(',').Select(x => ReadPcm(Path.Combine(dir, x))).ToArray();
+            short[][] pcm = f[0].StartsWith("wave_to_") ? null : f[3].Split(',').Select(x => ReadPcm(Path.Combine(dir, x))).ToArray();
             byte[] ours = File.ReadAllBytes(Path.Combine(dir, f[4]));
             byte[] managed;
             switch (f[0])
@@ -143,6 +165,11 @@ internal static unsafe class ParityHarness
                     break;
                 case "criadx": managed = ManagedAdx(pcm[0], p); break;
                 case "crihca": managed = ManagedHca(pcm, p); break;
+                case "wave_to_dsp":   // input = a WAVE file; the finished file against WaveReader -> DspWriter.GetFile
+                case "wave_to_adx":
+                case "wave_to_hca":
+                    managed = ManagedConvert(File.ReadAllBytes(Path.Combine(dir, f[3])), f[0], p);
+                    break;
                 default: Console.WriteLine($"unknown codec {f[0]}"); bad++; continue;
             }
             n++;

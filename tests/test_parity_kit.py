@@ -19,15 +19,15 @@ def _dump(tmp, *flags):
 
 def test_dump_vectors_manifest_is_complete(tmp_path):
     rows = _dump(tmp_path, "--oracle")
-    assert {r[0] for r in rows} == {"gcadpcm", "gcadpcm_decode", "criadx", "crihca"}
-    assert len(rows) >= 60
+    assert {r[0] for r in rows} == {"gcadpcm", "gcadpcm_decode", "criadx", "crihca", "wave_to_dsp", "wave_to_adx", "wave_to_hca"}
+    assert len(rows) >= 75
     for codec, name, params, inputs, output in rows:
         for f in inputs.split(",") + [output]:
             assert os.path.getsize(os.path.join(tmp_path, f)) >= 0, (codec, name, f)
-        assert all("=" in kv for kv in params.split(","))
+        assert all("=" in kv for kv in params.split(",") if kv)
     # the C# side exists and names every codec of the manifest
     harness = open(os.path.join(ROOT, "bindings", "csharp", "ParityHarness.cs")).read()
-    for codec in ("gcadpcm", "gcadpcm_decode", "criadx", "crihca"):
+    for codec in ("gcadpcm", "gcadpcm_decode", "criadx", "crihca", "wave_to_dsp", "wave_to_adx", "wave_to_hca"):
         assert f'"{codec}"' in harness
     tool = open(os.path.join(ROOT, "bindings", "csharp", "DspToolB200.cs")).read()
     for member in ("EncodeChannel", "DspCorrelateCoefs", "DspEncodeFrame", "DecodeChannel", "DecodeAdpcm"):  # IDspTool.cs:5-12
